@@ -1,0 +1,14 @@
+// Host-side interface of the tcgen05 convolution (nn_tc.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+namespace azb {
+// activations: NHWC bf16 [max_boards][8][8][channels], channels in {64, 128}
+int tc_make_act_map(CUtensorMap* map, const void* base, int channels, int max_boards);
+// weights: bf16 [9 taps][128 out][cin], BatchNorm already folded
+int tc_make_weight_map(CUtensorMap* map, const void* base, int cin);
+// out = act( conv3x3(in) + bias (+ residual) ); the board count is read from n_boards_dev when non-null
+int tc_conv3x3_launch(cudaStream_t stream, const CUtensorMap* in_map, const CUtensorMap* w_map, int cin, const float* bias,
+                      const void* residual, void* out, const int* n_boards_dev, int n_boards_static, int relu, int grid);
+}  // namespace azb
