@@ -1,17 +1,303 @@
-"""alphazero-chess_b200: B200-native batched self-play engine (host-side Python mirror over the C ABI)."""
+"""alphazero-chess_b200: B200-native batched self-play engine.
+
+Host-side Python mirror of the reference's interface for the self-play hot path (chess.rs / tree.rs / agent.rs /
+training.rs of AlexandreGac/alphazero-chess) over the C ABI in include/az_b200.h.  All compute happens in the
+sm_100a CUDA library next to this file; there is no CPU fallback: a missing library or a missing GPU is an error.
+"""
 import ctypes
 import os
+
+import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libaz_b200.so")
 _lib = None
 
+ACTION_SPACE = 4096
+MAX_MOVES = 256
+NUM_PLANES = 19
+NUM_WEIGHT_ARRAYS = 144
+MOVE_NONE = 0xFFFF
+ONGOING, DRAW, WHITE_WINS, BLACK_WINS, ILLEGAL = 0, 1, 2, 3, -1
+
+POSITION_DTYPE = np.dtype(
+    [("roles", "<u8", 6), ("colors", "<u8", 2), ("turn", "u1"), ("castling", "u1"), ("ep_square", "i1"), ("reserved", "u1"),
+     ("halfmoves", "<u2"), ("fullmoves", "<u2")]
+)
+assert POSITION_DTYPE.itemsize == 72
+
+SAMPLE_DTYPE = np.dtype(
+    [("position", POSITION_DTYPE), ("final_value", "<f4"), ("search_depth", "<i4"), ("game_id", "<u8"), ("ply", "<u4"),
+     ("action", "<u2"), ("n_visits", "<u2"), ("index", "<u2", MAX_MOVES), ("count", "<u2", MAX_MOVES)]
+)
+assert SAMPLE_DTYPE.itemsize == 1120
+
+
+class Config(ctypes.Structure):
+    """az_config: parameters.rs as runtime configuration."""
+
+    _fields_ = [
+        ("device", ctypes.c_int32), ("max_games", ctypes.c_int32), ("max_batch", ctypes.c_int32), ("num_simulations", ctypes.c_int32),
+        ("c_puct", ctypes.c_float), ("dirichlet_alpha", ctypes.c_float), ("dirichlet_epsilon", ctypes.c_float),
+        ("temperature_annealing", ctypes.c_uint32), ("num_halfmoves", ctypes.c_uint32), ("num_fullmoves", ctypes.c_uint32),
+        ("repetitions", ctypes.c_uint32), ("seed", ctypes.c_uint64), ("precision", ctypes.c_int32), ("cache_log2", ctypes.c_int32),
+        ("edge_capacity_per_node", ctypes.c_int32), ("reserved", ctypes.c_int32),
+    ]
+
+
+class SelfplayStats(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint64) for n in ("simulations", "positions", "evaluations", "cache_hits", "terminal_leaves",
+                                               "games_finished", "sum_leaf_depth", "sum_edges", "waves", "pending_samples")]
+
+
+class EngineError(RuntimeError):
+    pass
+
 
 def lib():
-    """Loads the CUDA extension; there is no CPU fallback, a missing library is an error."""
+    """Loads the CUDA extension; a missing library is an error (no fallback path exists)."""
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(f"{LIB_PATH} is missing: run __graft_entry__.build() (nvcc, sm_100a) first")
-        _lib = ctypes.CDLL(LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        L.az_last_error.restype = ctypes.c_char_p
+        L.az_version.restype = ctypes.c_char_p
+        L.az_weight_name.restype = ctypes.c_char_p
+        L.az_weight_size.restype = ctypes.c_int64
+        L.az_engine_destroy.restype = None
+        L.az_config_default.restype = None
+        L.az_position_start.restype = None
+        _lib = L
     return _lib
+
+
+def _ptr(a):
+    return ctypes.c_void_p(a.ctypes.data) if a is not None else ctypes.c_void_p(0)
+
+
+def default_config(**overrides):
+    c = Config()
+    lib().az_config_default(ctypes.byref(c))
+    for k, v in overrides.items():
+        setattr(c, k, v)
+    return c
+
+
+def start_position():
+    p = np.zeros(1, POSITION_DTYPE)
+    lib().az_position_start(_ptr(p))
+    return p[0]
+
+
+def position_from_fen(fen):
+    p = np.zeros(1, POSITION_DTYPE)
+    rc = lib().az_position_from_fen(fen.encode(), _ptr(p))
+    if rc:
+        raise ValueError(f"bad FEN: {fen}")
+    return p[0]
+
+
+def weight_names():
+    L = lib()
+    return [L.az_weight_name(i).decode() for i in range(NUM_WEIGHT_ARRAYS)]
+
+
+def weight_sizes():
+    L = lib()
+    return [int(L.az_weight_size(i)) for i in range(NUM_WEIGHT_ARRAYS)]
+
+
+_FAN_IN = {"input_conv": 19 * 9, "conv1": 128 * 9, "conv2": 128 * 9, "policy_conv_1": 128, "policy_conv_2": 32, "value_conv": 128,
+           "value_linear_1": 512, "value_linear_2": 64}
+
+
+def random_weights(seed=42, randomize_bn=False, sizes=None, names=None):
+    """Random-init 10x128 network in burn's layout (AlphaZero::new, agent.rs:69-110): conv/linear U(-k, k) with
+    k = 1/sqrt(fan_in); BatchNorm gamma 1, beta 0, mean 0, var 1 (optionally randomised for tests)."""
+    names = names or weight_names()
+    sizes = sizes or weight_sizes()
+    rng = np.random.default_rng(seed)
+    out = []
+    for name, size in zip(names, sizes):
+        parts = name.split(".")
+        layer, field = parts[-2], parts[-1]
+        if field in ("weight", "bias"):
+            k = 1.0 / np.sqrt(_FAN_IN[layer])
+            a = rng.uniform(-k, k, size).astype(np.float32)
+        elif field == "gamma":
+            a = rng.uniform(0.5, 1.5, size).astype(np.float32) if randomize_bn else np.ones(size, np.float32)
+        elif field == "running_var":
+            a = rng.uniform(0.5, 1.5, size).astype(np.float32) if randomize_bn else np.ones(size, np.float32)
+        else:
+            a = rng.uniform(-0.2, 0.2, size).astype(np.float32) if randomize_bn else np.zeros(size, np.float32)
+        out.append(a)
+    return out
+
+
+class Engine:
+    """One engine per GPU (az_engine).  Methods mirror the reference items named in include/az_b200.h."""
+
+    def __init__(self, config=None, **overrides):
+        self._L = lib()
+        self.config = config if config is not None else default_config(**overrides)
+        self._h = ctypes.c_void_p(0)
+        rc = self._L.az_engine_create(ctypes.byref(self.config), ctypes.byref(self._h))
+        if rc:
+            msg = self._L.az_last_error(self._h).decode() if self._h else "az_engine_create failed"
+            if self._h:
+                self._L.az_engine_destroy(self._h)
+                self._h = ctypes.c_void_p(0)
+            raise EngineError(f"az_engine_create: {rc}: {msg}")
+
+    def close(self):
+        if self._h:
+            self._L.az_engine_destroy(self._h)
+            self._h = ctypes.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc, what):
+        if rc:
+            raise EngineError(f"{what}: {rc}: {self._L.az_last_error(self._h).decode()}")
+
+    @staticmethod
+    def _positions(pos):
+        a = np.ascontiguousarray(np.atleast_1d(pos), dtype=POSITION_DTYPE)
+        return a
+
+    # ---- agent.rs ---------------------------------------------------------------------------------------------
+    def load_weights(self, arrays):
+        """load_model (main.rs:109-116): 144 f32 arrays in az_weight_name order."""
+        arrs = [np.ascontiguousarray(a, np.float32).ravel() for a in arrays]
+        sizes = weight_sizes()
+        if len(arrs) != NUM_WEIGHT_ARRAYS or any(a.size != s for a, s in zip(arrs, sizes)):
+            raise ValueError("expected 144 arrays with the sizes of az_weight_size")
+        ptrs = (ctypes.c_void_p * NUM_WEIGHT_ARRAYS)(*[a.ctypes.data for a in arrs])
+        self._check(self._L.az_load_weights(self._h, ptrs, NUM_WEIGHT_ARRAYS), "az_load_weights")
+
+    def load_weights_dev(self, device_ptrs):
+        ptrs = (ctypes.c_void_p * NUM_WEIGHT_ARRAYS)(*device_ptrs)
+        self._check(self._L.az_load_weights_dev(self._h, ptrs, NUM_WEIGHT_ARRAYS), "az_load_weights_dev")
+
+    def forward_planes(self, planes):
+        """AlphaZero::forward (agent.rs:112-144): [n,19,8,8] -> (policy [n,4096], value [n])."""
+        x = np.ascontiguousarray(planes, np.float32).reshape(-1, NUM_PLANES, 8, 8)
+        n = x.shape[0]
+        policy = np.empty((n, ACTION_SPACE), np.float32)
+        value = np.empty(n, np.float32)
+        self._check(self._L.az_forward_planes(self._h, n, _ptr(x), _ptr(policy), _ptr(value)), "az_forward_planes")
+        return policy, value
+
+    def forward(self, pos):
+        p = self._positions(pos)
+        n = p.shape[0]
+        policy = np.empty((n, ACTION_SPACE), np.float32)
+        value = np.empty(n, np.float32)
+        self._check(self._L.az_forward(self._h, n, _ptr(p), _ptr(policy), _ptr(value)), "az_forward")
+        return policy, value
+
+    # ---- chess.rs ---------------------------------------------------------------------------------------------
+    def movegen(self, pos):
+        """Chess::legal_moves + move_to_index: (moves [n,256], indices [n,256], counts [n])."""
+        p = self._positions(pos)
+        n = p.shape[0]
+        moves = np.empty((n, MAX_MOVES), np.uint16)
+        index = np.empty((n, MAX_MOVES), np.uint16)
+        count = np.empty(n, np.int32)
+        self._check(self._L.az_movegen(self._h, n, _ptr(p), _ptr(moves), _ptr(index), _ptr(count)), "az_movegen")
+        return moves, index, count
+
+    def perft(self, pos, depth):
+        p = self._positions(pos)
+        n = p.shape[0]
+        nodes = np.zeros(n, np.uint64)
+        self._check(self._L.az_perft(self._h, n, _ptr(p), int(depth), _ptr(nodes)), "az_perft")
+        return nodes
+
+    def play_move(self, pos, action_index, history=None, hist_offsets=None):
+        """play_move (chess.rs:36-63) through a policy index; returns (new positions, GameResult codes)."""
+        p = self._positions(pos).copy()
+        n = p.shape[0]
+        act = np.ascontiguousarray(np.atleast_1d(action_index), np.uint16)
+        res = np.empty(n, np.int32)
+        h = self._positions(history) if history is not None else None
+        ho = np.ascontiguousarray(hist_offsets, np.uint32) if hist_offsets is not None else None
+        self._check(self._L.az_play_move(self._h, n, _ptr(p), _ptr(h), _ptr(ho), _ptr(act), _ptr(res)), "az_play_move")
+        return p, res
+
+    def move_to_index(self, pos, moves):
+        p = self._positions(pos)
+        m = np.ascontiguousarray(np.atleast_1d(moves), np.uint16)
+        out = np.empty(p.shape[0], np.uint16)
+        self._check(self._L.az_move_to_index(self._h, p.shape[0], _ptr(p), _ptr(m), _ptr(out)), "az_move_to_index")
+        return out
+
+    def index_to_move(self, pos, index):
+        p = self._positions(pos)
+        i = np.ascontiguousarray(np.atleast_1d(index), np.uint16)
+        out = np.empty(p.shape[0], np.uint16)
+        self._check(self._L.az_index_to_move(self._h, p.shape[0], _ptr(p), _ptr(i), _ptr(out)), "az_index_to_move")
+        return out
+
+    def encode(self, pos):
+        """to_tensor (chess.rs:191-245): [n,19,8,8] f32."""
+        p = self._positions(pos)
+        out = np.empty((p.shape[0], NUM_PLANES, 8, 8), np.float32)
+        self._check(self._L.az_encode(self._h, p.shape[0], _ptr(p), _ptr(out)), "az_encode")
+        return out
+
+    # ---- tree.rs ----------------------------------------------------------------------------------------------
+    def set_evaluator_stub(self, kind, seed=0):
+        self._check(self._L.az_set_evaluator_stub(self._h, int(kind), ctypes.c_uint64(seed)), "az_set_evaluator_stub")
+
+    def search(self, roots, num_simulations=None, history=None, hist_offsets=None, noise_game_ids=None, noise_plies=None,
+               want_scores=False):
+        """MCTree::init + monte_carlo_tree_search for a batch of roots: (visits [n,4096], scores or None, depth [n])."""
+        p = self._positions(roots)
+        n = p.shape[0]
+        sims = int(num_simulations or self.config.num_simulations)
+        visits = np.empty((n, ACTION_SPACE), np.float32)
+        scores = np.empty((n, ACTION_SPACE), np.float32) if want_scores else None
+        depth = np.empty(n, np.int32)
+        h = self._positions(history) if history is not None else None
+        ho = np.ascontiguousarray(hist_offsets, np.uint32) if hist_offsets is not None else None
+        ids = np.ascontiguousarray(noise_game_ids, np.uint64) if noise_game_ids is not None else None
+        pl = np.ascontiguousarray(noise_plies, np.uint32) if noise_plies is not None else None
+        self._check(self._L.az_search(self._h, n, _ptr(p), _ptr(h), _ptr(ho), sims, _ptr(ids), _ptr(pl), _ptr(visits), _ptr(scores),
+                                      _ptr(depth)), "az_search")
+        return visits, scores, depth
+
+    # ---- training.rs ------------------------------------------------------------------------------------------
+    def selfplay_begin(self, n_games, first_game_id=0):
+        self._check(self._L.az_selfplay_begin(self._h, int(n_games), ctypes.c_uint64(first_game_id)), "az_selfplay_begin")
+
+    def selfplay_step(self, waves):
+        st = SelfplayStats()
+        self._check(self._L.az_selfplay_step(self._h, int(waves), ctypes.byref(st)), "az_selfplay_step")
+        return st
+
+    def selfplay_drain(self, max_samples=None):
+        cap = int(max_samples or max(self.config.max_games * 128, 1 << 16))
+        out = np.empty(cap, SAMPLE_DTYPE)
+        n = ctypes.c_int(0)
+        self._check(self._L.az_selfplay_drain(self._h, _ptr(out), cap, ctypes.byref(n)), "az_selfplay_drain")
+        return out[: n.value]
+
+
+def improved_policy(sample, num_simulations):
+    """Dense EpisodeStep::improved_policy (Box<[f32; 4096]>) of a drained sample."""
+    dense = np.zeros(ACTION_SPACE, np.float32)
+    k = int(sample["n_visits"])
+    dense[sample["index"][:k]] = sample["count"][:k].astype(np.float32) / np.float32(num_simulations)
+    return dense

@@ -15,6 +15,10 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", os.path
 # translation units and their extra flags; the search/rules kernels must not contract a*b+c into FMA because visit
 # counts are bit-exact against the reference's f32 arithmetic (tree.rs:187-189)
 UNITS = [
+    ("engine.cu", []),
+    ("chess_kernels.cu", []),
+    ("mcts.cu", ["-fmad=false"]),
+    ("nn.cu", []),
     ("nn_tc.cu", []),
     ("dbg.cu", []),
 ]

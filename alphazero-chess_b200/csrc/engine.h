@@ -1,0 +1,74 @@
+// Internal engine state shared by the translation units of libaz_b200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+#include "../../include/az_b200.h"
+#include "chess.cuh"
+
+namespace azb {
+
+struct NetWeights;   // nn_weights.cu
+struct SearchState;  // mcts.cu
+
+struct RuleParams {
+    int num_halfmoves, num_fullmoves, repetitions;
+};
+
+}  // namespace azb
+
+struct az_engine {
+    az_config cfg;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int max_batch = 0;
+    int sm_count = 148;
+
+    // staging for the batched chess.rs entry points (device)
+    az_position* d_wire = nullptr;     // [max_batch]
+    az_position* d_hist = nullptr;     // history staging (grown on demand)
+    size_t hist_cap = 0;
+    uint32_t* d_hist_off = nullptr;    // [max_batch + 1]
+    uint16_t* d_moves = nullptr;       // [max_batch][256]
+    uint16_t* d_index = nullptr;       // [max_batch][256]
+    int32_t* d_count = nullptr;        // [max_batch]
+    uint16_t* d_u16a = nullptr;        // [max_batch]
+    uint16_t* d_u16b = nullptr;        // [max_batch]
+    float* d_planes = nullptr;         // [max_batch][19*64]
+    float* d_policy = nullptr;         // [max_batch][4096]
+    float* d_value = nullptr;          // [max_batch]
+    float* d_scores = nullptr;         // [max_batch][4096] (az_search scores export, lazy)
+
+    // perft level buffers (allocated lazily)
+    std::vector<azb::DPos*> perft_pos;
+    std::vector<uint32_t*> perft_root;
+    unsigned long long* d_perft_count = nullptr;
+    unsigned long long* d_perft_nodes = nullptr;
+    size_t perft_cap = 0;
+
+    azb::NetWeights* net = nullptr;
+    azb::SearchState* search = nullptr;
+    int stub_kind = 0;
+    uint64_t stub_seed = 0;
+};
+
+namespace azb {
+
+int set_err(az_engine* e, int code, const char* what);
+int check_cuda(az_engine* e, cudaError_t r, const char* what);
+#define AZ_CUDA(e, call) do { int _r = azb::check_cuda((e), (call), #call); if (_r) return _r; } while (0)
+
+// chess_kernels.cu
+void launch_movegen(cudaStream_t s, const az_position* wire, int n, uint16_t* moves, uint16_t* index, int32_t* count);
+void launch_play_move(cudaStream_t s, az_position* wire, const az_position* hist, const uint32_t* hist_off, const uint16_t* action,
+                      int32_t* result, int n, RuleParams rp);
+void launch_move_to_index(cudaStream_t s, const az_position* wire, const uint16_t* moves, uint16_t* index, int n);
+void launch_index_to_move(cudaStream_t s, const az_position* wire, const uint16_t* index, uint16_t* moves, int n);
+void launch_encode_f32(cudaStream_t s, const az_position* wire, float* planes, int n);
+void launch_wire_to_dpos(cudaStream_t s, const az_position* wire, DPos* out, uint32_t* root_ids, int n);
+void launch_perft_expand(cudaStream_t s, const DPos* in, const uint32_t* in_root, int n_in, DPos* out, uint32_t* out_root,
+                         unsigned long long* out_count);
+void launch_perft_count(cudaStream_t s, const DPos* in, const uint32_t* in_root, int n_in, unsigned long long* nodes);
+
+}  // namespace azb

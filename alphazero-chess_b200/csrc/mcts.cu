@@ -1,0 +1,952 @@
+// Device-resident PUCT search and self-play: one warp per game, struct-of-arrays tree pools in HBM.
+//
+// Restates tree.rs (MCTree::new / simulation / expand / traverse_new / apply_dirichlet_noise / max_subtree_depth)
+// and training.rs run_episode with exactly the reference's arithmetic: one simulation in flight per game
+// (tree.rs:170-172), PUCT = q + ((c*P)*sqrt(total))/(1+N) evaluated left to right in f32 with strict '>' and
+// first-max-in-move-order ties (tree.rs:184-195), W += v ; N += 1 on the way back with a sign flip per level
+// (tree.rs:197-206), terminal children never stored (tree.rs:233-234), no tree reuse between moves (tree.rs:239-256).
+// This translation unit is compiled with -fmad=false and uses explicit _rn intrinsics so no FMA contraction can
+// change a bit.  A "wave" lets every game run until it needs a network evaluation; the evaluations of all games form
+// one batch (the reference's recv_many batch, training.rs:369).
+#include "mcts.h"
+#include "nn.h"
+#include <cstring>
+#include <algorithm>
+
+namespace azb {
+
+constexpr int WARPS = 4;
+
+struct WarpShared {
+    double gam[AZ_MAX_MOVES];
+    float fval[AZ_MAX_MOVES];
+    uint16_t moves[AZ_MAX_MOVES];
+    uint16_t sidx[AZ_MAX_MOVES];
+    DPos child;
+    int n_moves;
+    int term;       // 0 ongoing, 1 draw, 2 decisive (side to move in the child is mated)
+    int has_ep;
+    int pad;
+};
+
+// ------------------------------------------------------------------------------------------- deterministic RNG
+// Counter-based generator + IEEE-exact log/exp, bit-identical to oracle/mcts.cpp (spec in DESIGN.md).
+__device__ __forceinline__ u64 splitmix64(u64 x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+__device__ __forceinline__ u64 rng_u64(u64 seed, u64 game, u64 ply, u64 stream, u64 counter) {
+    u64 h = splitmix64(seed);
+    h = splitmix64(h ^ game);
+    h = splitmix64(h ^ ply);
+    h = splitmix64(h ^ stream);
+    h = splitmix64(h ^ counter);
+    return h;
+}
+__device__ __forceinline__ double rng_uniform(u64 seed, u64 game, u64 ply, u64 stream, u64 counter) {
+    u64 h = rng_u64(seed, game, ply, stream, counter);
+    return ((double)(h >> 12) + 0.5) * (1.0 / 4503599627370496.0);
+}
+__device__ double det_log(double x) {
+    u64 bits = (u64)__double_as_longlong(x);
+    int e = (int)((bits >> 52) & 0x7FF) - 1023;
+    bits = (bits & 0x000FFFFFFFFFFFFFULL) | 0x3FF0000000000000ULL;
+    double m = __longlong_as_double((long long)bits);
+    if (m > 1.4142135623730951) { m = m * 0.5; e += 1; }
+    double s = (m - 1.0) / (m + 1.0);
+    double s2 = s * s;
+    double t = 1.0 / 23.0;
+    t = t * s2 + 1.0 / 21.0; t = t * s2 + 1.0 / 19.0; t = t * s2 + 1.0 / 17.0; t = t * s2 + 1.0 / 15.0;
+    t = t * s2 + 1.0 / 13.0; t = t * s2 + 1.0 / 11.0; t = t * s2 + 1.0 / 9.0; t = t * s2 + 1.0 / 7.0;
+    t = t * s2 + 1.0 / 5.0; t = t * s2 + 1.0 / 3.0; t = t * s2 + 1.0;
+    return (double)e * 0.6931471805599453 + 2.0 * s * t;
+}
+__device__ double det_exp(double x) {
+    double kf = x * 1.4426950408889634;
+    long long k = (long long)(kf < 0 ? kf - 0.5 : kf + 0.5);
+    double r = x - (double)k * 0.6931471805599453;
+    double t = 1.0 / 6227020800.0;
+    t = t * r + 1.0 / 479001600.0; t = t * r + 1.0 / 39916800.0; t = t * r + 1.0 / 3628800.0;
+    t = t * r + 1.0 / 362880.0; t = t * r + 1.0 / 40320.0; t = t * r + 1.0 / 5040.0; t = t * r + 1.0 / 720.0;
+    t = t * r + 1.0 / 120.0; t = t * r + 1.0 / 24.0; t = t * r + 1.0 / 6.0; t = t * r + 0.5; t = t * r + 1.0;
+    t = t * r + 1.0;
+    double sc = __longlong_as_double((long long)((u64)(k + 1023) << 52));
+    return t * sc;
+}
+// Gamma(alpha, 1), Marsaglia-Tsang with the alpha < 1 boost (the scheme of rand_distr 0.4.3)
+__device__ double gamma_sample(u64 seed, u64 game, u64 ply, u64 stream, double alpha) {
+    u64 ctr = 0;
+    double a = alpha < 1.0 ? alpha + 1.0 : alpha;
+    double d = a - 1.0 / 3.0;
+    double c = 1.0 / sqrt(9.0 * d);
+    double v, x;
+    for (;;) {
+        double u1, u2, s;
+        do {
+            u1 = 2.0 * rng_uniform(seed, game, ply, stream, ctr++) - 1.0;
+            u2 = 2.0 * rng_uniform(seed, game, ply, stream, ctr++) - 1.0;
+            s = u1 * u1 + u2 * u2;
+        } while (s >= 1.0 || s == 0.0);
+        x = u1 * sqrt(-2.0 * det_log(s) / s);
+        v = 1.0 + c * x;
+        if (v <= 0.0) continue;
+        v = v * v * v;
+        double u = rng_uniform(seed, game, ply, stream, ctr++);
+        if (det_log(u) < 0.5 * x * x + d - d * v + d * det_log(v)) break;
+    }
+    double g = d * v;
+    if (alpha < 1.0) { double u = rng_uniform(seed, game, ply, stream, ctr++); g = g * det_exp(det_log(u) / alpha); }
+    return g;
+}
+
+// ------------------------------------------------------------------------------------------- synthetic evaluator
+__device__ __forceinline__ u64 stub_position_hash(u64 seed, const DPos& p) {
+    const u64 occ = occupied(p);
+    u64 h = splitmix64(seed);
+    h = splitmix64(h ^ p.pawn); h = splitmix64(h ^ p.knight); h = splitmix64(h ^ p.bishop);
+    h = splitmix64(h ^ p.rook); h = splitmix64(h ^ p.queen); h = splitmix64(h ^ p.king);
+    h = splitmix64(h ^ p.white); h = splitmix64(h ^ (occ ^ p.white));
+    const int ep = pseudo_legal_ep(p);
+    u64 meta = (u64)meta_turn(p.meta) | ((u64)meta_castling(p.meta) << 8) | ((u64)(ep + 1) << 16) | ((u64)meta_halfmoves(p.meta) << 32) |
+               ((u64)meta_fullmoves(p.meta) << 48);
+    return splitmix64(h ^ meta);
+}
+// one warp per request: policy [4096] normalised integers, value in [-1, 1)
+__global__ void k_stub_eval(const DPos* __restrict__ req_pos, const int* __restrict__ n_dev, int n_static, u64 seed,
+                            float* __restrict__ policy, float* __restrict__ value) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int n = n_dev ? *n_dev : n_static;
+    if (warp >= n) return;
+    const DPos p = req_pos[warp];
+    const u64 h = stub_position_hash(seed, p);
+    u64 total = 0;
+    float* po = policy + (size_t)warp * AZ_ACTION_SPACE;
+    for (int i = lane; i < AZ_ACTION_SPACE; i += 32) {
+        u64 r = ((splitmix64(h + (u64)i) >> 52) << 12) + (u64)i + 1;
+        total += r;
+        po[i] = (float)r;
+    }
+    for (int d = 16; d; d >>= 1) total += __shfl_xor_sync(0xffffffffu, total, d);
+    const float tf = (float)total;
+    __syncwarp();
+    for (int i = lane; i < AZ_ACTION_SPACE; i += 32) po[i] = __fdiv_rn(po[i], tf);
+    if (lane == 0) {
+        u64 v = splitmix64(h ^ 0xA5A5A5A5A5A5A5A5ULL) >> 40;
+        value[warp] = __fsub_rn(__fmul_rn((float)v, 1.0f / 8388608.0f), 1.0f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------- per-game helpers
+struct Ctx {
+    const SearchParams& prm;
+    const SearchPtrs& ptr;
+    WarpShared* sh;
+    int g, lane;
+    size_t nbase, ebase;   // first node / edge of this game
+    GameCtl c;
+    // statistics accumulated by lane 0
+    unsigned int st_sims, st_pos, st_evals, st_term, st_games, st_depth, st_edges;
+};
+
+// Expands `mv` from `parent` on lane 0: child position, its legal moves (into shared memory), mate / stalemate /
+// insufficient material.  Repetition and move-count draws are decided afterwards by the whole warp.
+__device__ __forceinline__ void lane0_make_child(Ctx& x, const DPos& parent, uint16_t mv) {
+    if (x.lane == 0) {
+        DPos child = make_move(parent, mv);
+        ListSink sink{x.sh->moves, 0};
+        GenInfo gi = gen_legal(child, sink);
+        int term = 0;
+        if (sink.n == 0) term = gi.checkers ? 2 : 1;
+        else if (insufficient_material(child)) term = 1;
+        set_key_bits(child, gi.has_legal_ep);
+        x.sh->child = child;
+        x.sh->n_moves = sink.n;
+        x.sh->term = term;
+    }
+    __syncwarp();
+}
+
+// chess.rs:52-60: pos_count[child] (this occurrence included) reaches REPETITIONS, or a move counter hits its limit.
+// Candidates are the positions with the same side to move since the last irreversible move: they live on the
+// search path (depth >= 1) or in the game history.  `depth_child` = edges from the root to the child.
+__device__ __forceinline__ bool draw_by_rules(Ctx& x, const DPos& child, int depth_child) {
+    const int hm = meta_halfmoves(child.meta);
+    if (hm >= x.prm.num_halfmoves || meta_fullmoves(child.meta) >= x.prm.num_fullmoves) return true;
+    const int root_v = (int)x.c.hist_len - 1;          // virtual index of the root
+    const int v = root_v + depth_child;
+    int matches = 0;
+    const int n_cand = hm >> 1;
+    for (int k0 = 0; k0 < n_cand; k0 += 32) {
+        const int k = k0 + x.lane + 1;
+        bool eq = false;
+        const int j = v - 2 * k;
+        if (k <= n_cand && j >= 0) {
+            const DPos* q;
+            if (j > root_v) q = &x.ptr.node_pos[x.nbase + (x.ptr.path[(size_t)x.g * x.prm.node_cap + (j - root_v)] & 0xFFFF)];
+            else q = &x.ptr.hist[(size_t)x.g * HIST_CAP + j];
+            eq = same_position_key(*q, child);
+        }
+        matches += __popc(__ballot_sync(0xffffffffu, eq));
+    }
+    return matches + 1 >= x.prm.repetitions;
+}
+
+// tree.rs:272-289 on the edge list.  The reference draws one component per legal move INCLUDING the three
+// under-promotion duplicates that share a policy index with the queen promotion; edges keep one entry per index,
+// so a queen-promotion edge receives four consecutive components.
+__device__ void apply_noise(Ctx& x, int node, u64 game_id, u64 ply) {
+    const size_t off = x.ebase + x.ptr.node_edge_off[x.nbase + node];
+    const int L = x.ptr.node_nedges[x.nbase + node], n = x.ptr.node_nmoves[x.nbase + node];
+    if (n < 2) return;
+    for (int i = x.lane; i < n; i += 32) x.sh->gam[i] = gamma_sample(x.prm.seed, game_id, ply, 1000 + (u64)i, (double)x.prm.alpha);
+    __syncwarp();
+    double sum = 0.0;
+    if (x.lane == 0) for (int i = 0; i < n; i++) sum = sum + x.sh->gam[i];
+    sum = __shfl_sync(0xffffffffu, sum, 0);
+    for (int i = x.lane; i < n; i += 32) x.sh->fval[i] = (float)(x.sh->gam[i] / sum);
+    // component offset of every edge
+    if (x.lane == 0) {
+        int comp = 0;
+        for (int e = 0; e < L; e++) {
+            x.sh->sidx[e] = (uint16_t)comp;
+            comp += (((x.ptr.edge_mv[off + e] >> 12) & 7) == 4) ? 4 : 1;
+        }
+    }
+    __syncwarp();
+    const float keep = __fsub_rn(1.0f, x.prm.eps);
+    for (int e = x.lane; e < L; e += 32) {
+        float p = __fmul_rn(x.ptr.edge_P[off + e], keep);
+        const int c0 = x.sh->sidx[e];
+        const int reps = (((x.ptr.edge_mv[off + e] >> 12) & 7) == 4) ? 4 : 1;
+        for (int r = 0; r < reps; r++) p = __fadd_rn(p, __fmul_rn(x.prm.eps, x.sh->fval[c0 + r]));
+        x.ptr.edge_P[off + e] = p;
+    }
+    __syncwarp();
+}
+
+// Creates a tree node from sh->child / sh->moves (MCTree::new, tree.rs:84-104) without priors.
+// Returns the node id or -1 on pool exhaustion.
+__device__ __forceinline__ int create_node(Ctx& x, int depth) {
+    const int n = x.sh->n_moves;
+    int L = 0;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        const int i = i0 + x.lane;
+        bool keep = false;
+        if (i < n) { int pr = (x.sh->moves[i] >> 12) & 7; keep = pr == 0 || pr == 4; }
+        L += __popc(__ballot_sync(0xffffffffu, keep));
+    }
+    if ((int)x.c.n_nodes >= x.prm.node_cap || (int)x.c.n_edges + L > x.prm.edge_cap) return -1;
+    const int node = (int)x.c.n_nodes;
+    const uint32_t eoff = x.c.n_edges;
+    const int turn = meta_turn(x.sh->child.meta);
+    int written = 0;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        const int i = i0 + x.lane;
+        bool keep = false;
+        uint16_t mv = 0;
+        if (i < n) { mv = x.sh->moves[i]; int pr = (mv >> 12) & 7; keep = pr == 0 || pr == 4; }
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const size_t e = x.ebase + eoff + written + __popc(bal & ((1u << x.lane) - 1));
+            x.ptr.edge_mv[e] = (uint32_t)mv | ((uint32_t)move_to_index(mv, turn) << 16);
+            x.ptr.edge_N[e] = 0.0f;
+            x.ptr.edge_W[e] = 0.0f;
+            x.ptr.edge_P[e] = 0.0f;
+            x.ptr.edge_child[e] = -1;
+        }
+        written += __popc(bal);
+    }
+    if (x.lane == 0) {
+        const size_t ni = x.nbase + node;
+        x.ptr.node_pos[ni] = x.sh->child;
+        x.ptr.node_edge_off[ni] = eoff;
+        x.ptr.node_nedges[ni] = (uint16_t)L;
+        x.ptr.node_nmoves[ni] = (uint16_t)n;
+        x.ptr.node_total[ni] = 0.0f;
+        x.ptr.node_depth[ni] = (uint16_t)depth;
+    }
+    x.c.n_nodes++;
+    x.c.n_edges += L;
+    __syncwarp();
+    return node;
+}
+
+// Queues the position in sh->child for evaluation; returns the batch slot.
+__device__ __forceinline__ int submit_request(Ctx& x) {
+    int slot = 0;
+    if (x.lane == 0) slot = atomicAdd(x.ptr.batch_count, 1);
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    const DPos child = x.sh->child;
+    if (x.lane == 0) x.ptr.req_pos[slot] = child;
+    if (x.prm.fp32_planes) {
+        const u64 occ = occupied(child);
+        const u64 ours = meta_turn(child.meta) == 0 ? child.white : occ ^ child.white;
+        const int pep = pseudo_legal_ep(child);
+        float* out = x.ptr.req_f32 + (size_t)slot * (AZ_NUM_PLANES * 64);
+        for (int e = x.lane; e < AZ_NUM_PLANES * 64; e += 32) out[e] = plane_value(child, e >> 6, e & 63, pep, ours, occ ^ ours);
+    } else {
+        encode_bf16_warp(child, x.ptr.req_bf16 + (size_t)slot * 4096, x.lane);
+    }
+    if (x.lane == 0) x.st_evals++;
+    return slot;
+}
+
+// W[a] += v ; N[a] += 1 along the stored path, leaf parent first (tree.rs:197-206).  `leaf_value` is what
+// expand() returned (the child's point of view).
+__device__ __forceinline__ void backup(Ctx& x, float leaf_value, int path_len) {
+    for (int i0 = 0; i0 < path_len; i0 += 32) {
+        const int i = i0 + x.lane;
+        if (i < path_len) {
+            const uint32_t pe = x.ptr.path[(size_t)x.g * x.prm.node_cap + i];
+            const int node = pe & 0xFFFF, edge = pe >> 16;
+            const size_t e = x.ebase + x.ptr.node_edge_off[x.nbase + node] + edge;
+            // levels above the leaf's parent: the sign flips once per level
+            const int up = path_len - 1 - i;
+            const float v = (up & 1) ? leaf_value : -leaf_value;
+            x.ptr.edge_W[e] = __fadd_rn(x.ptr.edge_W[e], v);
+            x.ptr.edge_N[e] = __fadd_rn(x.ptr.edge_N[e], 1.0f);
+            x.ptr.node_total[x.nbase + node] = __fadd_rn(x.ptr.node_total[x.nbase + node], 1.0f);
+        }
+    }
+    __syncwarp();
+}
+
+// One PUCT descent from the root (tree.rs:180-202).  Fills the path and returns (node, edge) of the leaf edge.
+__device__ __forceinline__ void select_leaf(Ctx& x, int& leaf_node, int& leaf_edge, int& depth) {
+    int node = 0;
+    depth = 0;
+    for (;;) {
+        const size_t ni = x.nbase + node;
+        const size_t off = x.ebase + x.ptr.node_edge_off[ni];
+        const int L = x.ptr.node_nedges[ni];
+        const float total = __fadd_rn(x.ptr.node_total[ni], 1.0f);
+        const float sq = __fsqrt_rn(total);
+        float best = -INFINITY;
+        int best_e = 0x7FFFFFFF;
+        for (int e = x.lane; e < L; e += 32) {
+            const float P = x.ptr.edge_P[off + e], N = x.ptr.edge_N[off + e], W = x.ptr.edge_W[off + e];
+            const float u = __fdiv_rn(__fmul_rn(__fmul_rn(x.prm.c_puct, P), sq), __fadd_rn(1.0f, N));
+            const float q = N > 0.0f ? __fdiv_rn(W, N) : 0.0f;
+            const float v = __fadd_rn(q, u);
+            if (v > best) { best = v; best_e = e; }
+        }
+        // warp argmax: larger value wins, ties go to the earlier move (strict '>' in list order)
+        for (int d = 16; d; d >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, d);
+            const int oe = __shfl_xor_sync(0xffffffffu, best_e, d);
+            if (ov > best || (ov == best && oe < best_e)) { best = ov; best_e = oe; }
+        }
+        if (best_e == 0x7FFFFFFF) best_e = 0;  // every score was NaN / -inf: the reference keeps max_index = 0 (first move)
+        if (x.lane == 0) {
+            x.ptr.path[(size_t)x.g * x.prm.node_cap + depth] = (uint32_t)node | ((uint32_t)best_e << 16);
+            x.st_edges += L;
+        }
+        const int child = x.ptr.edge_child[off + best_e];
+        if (child < 0) { leaf_node = node; leaf_edge = best_e; __syncwarp(); return; }
+        node = child;
+        depth++;
+    }
+}
+
+__device__ __forceinline__ void setup_root_from_shared(Ctx& x) {
+    // fresh tree whose root is sh->child / sh->moves (priors are written by the caller)
+    x.c.n_nodes = 0; x.c.n_edges = 0; x.c.sims_done = 0; x.c.max_depth = 0; x.c.pending_node = -1;
+    create_node(x, 0);
+}
+
+// training.rs:303-335 for one finished search: record the EpisodeStep, pick the move, advance or finish the game.
+__device__ void move_step(Ctx& x) {
+    const size_t ni = x.nbase;  // root
+    const size_t off = x.ebase + x.ptr.node_edge_off[ni];
+    const int L = x.ptr.node_nedges[ni];
+    const DPos root = x.ptr.node_pos[ni];
+    const int turn = meta_turn(root.meta);
+    // ---- sort the visited edges by policy index (the reference works on the dense 4096-vector)
+    int nv = 0;
+    for (int e0 = 0; e0 < L; e0 += 32) {
+        const int e = e0 + x.lane;
+        int rank = -1;
+        if (e < L && x.ptr.edge_N[off + e] > 0.0f) {
+            const uint32_t my = x.ptr.edge_mv[off + e] >> 16;
+            rank = 0;
+            for (int o = 0; o < L; o++)
+                if (x.ptr.edge_N[off + o] > 0.0f && (x.ptr.edge_mv[off + o] >> 16) < my) rank++;
+            x.sh->sidx[rank] = (uint16_t)e;
+        }
+        nv += __popc(__ballot_sync(0xffffffffu, rank >= 0));
+    }
+    __syncwarp();
+    // ---- EpisodeStep
+    const uint32_t sidx_slot = x.c.n_samples;
+    az_sample* smp = nullptr;
+    if (sidx_slot < MAX_SAMPLE_PLIES) {
+        smp = x.ptr.game_samples + (size_t)x.g * MAX_SAMPLE_PLIES + sidx_slot;
+        for (int i = x.lane; i < nv; i += 32) {
+            const size_t e = off + x.sh->sidx[i];
+            smp->index[i] = (uint16_t)(x.ptr.edge_mv[e] >> 16);
+            smp->count[i] = (uint16_t)x.ptr.edge_N[e];
+        }
+    }
+    // ---- action (training.rs:310-321)
+    int action_edge = 0;
+    if (x.lane == 0) {
+        const float S = x.ptr.node_total[ni];  // weights_sum (T = 1: visits^(1/T) = visits)
+        if ((uint32_t)meta_fullmoves(root.meta) >= x.prm.anneal) {
+            float best = -1.0f;  // Iterator::max_by keeps the LAST maximum in index order
+            for (int i = 0; i < nv; i++) {
+                const float w = __fdiv_rn(x.ptr.edge_N[off + x.sh->sidx[i]], S);
+                if (w >= best) { best = w; action_edge = x.sh->sidx[i]; }
+            }
+        } else {
+            float total = 0.0f;  // WeightedIndex: cumulative f32 weights in index order
+            for (int i = 0; i < nv; i++) total = __fadd_rn(total, __fdiv_rn(x.ptr.edge_N[off + x.sh->sidx[i]], S));
+            const u64 h = rng_u64(x.prm.seed, x.c.game_id, x.c.ply, 1, 0);
+            const float u = __fmul_rn((float)(h >> 40), 1.0f / 16777216.0f);
+            const float chosen = __fmul_rn(u, total);
+            float cum = 0.0f;
+            action_edge = nv > 0 ? x.sh->sidx[nv - 1] : 0;
+            for (int i = 0; i < nv; i++) {
+                cum = __fadd_rn(cum, __fdiv_rn(x.ptr.edge_N[off + x.sh->sidx[i]], S));
+                if (cum > chosen) { action_edge = x.sh->sidx[i]; break; }
+            }
+        }
+    }
+    action_edge = __shfl_sync(0xffffffffu, action_edge, 0);
+    const uint32_t amv = x.ptr.edge_mv[off + action_edge];
+    if (smp && x.lane == 0) {
+        smp->position = dpos_to_wire(root);
+        smp->final_value = turn == 0 ? 1.0f : -1.0f;
+        smp->search_depth = (int32_t)x.c.max_depth;
+        smp->game_id = x.c.game_id;
+        smp->ply = x.c.ply;
+        smp->action = (uint16_t)(amv >> 16);
+        smp->n_visits = (uint16_t)nv;
+        x.st_pos++;
+    }
+    x.c.n_samples = min(x.c.n_samples + 1, (uint32_t)MAX_SAMPLE_PLIES);
+    // ---- play it (chess.rs:36-63)
+    const int child_node = x.ptr.edge_child[off + action_edge];
+    lane0_make_child(x, root, (uint16_t)(amv & 0xFFFF));
+    int term = x.sh->term;
+    if (term == 0 && draw_by_rules(x, x.sh->child, 1)) term = 1;
+    if (term == 0) {
+        // traverse_new (tree.rs:239-256): keep the child's priors, drop everything else, fresh noise
+        float keepP[7];
+        int Lc = 0;
+        if (child_node >= 0) {
+            const size_t coff = x.ebase + x.ptr.node_edge_off[x.nbase + child_node];
+            Lc = x.ptr.node_nedges[x.nbase + child_node];
+#pragma unroll
+            for (int k = 0; k < 7; k++) { int e = x.lane + 32 * k; keepP[k] = e < Lc ? x.ptr.edge_P[coff + e] : 0.0f; }
+        } else {
+            x.c.status = 3;  // a move with visits but no stored child must be terminal
+        }
+        __syncwarp();
+        if (x.lane == 0 && x.c.hist_len < HIST_CAP) x.ptr.hist[(size_t)x.g * HIST_CAP + x.c.hist_len] = x.sh->child;
+        x.c.hist_len = min(x.c.hist_len + 1, (uint32_t)HIST_CAP);
+        x.c.ply++;
+        setup_root_from_shared(x);
+#pragma unroll
+        for (int k = 0; k < 7; k++) { int e = x.lane + 32 * k; if (e < Lc) x.ptr.edge_P[x.ebase + e] = keepP[k]; }
+        __syncwarp();
+        apply_noise(x, 0, x.c.game_id, x.c.ply);
+        return;
+    }
+    // ---- game over: back-fill final_value (training.rs:332-335), publish the samples, start a new game
+    const float mover = turn == 0 ? 1.0f : -1.0f;
+    const float result = term == 1 ? 0.0f : mover;
+    const float decay = __fsub_rn(1.0f, __fdiv_rn((float)meta_fullmoves(x.sh->child.meta), __fmul_rn(2.0f, (float)x.prm.num_fullmoves)));
+    const float scale = __fmul_rn(result, decay);
+    const int ns = (int)x.c.n_samples;
+    unsigned long long base = 0;
+    if (x.lane == 0) base = atomicAdd(&x.ptr.counters->samples_out, (unsigned long long)ns);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base + ns <= (unsigned long long)x.prm.sample_cap) {
+        az_sample* src = x.ptr.game_samples + (size_t)x.g * MAX_SAMPLE_PLIES;
+        for (int i = x.lane; i < ns; i += 32) src[i].final_value = __fmul_rn(src[i].final_value, scale);
+        __syncwarp();
+        const uint4* s4 = reinterpret_cast<const uint4*>(src);
+        uint4* d4 = reinterpret_cast<uint4*>(x.ptr.out_samples + base);
+        const int n16 = ns * (int)(sizeof(az_sample) / 16);
+        for (int i = x.lane; i < n16; i += 32) d4[i] = s4[i];
+    } else if (x.lane == 0) {
+        atomicAdd(&x.ptr.counters->errors, 1ULL);  // sample queue overflow: the host did not drain
+    }
+    if (x.lane == 0) x.st_games++;
+    // new game (training.rs:352-361): start position, shared start-position priors, noise
+    unsigned long long gid = 0;
+    if (x.lane == 0) gid = atomicAdd(&x.ptr.counters->next_game_id, 1ULL);
+    gid = __shfl_sync(0xffffffffu, gid, 0);
+    x.c.game_id = gid; x.c.ply = 0; x.c.n_samples = 0; x.c.hist_len = 1;
+    if (x.lane == 0) {
+        az_position sp;
+        sp.roles[0] = 0x00FF00000000FF00ULL; sp.roles[1] = 0x4200000000000042ULL; sp.roles[2] = 0x2400000000000024ULL;
+        sp.roles[3] = 0x8100000000000081ULL; sp.roles[4] = 0x0800000000000008ULL; sp.roles[5] = 0x1000000000000010ULL;
+        sp.colors[0] = 0xFFFFULL; sp.colors[1] = 0xFFFF000000000000ULL;
+        sp.turn = 0; sp.castling = 15; sp.ep_square = -1; sp.reserved = 0; sp.halfmoves = 0; sp.fullmoves = 1;
+        DPos s = dpos_from_wire(sp);
+        ListSink sink{x.sh->moves, 0};
+        GenInfo gi = gen_legal(s, sink);
+        set_key_bits(s, gi.has_legal_ep);
+        x.sh->child = s; x.sh->n_moves = sink.n; x.sh->term = 0;
+        x.ptr.hist[(size_t)x.g * HIST_CAP] = s;
+    }
+    __syncwarp();
+    setup_root_from_shared(x);
+    const int L0 = x.ptr.node_nedges[x.nbase];
+    for (int e = x.lane; e < L0; e += 32) x.ptr.edge_P[x.ebase + e] = x.ptr.start_prior[e];
+    __syncwarp();
+    apply_noise(x, 0, x.c.game_id, 0);
+}
+
+// ------------------------------------------------------------------------------------------- the wave kernel
+__global__ void __launch_bounds__(WARPS * 32) k_advance(SearchParams prm, SearchPtrs ptr) {
+    __shared__ WarpShared shared[WARPS];
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (g >= prm.n_games) return;
+    Ctx x{prm, ptr, &shared[threadIdx.x >> 5], g, (int)(threadIdx.x & 31), (size_t)g * prm.node_cap, (size_t)g * prm.edge_cap,
+          ptr.ctl[g], 0, 0, 0, 0, 0, 0, 0};
+    if (x.c.status != 0) return;
+
+    // ---- 1. the evaluation requested in the previous wave has arrived
+    if (x.c.pending_node >= 0) {
+        const int node = x.c.pending_node, slot = x.c.pending_slot;
+        const size_t off = x.ebase + ptr.node_edge_off[x.nbase + node];
+        const int L = ptr.node_nedges[x.nbase + node];
+        const float* pol = ptr.res_policy + (size_t)slot * AZ_ACTION_SPACE;
+        for (int e = x.lane; e < L; e += 32) ptr.edge_P[off + e] = pol[ptr.edge_mv[off + e] >> 16];
+        __syncwarp();
+        if (node == 0) {  // MCTree::init (tree.rs:37-64): root priors, optional noise, no backup
+            if (x.c.flags & 1) apply_noise(x, 0, x.c.game_id, x.c.noise_ply);
+        } else {
+            backup(x, ptr.res_value[slot], (int)x.c.path_len);
+            x.c.sims_done++;
+            if (x.lane == 0) x.st_sims++;
+        }
+        x.c.pending_node = -1;
+    }
+
+    // ---- 2. run until the network is needed again
+    for (int iter = 0; iter < prm.max_iters; iter++) {
+        if ((int)x.c.sims_done >= prm.S) {
+            if (prm.mode == 0) { x.c.status = 1; break; }
+            move_step(x);
+            if (x.c.status != 0) break;
+            continue;
+        }
+        int node, edge, depth;
+        select_leaf(x, node, edge, depth);
+        const size_t pe = x.ebase + ptr.node_edge_off[x.nbase + node] + edge;
+        const DPos parent = ptr.node_pos[x.nbase + node];
+        lane0_make_child(x, parent, (uint16_t)(ptr.edge_mv[pe] & 0xFFFF));
+        int term = x.sh->term;
+        if (term == 0 && draw_by_rules(x, x.sh->child, depth + 1)) term = 1;
+        if (x.lane == 0) x.st_depth += depth + 1;
+        if (term != 0) {
+            // Draw -> 0.0, decisive -> -1.0 from the child's side (tree.rs:233-234); nothing is stored
+            backup(x, term == 1 ? 0.0f : -1.0f, depth + 1);
+            x.c.sims_done++;
+            if (x.lane == 0) { x.st_sims++; x.st_term++; }
+            continue;
+        }
+        const int child = create_node(x, depth + 1);
+        if (child < 0) { x.c.status = 2; if (x.lane == 0) atomicAdd(&ptr.counters->errors, 1ULL); break; }
+        if (x.lane == 0) ptr.edge_child[pe] = child;
+        x.c.max_depth = max(x.c.max_depth, (uint32_t)(depth + 1));
+        x.c.pending_node = child;
+        x.c.pending_slot = submit_request(x);
+        x.c.path_len = depth + 1;
+        break;
+    }
+
+    if (x.lane == 0) {
+        ptr.ctl[g] = x.c;
+        Counters* ct = ptr.counters;
+        if (x.st_sims) atomicAdd(&ct->simulations, (unsigned long long)x.st_sims);
+        if (x.st_pos) atomicAdd(&ct->positions, (unsigned long long)x.st_pos);
+        if (x.st_evals) atomicAdd(&ct->evaluations, (unsigned long long)x.st_evals);
+        if (x.st_term) atomicAdd(&ct->terminal_leaves, (unsigned long long)x.st_term);
+        if (x.st_games) atomicAdd(&ct->games_finished, (unsigned long long)x.st_games);
+        if (x.st_depth) atomicAdd(&ct->sum_leaf_depth, (unsigned long long)x.st_depth);
+        if (x.st_edges) atomicAdd(&ct->sum_edges, (unsigned long long)x.st_edges);
+    }
+}
+
+// Root set-up for az_search (MCTree::init): node 0 from the given position, evaluation pending.
+__global__ void __launch_bounds__(WARPS * 32) k_init_search(SearchParams prm, SearchPtrs ptr, const az_position* __restrict__ roots,
+                                                            const az_position* __restrict__ hist, const uint32_t* __restrict__ hist_off,
+                                                            const unsigned long long* __restrict__ noise_ids,
+                                                            const uint32_t* __restrict__ noise_plies) {
+    __shared__ WarpShared shared[WARPS];
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (g >= prm.n_games) return;
+    GameCtl c;
+    memset(&c, 0, sizeof c);
+    Ctx x{prm, ptr, &shared[threadIdx.x >> 5], g, (int)(threadIdx.x & 31), (size_t)g * prm.node_cap, (size_t)g * prm.edge_cap, c,
+          0, 0, 0, 0, 0, 0, 0};
+    x.c.game_id = noise_ids ? noise_ids[g] : 0;
+    x.c.noise_ply = noise_plies ? noise_plies[g] : 0;
+    x.c.flags = noise_ids ? 1 : 0;
+    // history (positions already counted, current root last); key bits need the legal ep square of each entry
+    int hl = 1;
+    if (hist) {
+        const uint32_t h0 = hist_off[g], h1 = hist_off[g + 1];
+        int n = (int)(h1 - h0);
+        const uint32_t skip = n > HIST_CAP ? n - HIST_CAP : 0;
+        n -= skip;
+        for (int i = x.lane; i < n; i += 32) {
+            DPos q = dpos_from_wire(hist[h0 + skip + i]);
+            bool q_ep = false;
+            if (meta_ep(q.meta) >= 0) { CountSink t{0}; q_ep = gen_legal(q, t).has_legal_ep; }
+            set_key_bits(q, q_ep);
+            ptr.hist[(size_t)g * HIST_CAP + i] = q;
+        }
+        hl = max(n, 1);
+    }
+    __syncwarp();
+    if (x.lane == 0) {
+        DPos r = dpos_from_wire(roots[g]);
+        ListSink sink{x.sh->moves, 0};
+        GenInfo gi = gen_legal(r, sink);
+        set_key_bits(r, gi.has_legal_ep);
+        x.sh->child = r; x.sh->n_moves = sink.n; x.sh->term = 0;
+        if (!hist || hist_off[g + 1] == hist_off[g]) ptr.hist[(size_t)g * HIST_CAP] = r;
+    }
+    __syncwarp();
+    x.c.hist_len = hl;
+    setup_root_from_shared(x);
+    x.c.pending_node = 0;
+    x.c.pending_slot = submit_request(x);
+    if (x.sh->n_moves == 0) x.c.status = 1;  // nothing to search in a terminal position
+    if (x.lane == 0) ptr.ctl[g] = x.c;
+}
+
+// Game set-up for self-play (training.rs:352-361): start position, shared priors, Dirichlet noise.
+__global__ void __launch_bounds__(WARPS * 32) k_init_selfplay(SearchParams prm, SearchPtrs ptr, unsigned long long first_game_id) {
+    __shared__ WarpShared shared[WARPS];
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (g >= prm.n_games) return;
+    GameCtl c;
+    memset(&c, 0, sizeof c);
+    Ctx x{prm, ptr, &shared[threadIdx.x >> 5], g, (int)(threadIdx.x & 31), (size_t)g * prm.node_cap, (size_t)g * prm.edge_cap, c,
+          0, 0, 0, 0, 0, 0, 0};
+    x.c.game_id = first_game_id + g;
+    x.c.hist_len = 1;
+    if (x.lane == 0) {
+        az_position sp;
+        sp.roles[0] = 0x00FF00000000FF00ULL; sp.roles[1] = 0x4200000000000042ULL; sp.roles[2] = 0x2400000000000024ULL;
+        sp.roles[3] = 0x8100000000000081ULL; sp.roles[4] = 0x0800000000000008ULL; sp.roles[5] = 0x1000000000000010ULL;
+        sp.colors[0] = 0xFFFFULL; sp.colors[1] = 0xFFFF000000000000ULL;
+        sp.turn = 0; sp.castling = 15; sp.ep_square = -1; sp.reserved = 0; sp.halfmoves = 0; sp.fullmoves = 1;
+        DPos s = dpos_from_wire(sp);
+        ListSink sink{x.sh->moves, 0};
+        GenInfo gi = gen_legal(s, sink);
+        set_key_bits(s, gi.has_legal_ep);
+        x.sh->child = s; x.sh->n_moves = sink.n; x.sh->term = 0;
+        ptr.hist[(size_t)g * HIST_CAP] = s;
+    }
+    __syncwarp();
+    setup_root_from_shared(x);
+    const int L0 = ptr.node_nedges[x.nbase];
+    for (int e = x.lane; e < L0; e += 32) ptr.edge_P[x.ebase + e] = ptr.start_prior[e];
+    __syncwarp();
+    apply_noise(x, 0, x.c.game_id, 0);
+    if (x.lane == 0) ptr.ctl[g] = x.c;
+}
+
+// start-position priors from a policy row (the single shared forward of training.rs:344-350)
+__global__ void k_start_prior(const float* __restrict__ policy_row, float* __restrict__ start_prior) {
+    if (threadIdx.x == 0) {
+        az_position sp;
+        sp.roles[0] = 0x00FF00000000FF00ULL; sp.roles[1] = 0x4200000000000042ULL; sp.roles[2] = 0x2400000000000024ULL;
+        sp.roles[3] = 0x8100000000000081ULL; sp.roles[4] = 0x0800000000000008ULL; sp.roles[5] = 0x1000000000000010ULL;
+        sp.colors[0] = 0xFFFFULL; sp.colors[1] = 0xFFFF000000000000ULL;
+        sp.turn = 0; sp.castling = 15; sp.ep_square = -1; sp.reserved = 0; sp.halfmoves = 0; sp.fullmoves = 1;
+        DPos s = dpos_from_wire(sp);
+        uint16_t mv[AZ_MAX_MOVES];
+        ListSink sink{mv, 0};
+        gen_legal(s, sink);
+        for (int i = 0; i < sink.n && i < 32; i++) start_prior[i] = policy_row[move_to_index(mv[i], 0)];
+    }
+}
+
+// dense export of the root statistics (Box<[f32; 4096]> visits / scores)
+__global__ void k_export_root(SearchParams prm, SearchPtrs ptr, float* __restrict__ visits, float* __restrict__ scores,
+                              int32_t* __restrict__ depth) {
+    const int g = blockIdx.x;
+    float* vo = visits + (size_t)g * AZ_ACTION_SPACE;
+    float* so = scores ? scores + (size_t)g * AZ_ACTION_SPACE : nullptr;
+    for (int i = threadIdx.x; i < AZ_ACTION_SPACE; i += blockDim.x) { vo[i] = 0.0f; if (so) so[i] = 0.0f; }
+    __syncthreads();
+    const size_t nb = (size_t)g * prm.node_cap, eb = (size_t)g * prm.edge_cap + ptr.node_edge_off[nb];
+    const int L = ptr.node_nedges[nb];
+    for (int e = threadIdx.x; e < L; e += blockDim.x) {
+        const int idx = ptr.edge_mv[eb + e] >> 16;
+        vo[idx] = ptr.edge_N[eb + e];
+        if (so) so[idx] = ptr.edge_W[eb + e];
+    }
+    if (threadIdx.x == 0 && depth) depth[g] = (int32_t)ptr.ctl[g].max_depth;
+}
+
+__global__ void k_count_active(SearchParams prm, SearchPtrs ptr, int* out) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < prm.n_games) {
+        const uint32_t s = ptr.ctl[g].status;
+        if (s == 0) atomicAdd(&out[0], 1);
+        if (s >= 2) atomicAdd(&out[1], 1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------- host side
+template <class T>
+static int salloc(az_engine* e, SearchState* st, T** p, size_t n) {
+    cudaError_t r = cudaMalloc(p, n * sizeof(T));
+    if (r != cudaSuccess) return check_cuda(e, r, "cudaMalloc(search)");
+    st->allocs.push_back(*p);
+    return 0;
+}
+
+int search_create(az_engine* e) {
+    SearchState* st = new SearchState;
+    e->search = st;
+    const az_config& c = e->cfg;
+    const int G = c.max_games;
+    st->G = G;
+    SearchParams& p = st->prm;
+    p.n_games = G; p.S = c.num_simulations; p.c_puct = c.c_puct; p.alpha = c.dirichlet_alpha; p.eps = c.dirichlet_epsilon;
+    p.anneal = c.temperature_annealing; p.num_halfmoves = (int)c.num_halfmoves; p.num_fullmoves = (int)c.num_fullmoves;
+    p.repetitions = (int)c.repetitions; p.seed = c.seed;
+    p.node_cap = c.num_simulations + 2;
+    if (p.node_cap > 65535) return set_err(e, AZ_ERR_INVALID_ARGUMENT, "num_simulations must be < 65534");
+    const int per_node = c.edge_capacity_per_node > 0 ? c.edge_capacity_per_node : 96;
+    p.edge_cap = std::max(p.node_cap * std::min(per_node, 218), 256);
+    p.mode = 0; p.max_iters = 8; p.fp32_planes = c.precision == 1 ? 1 : 0;
+    p.sample_cap = std::max(G * 128, 1 << 16);
+    SearchPtrs& q = st->ptr;
+    const size_t NN = (size_t)G * p.node_cap, NE = (size_t)G * p.edge_cap;
+    int r = 0;
+    r |= salloc(e, st, &q.node_pos, NN); r |= salloc(e, st, &q.node_edge_off, NN); r |= salloc(e, st, &q.node_nedges, NN);
+    r |= salloc(e, st, &q.node_nmoves, NN); r |= salloc(e, st, &q.node_total, NN); r |= salloc(e, st, &q.node_depth, NN);
+    r |= salloc(e, st, &q.edge_P, NE); r |= salloc(e, st, &q.edge_N, NE); r |= salloc(e, st, &q.edge_W, NE);
+    r |= salloc(e, st, &q.edge_child, NE); r |= salloc(e, st, &q.edge_mv, NE);
+    r |= salloc(e, st, &q.ctl, (size_t)G); r |= salloc(e, st, &q.path, NN); r |= salloc(e, st, &q.hist, (size_t)G * HIST_CAP);
+    r |= salloc(e, st, &q.batch_count, 4); r |= salloc(e, st, &q.req_pos, (size_t)e->max_batch);
+    r |= salloc(e, st, &q.req_f32, (size_t)e->max_batch * AZ_NUM_PLANES * 64);
+    r |= salloc(e, st, &q.start_prior, 32); r |= salloc(e, st, &q.counters, 1);
+    if (r) return AZ_ERR_OUT_OF_MEMORY;
+    q.req_bf16 = e->net->a_in;
+    q.res_policy = e->d_policy;
+    q.res_value = e->d_value;
+    q.game_samples = nullptr;
+    q.out_samples = nullptr;
+    cudaMemset(q.counters, 0, sizeof(Counters));
+    cudaMemset(q.batch_count, 0, 16);
+    return 0;
+}
+
+void search_destroy(az_engine* e) {
+    SearchState* st = e->search;
+    if (!st) return;
+    for (void* p : st->allocs) cudaFree(p);
+    delete st;
+    e->search = nullptr;
+}
+
+// evaluates the queued requests: the network (bf16 or fp32) or the synthetic evaluator
+static int evaluate_batch(az_engine* e, SearchState* st) {
+    const SearchPtrs& q = st->ptr;
+    if (e->stub_kind == 1) {
+        const int warps = e->max_batch;
+        k_stub_eval<<<(warps + 3) / 4, 128, 0, e->stream>>>(q.req_pos, q.batch_count, 0, e->stub_seed, e->d_policy, e->d_value);
+        return check_cuda(e, cudaGetLastError(), "k_stub_eval");
+    }
+    if (e->cfg.precision == 1) return net_forward_fp32(e, q.req_f32, q.batch_count, 0, e->d_policy, e->d_value);
+    return net_forward_bf16(e, q.batch_count, 0, e->d_policy, e->d_value);
+}
+
+static int run_wave(az_engine* e, SearchState* st) {
+    const int blocks = (st->prm.n_games + WARPS - 1) / WARPS;
+    AZ_CUDA(e, cudaMemsetAsync(st->ptr.batch_count, 0, sizeof(int), e->stream));
+    k_advance<<<blocks, WARPS * 32, 0, e->stream>>>(st->prm, st->ptr);
+    AZ_CUDA(e, cudaGetLastError());
+    return evaluate_batch(e, st);
+}
+
+}  // namespace azb
+
+using namespace azb;
+
+extern "C" {
+
+int az_set_evaluator_stub(az_engine* e, int kind, uint64_t seed) {
+    if (!e || kind < 0 || kind > 1) return AZ_ERR_INVALID_ARGUMENT;
+    e->stub_kind = kind;
+    e->stub_seed = seed;
+    return AZ_OK;
+}
+
+int az_search(az_engine* e, int n, const az_position* roots, const az_position* history, const uint32_t* hist_offsets,
+              int num_simulations, const uint64_t* noise_game_ids, const uint32_t* noise_plies, float* visits_out, float* scores_out,
+              int32_t* depth_out) {
+    if (!e) return AZ_ERR_INVALID_ARGUMENT;
+    SearchState* st = e->search;
+    if (n < 0 || n > st->G) return set_err(e, AZ_ERR_CAPACITY, "more roots than az_config.max_games");
+    if (n == 0) return AZ_OK;
+    if (!roots || !visits_out) return set_err(e, AZ_ERR_INVALID_ARGUMENT, "null buffer");
+    if (num_simulations <= 0 || num_simulations + 2 > st->prm.node_cap)
+        return set_err(e, AZ_ERR_CAPACITY, "num_simulations exceeds az_config.num_simulations (pool size)");
+    if (e->stub_kind == 0 && !e->net->loaded) return set_err(e, AZ_ERR_NO_WEIGHTS, "az_load_weights has not been called");
+    cudaSetDevice(e->cfg.device);
+    st->selfplay_active = false;
+    SearchParams prm = st->prm;
+    prm.n_games = n; prm.S = num_simulations; prm.mode = 0;
+    SearchState run = *st;
+    run.prm = prm;
+    // stage inputs
+    AZ_CUDA(e, cudaMemcpyAsync(e->d_wire, roots, (size_t)n * sizeof(az_position), cudaMemcpyHostToDevice, e->stream));
+    const az_position* d_hist = nullptr;
+    if (history && hist_offsets) {
+        size_t total = hist_offsets[n];
+        if (total > e->hist_cap) {
+            cudaFree(e->d_hist); e->d_hist = nullptr; e->hist_cap = 0;
+            AZ_CUDA(e, cudaMalloc(&e->d_hist, std::max<size_t>(total, 1024) * sizeof(az_position)));
+            e->hist_cap = std::max<size_t>(total, 1024);
+        }
+        if (total) AZ_CUDA(e, cudaMemcpyAsync(e->d_hist, history, total * sizeof(az_position), cudaMemcpyHostToDevice, e->stream));
+        AZ_CUDA(e, cudaMemcpyAsync(e->d_hist_off, hist_offsets, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, e->stream));
+        d_hist = e->d_hist ? e->d_hist : (const az_position*)e->d_wire;
+    }
+    unsigned long long* d_ids = nullptr;
+    uint32_t* d_plies = nullptr;
+    if (noise_game_ids) {
+        AZ_CUDA(e, cudaMalloc(&d_ids, (size_t)n * 8));
+        AZ_CUDA(e, cudaMalloc(&d_plies, (size_t)n * 4));
+        AZ_CUDA(e, cudaMemcpyAsync(d_ids, noise_game_ids, (size_t)n * 8, cudaMemcpyHostToDevice, e->stream));
+        if (noise_plies) AZ_CUDA(e, cudaMemcpyAsync(d_plies, noise_plies, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
+        else AZ_CUDA(e, cudaMemsetAsync(d_plies, 0, (size_t)n * 4, e->stream));
+    }
+    const int blocks = (n + WARPS - 1) / WARPS;
+    AZ_CUDA(e, cudaMemsetAsync(run.ptr.batch_count, 0, 16, e->stream));
+    k_init_search<<<blocks, WARPS * 32, 0, e->stream>>>(run.prm, run.ptr, e->d_wire, d_hist, e->d_hist_off, d_ids, d_plies);
+    AZ_CUDA(e, cudaGetLastError());
+    int r = evaluate_batch(e, &run);
+    if (r) return r;
+    // every wave completes at least one simulation per active game
+    int* d_flags = run.ptr.batch_count + 2;
+    int rc = AZ_OK;
+    for (int wave = 0;; wave++) {
+        r = run_wave(e, &run);
+        if (r) { rc = r; break; }
+        if (wave + 1 >= num_simulations && (wave + 1 - num_simulations) % 4 == 0) {
+            int flags[2] = {0, 0};
+            AZ_CUDA(e, cudaMemsetAsync(d_flags, 0, 8, e->stream));
+            k_count_active<<<(n + 127) / 128, 128, 0, e->stream>>>(run.prm, run.ptr, d_flags);
+            AZ_CUDA(e, cudaMemcpyAsync(flags, d_flags, 8, cudaMemcpyDeviceToHost, e->stream));
+            AZ_CUDA(e, cudaStreamSynchronize(e->stream));
+            if (flags[1]) { rc = set_err(e, AZ_ERR_CAPACITY, "a per-game node/edge pool overflowed (raise edge_capacity_per_node)"); break; }
+            if (flags[0] == 0) break;
+            if (wave > 4 * num_simulations + 16) { rc = set_err(e, AZ_ERR_STATE, "search did not converge"); break; }
+        }
+    }
+    if (rc == AZ_OK) {
+        float* d_vis = e->d_policy;  // reuse the result buffers for the dense export
+        float* d_sc = nullptr;
+        if (scores_out) {
+            if (!e->d_scores) AZ_CUDA(e, cudaMalloc(&e->d_scores, (size_t)e->max_batch * AZ_ACTION_SPACE * 4));
+            d_sc = e->d_scores;
+        }
+        k_export_root<<<n, 256, 0, e->stream>>>(run.prm, run.ptr, d_vis, d_sc, e->d_count);
+        AZ_CUDA(e, cudaGetLastError());
+        AZ_CUDA(e, cudaMemcpyAsync(visits_out, d_vis, (size_t)n * AZ_ACTION_SPACE * 4, cudaMemcpyDeviceToHost, e->stream));
+        if (scores_out) AZ_CUDA(e, cudaMemcpyAsync(scores_out, d_sc, (size_t)n * AZ_ACTION_SPACE * 4, cudaMemcpyDeviceToHost, e->stream));
+        if (depth_out) AZ_CUDA(e, cudaMemcpyAsync(depth_out, e->d_count, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
+        AZ_CUDA(e, cudaStreamSynchronize(e->stream));
+    }
+    cudaFree(d_ids); cudaFree(d_plies);
+    return rc;
+}
+
+int az_selfplay_begin(az_engine* e, int n_games, uint64_t first_game_id) {
+    if (!e) return AZ_ERR_INVALID_ARGUMENT;
+    SearchState* st = e->search;
+    if (n_games <= 0 || n_games > st->G) return set_err(e, AZ_ERR_CAPACITY, "more games than az_config.max_games");
+    if (e->stub_kind == 0 && !e->net->loaded) return set_err(e, AZ_ERR_NO_WEIGHTS, "az_load_weights has not been called");
+    cudaSetDevice(e->cfg.device);
+    SearchPtrs& q = st->ptr;
+    if (!q.game_samples) {
+        int r = salloc(e, st, &q.game_samples, (size_t)st->G * MAX_SAMPLE_PLIES);
+        r |= salloc(e, st, &q.out_samples, (size_t)st->prm.sample_cap);
+        if (r) return AZ_ERR_OUT_OF_MEMORY;
+    }
+    st->prm.n_games = n_games; st->prm.mode = 1; st->prm.S = e->cfg.num_simulations;
+    Counters zero;
+    std::memset(&zero, 0, sizeof zero);
+    zero.next_game_id = first_game_id + n_games;
+    AZ_CUDA(e, cudaMemcpyAsync(q.counters, &zero, sizeof zero, cudaMemcpyHostToDevice, e->stream));
+    // the one shared forward of the start position (training.rs:344-350)
+    az_position sp;
+    az_position_start(&sp);
+    AZ_CUDA(e, cudaMemcpyAsync(e->d_wire, &sp, sizeof sp, cudaMemcpyHostToDevice, e->stream));
+    int r;
+    if (e->stub_kind == 1) {
+        DPos d = dpos_from_wire(sp);
+        AZ_CUDA(e, cudaMemcpyAsync(q.req_pos, &d, sizeof d, cudaMemcpyHostToDevice, e->stream));
+        k_stub_eval<<<1, 128, 0, e->stream>>>(q.req_pos, nullptr, 1, e->stub_seed, e->d_policy, e->d_value);
+        r = check_cuda(e, cudaGetLastError(), "k_stub_eval");
+    } else if (e->cfg.precision == 1) {
+        launch_encode_f32(e->stream, e->d_wire, e->d_planes, 1);
+        r = net_forward_fp32(e, e->d_planes, nullptr, 1, e->d_policy, e->d_value);
+    } else {
+        launch_encode_bf16_wire(e->stream, e->d_wire, e->net->a_in, 1);
+        r = net_forward_bf16(e, nullptr, 1, e->d_policy, e->d_value);
+    }
+    if (r) return r;
+    k_start_prior<<<1, 32, 0, e->stream>>>(e->d_policy, q.start_prior);
+    const int blocks = (n_games + WARPS - 1) / WARPS;
+    k_init_selfplay<<<blocks, WARPS * 32, 0, e->stream>>>(st->prm, st->ptr, first_game_id);
+    AZ_CUDA(e, cudaGetLastError());
+    AZ_CUDA(e, cudaStreamSynchronize(e->stream));
+    st->selfplay_active = true;
+    return AZ_OK;
+}
+
+int az_selfplay_step(az_engine* e, int waves, az_selfplay_stats* out) {
+    if (!e) return AZ_ERR_INVALID_ARGUMENT;
+    SearchState* st = e->search;
+    if (!st->selfplay_active) return set_err(e, AZ_ERR_STATE, "az_selfplay_begin has not been called");
+    cudaSetDevice(e->cfg.device);
+    for (int w = 0; w < waves; w++) {
+        int r = run_wave(e, st);
+        if (r) return r;
+    }
+    Counters c;
+    AZ_CUDA(e, cudaMemcpyAsync(&c, st->ptr.counters, sizeof c, cudaMemcpyDeviceToHost, e->stream));
+    AZ_CUDA(e, cudaStreamSynchronize(e->stream));
+    if (out) {
+        out->simulations = c.simulations; out->positions = c.positions; out->evaluations = c.evaluations; out->cache_hits = c.cache_hits;
+        out->terminal_leaves = c.terminal_leaves; out->games_finished = c.games_finished; out->sum_leaf_depth = c.sum_leaf_depth;
+        out->sum_edges = c.sum_edges; out->waves = (uint64_t)waves; out->pending_samples = std::min<unsigned long long>(c.samples_out, st->prm.sample_cap);
+    }
+    if (c.errors) return set_err(e, AZ_ERR_CAPACITY, "pool or sample-queue overflow during self-play (drain more often / raise capacities)");
+    return AZ_OK;
+}
+
+int az_selfplay_drain(az_engine* e, az_sample* out, int max_samples, int* n_out) {
+    if (!e || !n_out) return AZ_ERR_INVALID_ARGUMENT;
+    SearchState* st = e->search;
+    if (!st->selfplay_active) return set_err(e, AZ_ERR_STATE, "az_selfplay_begin has not been called");
+    cudaSetDevice(e->cfg.device);
+    Counters c;
+    AZ_CUDA(e, cudaMemcpy(&c, st->ptr.counters, sizeof c, cudaMemcpyDeviceToHost));
+    unsigned long long avail = std::min<unsigned long long>(c.samples_out, st->prm.sample_cap);
+    if (avail > (unsigned long long)max_samples) return set_err(e, AZ_ERR_CAPACITY, "drain buffer smaller than the pending sample count");
+    if (avail && out) AZ_CUDA(e, cudaMemcpy(out, st->ptr.out_samples, (size_t)avail * sizeof(az_sample), cudaMemcpyDeviceToHost));
+    unsigned long long zero = 0;
+    AZ_CUDA(e, cudaMemcpy(&st->ptr.counters->samples_out, &zero, sizeof zero, cudaMemcpyHostToDevice));
+    *n_out = (int)avail;
+    return AZ_OK;
+}
+
+}  // extern "C"

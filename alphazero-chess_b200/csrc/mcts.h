@@ -1,0 +1,89 @@
+// Device-resident PUCT search and self-play (tree.rs:25-289, training.rs:294-378).
+#pragma once
+#include "engine.h"
+#include <cuda_bf16.h>
+
+namespace azb {
+
+constexpr int HIST_CAP = 512;     // positions kept per game (a game ends by fullmove 200 => < 400 plies)
+constexpr int MAX_SAMPLE_PLIES = 512;
+
+struct __align__(16) GameCtl {
+    unsigned long long game_id;
+    uint32_t n_nodes, n_edges;
+    uint32_t sims_done, ply;
+    uint32_t hist_len;
+    int32_t pending_node;   // node waiting for its evaluation (-1 none)
+    int32_t pending_slot;
+    uint32_t path_len;      // edges on the path of the pending simulation
+    uint32_t max_depth;
+    uint32_t status;        // 0 active, 1 search finished, 2 capacity error, 3 illegal state
+    uint32_t noise_ply;
+    uint32_t flags;         // bit0: Dirichlet noise at the root
+    uint32_t n_samples;
+    uint32_t pad;
+};
+
+struct SearchParams {
+    int n_games;
+    int S;
+    float c_puct, alpha, eps;
+    uint32_t anneal;
+    int num_halfmoves, num_fullmoves, repetitions;
+    unsigned long long seed;
+    int node_cap, edge_cap;
+    int mode;        // 0: az_search (stop after S simulations), 1: self-play
+    int max_iters;   // simulations a game may complete per wave without needing the network
+    int fp32_planes; // 1: requests are written as f32 NCHW planes, 0: bf16 NHWC
+    int sample_cap;
+};
+
+struct Counters {
+    unsigned long long simulations, positions, evaluations, cache_hits, terminal_leaves, games_finished, sum_leaf_depth, sum_edges,
+        next_game_id, samples_out, errors;
+};
+
+struct SearchPtrs {
+    // nodes [G * node_cap]
+    DPos* node_pos;
+    uint32_t* node_edge_off;
+    uint16_t* node_nedges;
+    uint16_t* node_nmoves;
+    float* node_total;
+    uint16_t* node_depth;
+    // edges [G * edge_cap]
+    float* edge_P;
+    float* edge_N;
+    float* edge_W;
+    int32_t* edge_child;
+    uint32_t* edge_mv;   // wire move | policy index << 16
+    // per game
+    GameCtl* ctl;
+    uint32_t* path;      // [G][node_cap]: node | edge << 16
+    DPos* hist;          // [G][HIST_CAP]
+    // evaluation requests / results
+    int* batch_count;
+    DPos* req_pos;             // [max_batch]
+    __nv_bfloat16* req_bf16;   // [max_batch][64][64]
+    float* req_f32;            // [max_batch][19][64]
+    const float* res_policy;   // [max_batch][4096]
+    const float* res_value;    // [max_batch]
+    // self-play
+    az_sample* game_samples;   // [G][MAX_SAMPLE_PLIES]
+    az_sample* out_samples;    // [sample_cap]
+    float* start_prior;        // [32] priors of the start position's legal moves (move order)
+    Counters* counters;
+};
+
+struct SearchState {
+    SearchParams prm;
+    SearchPtrs ptr;
+    int G = 0;
+    bool selfplay_active = false;
+    std::vector<void*> allocs;
+};
+
+int search_create(az_engine* e);
+void search_destroy(az_engine* e);
+
+}  // namespace azb

@@ -1,0 +1,457 @@
+// Policy/value network of agent.rs:11-144 on the device.
+//   bf16 path : 21 tcgen05 3x3 convolutions (nn_tc.cu) + one fused head kernel
+//   fp32 path : straightforward fp32 kernels (parity mode, 1e-5 against a torch fp32 reference)
+// BatchNorm (inference form, eps = 1e-5) is folded into the preceding convolution when the weights are imported.
+#include "nn.h"
+#include "nn_tc.h"
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+namespace azb {
+
+// ---------------------------------------------------------------------------------------------- weight catalogue
+static const int kBlocks = 10;
+static int64_t weight_size(int i) {
+    if (i == 0) return 128 * 19 * 9;
+    if (i < 6) return 128;
+    i -= 6;
+    if (i < kBlocks * 12) { int j = i % 12; return (j == 0 || j == 6) ? 128 * 128 * 9 : 128; }
+    i -= kBlocks * 12;
+    static const int64_t tail[18] = {32 * 128, 32, 32, 32, 32, 32, 64 * 32, 64, 8 * 128, 8, 8, 8, 8, 8, 512 * 64, 64, 64, 1};
+    return i < 18 ? tail[i] : 0;
+}
+static std::string weight_name(int i) {
+    static const char* bn[4] = {"gamma", "beta", "running_mean", "running_var"};
+    if (i == 0) return "input_conv.weight";
+    if (i == 1) return "input_conv.bias";
+    if (i < 6) return std::string("input_bn.") + bn[i - 2];
+    i -= 6;
+    if (i < kBlocks * 12) {
+        int b = i / 12, j = i % 12;
+        std::string p = "res_blocks." + std::to_string(b) + ".";
+        int half = j / 6, k = j % 6;
+        std::string c = half ? "conv2" : "conv1", n = half ? "bn2" : "bn1";
+        if (k == 0) return p + c + ".weight";
+        if (k == 1) return p + c + ".bias";
+        return p + n + "." + bn[k - 2];
+    }
+    i -= kBlocks * 12;
+    static const char* tail[18] = {"policy_conv_1.weight", "policy_conv_1.bias", "policy_bn.gamma", "policy_bn.beta",
+                                   "policy_bn.running_mean", "policy_bn.running_var", "policy_conv_2.weight", "policy_conv_2.bias",
+                                   "value_conv.weight", "value_conv.bias", "value_bn.gamma", "value_bn.beta", "value_bn.running_mean",
+                                   "value_bn.running_var", "value_linear_1.weight", "value_linear_1.bias", "value_linear_2.weight",
+                                   "value_linear_2.bias"};
+    return i < 18 ? tail[i] : "";
+}
+
+template <class T>
+static int dmalloc(az_engine* e, T** p, size_t n) {
+    return check_cuda(e, cudaMalloc(p, n * sizeof(T)), "cudaMalloc(net)");
+}
+
+int net_create(az_engine* e) {
+    NetWeights* w = new NetWeights;
+    e->net = w;
+    w->max_boards = e->max_batch;
+    const size_t nb = (size_t)e->max_batch;
+    int r = 0;
+    r |= dmalloc(e, &w->f_w_in, 128 * 19 * 9); r |= dmalloc(e, &w->f_b_in, 128);
+    r |= dmalloc(e, &w->f_w_tower, (size_t)20 * 128 * 128 * 9); r |= dmalloc(e, &w->f_b_tower, 20 * 128);
+    r |= dmalloc(e, &w->f_w40t, 128 * 40); r |= dmalloc(e, &w->f_b40, 40);
+    r |= dmalloc(e, &w->f_wp2t, 32 * 64); r |= dmalloc(e, &w->f_bp2, 64);
+    r |= dmalloc(e, &w->f_wl1, 512 * 64); r |= dmalloc(e, &w->f_bl1, 64);
+    r |= dmalloc(e, &w->f_wl2, 64); r |= dmalloc(e, &w->f_bl2, 1);
+    r |= dmalloc(e, &w->h_w_in, 9 * 128 * 64); r |= dmalloc(e, &w->h_w_tower, (size_t)20 * 9 * 128 * 128);
+    r |= dmalloc(e, &w->a_in, nb * 64 * 64);
+    for (int i = 0; i < 3; i++) r |= dmalloc(e, &w->a_buf[i], nb * 64 * 128);
+    if (r) return AZ_ERR_OUT_OF_MEMORY;
+    cudaMemset(w->a_in, 0, nb * 64 * 64 * 2);
+    if (tc_make_act_map(&w->map_a_in, w->a_in, 64, e->max_batch)) return set_err(e, AZ_ERR_CUDA, "cuTensorMapEncodeTiled(a_in)");
+    for (int i = 0; i < 3; i++)
+        if (tc_make_act_map(&w->map_a[i], w->a_buf[i], 128, e->max_batch)) return set_err(e, AZ_ERR_CUDA, "cuTensorMapEncodeTiled(act)");
+    if (tc_make_weight_map(&w->map_w_in, w->h_w_in, 64)) return set_err(e, AZ_ERR_CUDA, "cuTensorMapEncodeTiled(w_in)");
+    for (int l = 0; l < 20; l++)
+        if (tc_make_weight_map(&w->map_w_tower[l], w->h_w_tower + (size_t)l * 9 * 128 * 128, 128))
+            return set_err(e, AZ_ERR_CUDA, "cuTensorMapEncodeTiled(w_tower)");
+    return 0;
+}
+
+void net_destroy(az_engine* e) {
+    NetWeights* w = e->net;
+    if (!w) return;
+    cudaFree(w->f_w_in); cudaFree(w->f_b_in); cudaFree(w->f_w_tower); cudaFree(w->f_b_tower); cudaFree(w->f_w40t); cudaFree(w->f_b40);
+    cudaFree(w->f_wp2t); cudaFree(w->f_bp2); cudaFree(w->f_wl1); cudaFree(w->f_bl1); cudaFree(w->f_wl2); cudaFree(w->f_bl2);
+    cudaFree(w->h_w_in); cudaFree(w->h_w_tower); cudaFree(w->a_in);
+    for (int i = 0; i < 3; i++) { cudaFree(w->a_buf[i]); cudaFree(w->g_buf[i]); }
+    delete w;
+    e->net = nullptr;
+}
+
+// fold BN(gamma, beta, mean, var) into conv (weight [co][k], bias [co])
+static void fold(const float* wt, const float* bias, const float* g, const float* b, const float* m, const float* v, int co, int k,
+                 float* w_out, float* b_out) {
+    for (int o = 0; o < co; o++) {
+        float s = g[o] / std::sqrt(v[o] + 1e-5f);
+        for (int i = 0; i < k; i++) w_out[(size_t)o * k + i] = wt[(size_t)o * k + i] * s;
+        b_out[o] = (bias[o] - m[o]) * s + b[o];
+    }
+}
+
+static int upload(az_engine* e, void* dst, const void* src, size_t bytes) {
+    return check_cuda(e, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, e->stream), "upload weights");
+}
+
+static int load_from_host(az_engine* e, const float* const* a) {
+    NetWeights* w = e->net;
+    std::vector<float> fw((size_t)128 * 128 * 9), fb(128);
+    std::vector<__nv_bfloat16> hw((size_t)9 * 128 * 128);
+    int r = 0;
+    // input conv: [128][19][3][3]
+    fold(a[0], a[1], a[2], a[3], a[4], a[5], 128, 19 * 9, fw.data(), fb.data());
+    r |= upload(e, w->f_w_in, fw.data(), 128 * 19 * 9 * 4);
+    r |= upload(e, w->f_b_in, fb.data(), 128 * 4);
+    for (int tap = 0; tap < 9; tap++)
+        for (int co = 0; co < 128; co++)
+            for (int ci = 0; ci < 64; ci++)
+                hw[((size_t)tap * 128 + co) * 64 + ci] = __float2bfloat16_rn(ci < 19 ? fw[((size_t)co * 19 + ci) * 9 + tap] : 0.0f);
+    r |= upload(e, w->h_w_in, hw.data(), 9 * 128 * 64 * 2);
+    AZ_CUDA(e, cudaStreamSynchronize(e->stream));
+    for (int l = 0; l < 20; l++) {
+        const int o = 6 + (l / 2) * 12 + (l % 2) * 6;
+        fold(a[o], a[o + 1], a[o + 2], a[o + 3], a[o + 4], a[o + 5], 128, 128 * 9, fw.data(), fb.data());
+        r |= upload(e, w->f_w_tower + (size_t)l * 128 * 128 * 9, fw.data(), (size_t)128 * 128 * 9 * 4);
+        r |= upload(e, w->f_b_tower + l * 128, fb.data(), 128 * 4);
+        for (int tap = 0; tap < 9; tap++)
+            for (int co = 0; co < 128; co++)
+                for (int ci = 0; ci < 128; ci++)
+                    hw[((size_t)tap * 128 + co) * 128 + ci] = __float2bfloat16_rn(fw[((size_t)co * 128 + ci) * 9 + tap]);
+        r |= upload(e, w->h_w_tower + (size_t)l * 9 * 128 * 128, hw.data(), (size_t)9 * 128 * 128 * 2);
+        AZ_CUDA(e, cudaStreamSynchronize(e->stream));
+    }
+    const int h = 6 + kBlocks * 12;
+    std::vector<float> w40(40 * 128), b40(40), w40t(128 * 40), wp2t(32 * 64);
+    fold(a[h], a[h + 1], a[h + 2], a[h + 3], a[h + 4], a[h + 5], 32, 128, w40.data(), b40.data());
+    fold(a[h + 8], a[h + 9], a[h + 10], a[h + 11], a[h + 12], a[h + 13], 8, 128, w40.data() + 32 * 128, b40.data() + 32);
+    for (int o = 0; o < 40; o++) for (int c = 0; c < 128; c++) w40t[c * 40 + o] = w40[o * 128 + c];
+    for (int o = 0; o < 64; o++) for (int c = 0; c < 32; c++) wp2t[c * 64 + o] = a[h + 6][o * 32 + c];
+    r |= upload(e, w->f_w40t, w40t.data(), 128 * 40 * 4); r |= upload(e, w->f_b40, b40.data(), 40 * 4);
+    r |= upload(e, w->f_wp2t, wp2t.data(), 32 * 64 * 4); r |= upload(e, w->f_bp2, a[h + 7], 64 * 4);
+    r |= upload(e, w->f_wl1, a[h + 14], 512 * 64 * 4); r |= upload(e, w->f_bl1, a[h + 15], 64 * 4);
+    r |= upload(e, w->f_wl2, a[h + 16], 64 * 4); r |= upload(e, w->f_bl2, a[h + 17], 4);
+    AZ_CUDA(e, cudaStreamSynchronize(e->stream));
+    if (r) return AZ_ERR_CUDA;
+    w->loaded = true;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- plane converters
+__global__ void k_planes_to_bf16(const float* __restrict__ planes, __nv_bfloat16* __restrict__ out, int n) {
+    // out [n][64 sq][64 ch]; one thread per (board, square, 8-channel chunk)
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)n * 512) return;
+    const int b = (int)(i >> 9), sq = (int)((i >> 3) & 63), chunk = (int)(i & 7);
+    uint32_t packed[4] = {0, 0, 0, 0};
+    if (chunk < 3) {
+        for (int j = 0; j < 8; j++) {
+            int c = chunk * 8 + j;
+            float v = c < AZ_NUM_PLANES ? planes[((size_t)b * AZ_NUM_PLANES + c) * 64 + sq] : 0.0f;
+            __nv_bfloat16 h = __float2bfloat16_rn(v);
+            packed[j >> 1] |= (uint32_t)(*reinterpret_cast<unsigned short*>(&h)) << ((j & 1) * 16);
+        }
+    }
+    reinterpret_cast<uint4*>(out)[i] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+}
+void launch_planes_to_bf16(cudaStream_t s, const float* planes, __nv_bfloat16* out, int n) {
+    if (n > 0) k_planes_to_bf16<<<(unsigned)(((size_t)n * 512 + 255) / 256), 256, 0, s>>>(planes, out, n);
+}
+__global__ void k_encode_bf16_wire(const az_position* __restrict__ wire, __nv_bfloat16* __restrict__ out, int n) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n) return;
+    DPos p = dpos_from_wire(wire[warp]);
+    encode_bf16_warp(p, out + (size_t)warp * 4096, lane);
+}
+void launch_encode_bf16_wire(cudaStream_t s, const az_position* wire, __nv_bfloat16* out, int n) {
+    if (n > 0) k_encode_bf16_wire<<<(n + 3) / 4, 128, 0, s>>>(wire, out, n);
+}
+
+// ---------------------------------------------------------------------------------------------- fp32 convolution
+// NCHW fp32 3x3 same conv + bias (+residual) (+relu); one block per board, thread = (pixel, group of 32 out channels)
+template <int CIN>
+__global__ void __launch_bounds__(256) k_conv3x3_f32(const float* __restrict__ in, const float* __restrict__ wgt, const float* __restrict__ bias,
+                                                     const float* __restrict__ residual, float* __restrict__ out, const int* __restrict__ n_dev,
+                                                     int n_static, int relu) {
+    extern __shared__ float xs[];  // [CIN][64]
+    const int n = n_dev ? *n_dev : n_static;
+    const int b = blockIdx.x;
+    if (b >= n) return;
+    for (int i = threadIdx.x; i < CIN * 64; i += 256) xs[i] = in[(size_t)b * CIN * 64 + i];
+    __syncthreads();
+    const int px = threadIdx.x & 63, cobase = (threadIdx.x >> 6) * 32;
+    const int r = px >> 3, f = px & 7;
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) acc[j] = bias[cobase + j];
+    for (int ci = 0; ci < CIN; ci++) {
+#pragma unroll
+        for (int tap = 0; tap < 9; tap++) {
+            const int rr = r + tap / 3 - 1, ff = f + tap % 3 - 1;
+            const float x = (rr >= 0 && rr < 8 && ff >= 0 && ff < 8) ? xs[ci * 64 + rr * 8 + ff] : 0.0f;
+            const float* wp = wgt + ((size_t)cobase * CIN + ci) * 9 + tap;
+#pragma unroll
+            for (int j = 0; j < 32; j++) acc[j] = fmaf(__ldg(wp + (size_t)j * CIN * 9), x, acc[j]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        const size_t o = ((size_t)b * 128 + cobase + j) * 64 + px;
+        float v = acc[j];
+        if (residual) v += residual[o];
+        if (relu) v = fmaxf(v, 0.0f);
+        out[o] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- heads
+// One block (256 threads) per board: policy_conv_1+bn+relu and value_conv+bn+relu (40 x 128 per square),
+// policy_conv_2 (64 x 32 per square), softmax over the 4096 logits, value MLP + tanh (agent.rs:124-141).
+// IN_BF16: tower output NHWC bf16 [b][64][128]; otherwise NCHW f32 [b][128][64].
+constexpr int HEAD_SMEM = (128 * 65 + 128 * 40 + 40 * 64 + 64) * 4;
+
+template <bool IN_BF16, bool PRECISE>
+__global__ void __launch_bounds__(256) k_heads(const void* __restrict__ tower, const float* __restrict__ w40t, const float* __restrict__ b40,
+                                               const float* __restrict__ wp2t, const float* __restrict__ bp2, const float* __restrict__ wl1,
+                                               const float* __restrict__ bl1, const float* __restrict__ wl2, const float* __restrict__ bl2,
+                                               float* __restrict__ policy_out, float* __restrict__ value_out, const int* __restrict__ n_dev,
+                                               int n_static) {
+    extern __shared__ float sm[];
+    float* xs = sm;                  // [128][65] channel-major (padded); later reused as logits[4096]
+    float* wts = xs + 128 * 65;      // [128][40]
+    float* hs = wts + 128 * 40;      // [40][64] : rows 0-31 policy hidden, 32-39 value hidden (flatten index c*64+sq)
+    float* red = hs + 40 * 64;       // [64] scratch
+    const int n = n_dev ? *n_dev : n_static;
+    const int b = blockIdx.x;
+    if (b >= n) return;
+    const int t = threadIdx.x;
+    if (IN_BF16) {
+        const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(tower) + (size_t)b * 64 * 128;
+        for (int i = t; i < 64 * 64; i += 256) {  // pairs of channels
+            const int sq = i >> 6, c2 = (i & 63) * 2;
+            __nv_bfloat162 v = reinterpret_cast<const __nv_bfloat162*>(src)[i];
+            xs[c2 * 65 + sq] = __low2float(v);
+            xs[(c2 + 1) * 65 + sq] = __high2float(v);
+        }
+    } else {
+        const float* src = reinterpret_cast<const float*>(tower) + (size_t)b * 128 * 64;
+        for (int i = t; i < 128 * 64; i += 256) xs[(i >> 6) * 65 + (i & 63)] = src[i];
+    }
+    for (int i = t; i < 128 * 40; i += 256) wts[i] = w40t[i];
+    __syncthreads();
+    {   // stage 1: 40 outputs per square; thread = (square, group of 10 outputs)
+        const int sq = t & 63, og = (t >> 6) * 10;
+        float acc[10];
+#pragma unroll
+        for (int j = 0; j < 10; j++) acc[j] = b40[og + j];
+        for (int c = 0; c < 128; c++) {
+            const float x = xs[c * 65 + sq];
+#pragma unroll
+            for (int j = 0; j < 10; j++) acc[j] = fmaf(wts[c * 40 + og + j], x, acc[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 10; j++) hs[(og + j) * 64 + sq] = fmaxf(acc[j], 0.0f);
+    }
+    __syncthreads();
+    float* logits = xs;  // tower tile no longer needed
+    float lmax = -INFINITY;
+    {   // stage 2: logits[co*64+sq], thread = (square, 16 output channels)
+        const int sq = t & 63, cg = (t >> 6) * 16;
+        float acc[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) acc[j] = bp2[cg + j];
+        for (int k = 0; k < 32; k++) {
+            const float x = hs[k * 64 + sq];
+#pragma unroll
+            for (int j = 0; j < 16; j++) acc[j] = fmaf(__ldg(wp2t + k * 64 + cg + j), x, acc[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j++) { logits[(cg + j) * 64 + sq] = acc[j]; lmax = fmaxf(lmax, acc[j]); }
+    }
+    // block max
+    for (int d = 16; d; d >>= 1) lmax = fmaxf(lmax, __shfl_xor_sync(0xffffffffu, lmax, d));
+    if ((t & 31) == 0) red[t >> 5] = lmax;
+    __syncthreads();
+    float gmax = red[0];
+#pragma unroll
+    for (int i = 1; i < 8; i++) gmax = fmaxf(gmax, red[i]);
+    __syncthreads();
+    float lsum = 0.0f;
+    for (int i = t; i < 4096; i += 256) {
+        float ev = PRECISE ? expf(logits[i] - gmax) : __expf(logits[i] - gmax);
+        logits[i] = ev;
+        lsum += ev;
+    }
+    for (int d = 16; d; d >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, d);
+    if ((t & 31) == 0) red[8 + (t >> 5)] = lsum;
+    __syncthreads();
+    float gsum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) gsum += red[8 + i];
+    if (policy_out) {
+        float* po = policy_out + (size_t)b * 4096;
+        for (int i = t; i < 4096; i += 256) po[i] = __fdiv_rn(logits[i], gsum);
+    }
+    // value head: hidden[t] for t < 64
+    if (t < 64) {
+        float acc = bl1[t];
+        const float* v1 = hs + 32 * 64;  // [8][64] flattened c*64+sq
+        for (int i = 0; i < 512; i++) acc = fmaf(v1[i], __ldg(wl1 + i * 64 + t), acc);
+        acc = fmaxf(acc, 0.0f) * wl2[t];
+        for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+        if ((t & 31) == 0) red[16 + (t >> 5)] = acc;
+    }
+    __syncthreads();
+    if (t == 0) value_out[b] = tanhf(red[16] + red[17] + bl2[0]);
+}
+
+template <bool IN_BF16, bool PRECISE>
+static int launch_heads(az_engine* e, const void* tower, const int* n_dev, int n_static, int grid, float* policy_out, float* value_out) {
+    NetWeights* w = e->net;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_heads<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HEAD_SMEM);
+        cudaFuncSetAttribute(k_heads<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HEAD_SMEM);
+        cudaFuncSetAttribute(k_heads<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HEAD_SMEM);
+        attr = true;
+    }
+    if (grid <= 0) return 0;
+    k_heads<IN_BF16, PRECISE><<<grid, 256, HEAD_SMEM, e->stream>>>(tower, w->f_w40t, w->f_b40, w->f_wp2t, w->f_bp2, w->f_wl1, w->f_bl1,
+                                                                  w->f_wl2, w->f_bl2, policy_out, value_out, n_dev, n_static);
+    return check_cuda(e, cudaGetLastError(), "k_heads");
+}
+
+int net_forward_bf16(az_engine* e, const int* n_dev, int n_static, float* policy_out, float* value_out) {
+    NetWeights* w = e->net;
+    if (!w->loaded) return set_err(e, AZ_ERR_NO_WEIGHTS, "az_load_weights has not been called");
+    const int grid = e->sm_count & ~1;
+    int r = tc_conv3x3_launch(e->stream, &w->map_a_in, &w->map_w_in, 64, w->f_b_in, nullptr, w->a_buf[0], n_dev, n_static, 1, grid);
+    if (r) return set_err(e, AZ_ERR_CUDA, "tc conv (input) launch failed");
+    int x = 0;  // buffer holding the block input
+    for (int blk = 0; blk < 10; blk++) {
+        const int y = (x + 1) % 3, z = (x + 2) % 3;
+        r = tc_conv3x3_launch(e->stream, &w->map_a[x], &w->map_w_tower[2 * blk], 128, w->f_b_tower + (2 * blk) * 128, nullptr, w->a_buf[y],
+                              n_dev, n_static, 1, grid);
+        if (r) return set_err(e, AZ_ERR_CUDA, "tc conv launch failed");
+        r = tc_conv3x3_launch(e->stream, &w->map_a[y], &w->map_w_tower[2 * blk + 1], 128, w->f_b_tower + (2 * blk + 1) * 128, w->a_buf[x],
+                              w->a_buf[z], n_dev, n_static, 1, grid);
+        if (r) return set_err(e, AZ_ERR_CUDA, "tc conv launch failed");
+        x = z;
+    }
+    const int hgrid = n_dev ? w->max_boards : n_static;
+    return launch_heads<true, false>(e, w->a_buf[x], n_dev, n_static, hgrid, policy_out, value_out);
+}
+
+int net_forward_fp32(az_engine* e, const float* planes, const int* n_dev, int n_static, float* policy_out, float* value_out) {
+    NetWeights* w = e->net;
+    if (!w->loaded) return set_err(e, AZ_ERR_NO_WEIGHTS, "az_load_weights has not been called");
+    for (int i = 0; i < 3; i++)
+        if (!w->g_buf[i]) AZ_CUDA(e, cudaMalloc(&w->g_buf[i], (size_t)w->max_boards * 128 * 64 * sizeof(float)));
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(k_conv3x3_f32<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 64 * 4); attr = true; }
+    const int grid = n_dev ? w->max_boards : n_static;
+    if (grid <= 0) return 0;
+    k_conv3x3_f32<19><<<grid, 256, 19 * 64 * 4, e->stream>>>(planes, w->f_w_in, w->f_b_in, nullptr, w->g_buf[0], n_dev, n_static, 1);
+    int x = 0;
+    for (int blk = 0; blk < 10; blk++) {
+        const int y = (x + 1) % 3, z = (x + 2) % 3;
+        k_conv3x3_f32<128><<<grid, 256, 128 * 64 * 4, e->stream>>>(w->g_buf[x], w->f_w_tower + (size_t)(2 * blk) * 128 * 128 * 9,
+                                                                  w->f_b_tower + (2 * blk) * 128, nullptr, w->g_buf[y], n_dev, n_static, 1);
+        k_conv3x3_f32<128><<<grid, 256, 128 * 64 * 4, e->stream>>>(w->g_buf[y], w->f_w_tower + (size_t)(2 * blk + 1) * 128 * 128 * 9,
+                                                                  w->f_b_tower + (2 * blk + 1) * 128, w->g_buf[x], w->g_buf[z], n_dev,
+                                                                  n_static, 1);
+        x = z;
+    }
+    AZ_CUDA(e, cudaGetLastError());
+    return launch_heads<false, true>(e, w->g_buf[x], n_dev, n_static, grid, policy_out, value_out);
+}
+
+}  // namespace azb
+
+using namespace azb;
+
+extern "C" {
+
+const char* az_weight_name(int i) {
+    static std::string names[AZ_NUM_WEIGHT_ARRAYS];
+    if (i < 0 || i >= AZ_NUM_WEIGHT_ARRAYS) return "";
+    if (names[i].empty()) names[i] = weight_name(i);
+    return names[i].c_str();
+}
+int64_t az_weight_size(int i) { return (i < 0 || i >= AZ_NUM_WEIGHT_ARRAYS) ? 0 : weight_size(i); }
+
+int az_load_weights(az_engine* e, const float* const* arrays, int n_arrays) {
+    if (!e || !arrays) return AZ_ERR_INVALID_ARGUMENT;
+    if (n_arrays != AZ_NUM_WEIGHT_ARRAYS) return set_err(e, AZ_ERR_INVALID_ARGUMENT, "expected AZ_NUM_WEIGHT_ARRAYS tensors");
+    for (int i = 0; i < n_arrays; i++) if (!arrays[i]) return set_err(e, AZ_ERR_INVALID_ARGUMENT, "null weight tensor");
+    cudaSetDevice(e->cfg.device);
+    return load_from_host(e, arrays);
+}
+
+int az_load_weights_dev(az_engine* e, const float* const* arrays_dev, int n_arrays) {
+    if (!e || !arrays_dev) return AZ_ERR_INVALID_ARGUMENT;
+    if (n_arrays != AZ_NUM_WEIGHT_ARRAYS) return set_err(e, AZ_ERR_INVALID_ARGUMENT, "expected AZ_NUM_WEIGHT_ARRAYS tensors");
+    cudaSetDevice(e->cfg.device);
+    std::vector<std::vector<float>> host(n_arrays);
+    std::vector<const float*> ptrs(n_arrays);
+    for (int i = 0; i < n_arrays; i++) {
+        host[i].resize((size_t)weight_size(i));
+        AZ_CUDA(e, cudaMemcpy(host[i].data(), arrays_dev[i], host[i].size() * 4, cudaMemcpyDeviceToHost));
+        ptrs[i] = host[i].data();
+    }
+    return load_from_host(e, ptrs.data());
+}
+
+static int forward_common(az_engine* e, int n, float* policy_out, float* value_out) {
+    AZ_CUDA(e, cudaMemcpyAsync(policy_out, e->d_policy, (size_t)n * AZ_ACTION_SPACE * 4, cudaMemcpyDeviceToHost, e->stream));
+    AZ_CUDA(e, cudaMemcpyAsync(value_out, e->d_value, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
+    AZ_CUDA(e, cudaStreamSynchronize(e->stream));
+    return AZ_OK;
+}
+
+int az_forward_planes(az_engine* e, int n, const float* planes, float* policy_out, float* value_out) {
+    if (!e) return AZ_ERR_INVALID_ARGUMENT;
+    if (n < 0 || n > e->max_batch) return set_err(e, AZ_ERR_CAPACITY, "batch larger than az_config.max_batch");
+    if (n == 0) return AZ_OK;
+    if (!planes || !policy_out || !value_out) return set_err(e, AZ_ERR_INVALID_ARGUMENT, "null buffer");
+    cudaSetDevice(e->cfg.device);
+    AZ_CUDA(e, cudaMemcpyAsync(e->d_planes, planes, (size_t)n * AZ_NUM_PLANES * 64 * 4, cudaMemcpyHostToDevice, e->stream));
+    int r;
+    if (e->cfg.precision == 1) {
+        r = net_forward_fp32(e, e->d_planes, nullptr, n, e->d_policy, e->d_value);
+    } else {
+        launch_planes_to_bf16(e->stream, e->d_planes, e->net->a_in, n);
+        r = net_forward_bf16(e, nullptr, n, e->d_policy, e->d_value);
+    }
+    if (r) return r;
+    return forward_common(e, n, policy_out, value_out);
+}
+
+int az_forward(az_engine* e, int n, const az_position* pos, float* policy_out, float* value_out) {
+    if (!e) return AZ_ERR_INVALID_ARGUMENT;
+    if (n < 0 || n > e->max_batch) return set_err(e, AZ_ERR_CAPACITY, "batch larger than az_config.max_batch");
+    if (n == 0) return AZ_OK;
+    if (!pos || !policy_out || !value_out) return set_err(e, AZ_ERR_INVALID_ARGUMENT, "null buffer");
+    cudaSetDevice(e->cfg.device);
+    AZ_CUDA(e, cudaMemcpyAsync(e->d_wire, pos, (size_t)n * sizeof(az_position), cudaMemcpyHostToDevice, e->stream));
+    int r;
+    if (e->cfg.precision == 1) {
+        launch_encode_f32(e->stream, e->d_wire, e->d_planes, n);
+        r = net_forward_fp32(e, e->d_planes, nullptr, n, e->d_policy, e->d_value);
+    } else {
+        launch_encode_bf16_wire(e->stream, e->d_wire, e->net->a_in, n);
+        r = net_forward_bf16(e, nullptr, n, e->d_policy, e->d_value);
+    }
+    if (r) return r;
+    return forward_common(e, n, policy_out, value_out);
+}
+
+}  // extern "C"

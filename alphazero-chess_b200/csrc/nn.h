@@ -1,0 +1,76 @@
+// Policy/value network (agent.rs) on the device: weight import with BatchNorm folding, the bf16 tensor-core path
+// (tcgen05 convolutions + fused heads) and the fp32 parity path.
+#pragma once
+#include "engine.h"
+#include <cuda_bf16.h>
+
+namespace azb {
+
+struct NetWeights {
+    bool loaded = false;
+    int max_boards = 0;
+    // ---- fp32 parameters, BatchNorm folded: conv weights [co][ci][3][3], head matrices as documented in nn.cu
+    float* f_w_in = nullptr;     // [128][19][9]
+    float* f_b_in = nullptr;     // [128]
+    float* f_w_tower = nullptr;  // [20][128][128][9]
+    float* f_b_tower = nullptr;  // [20][128]
+    float* f_w40t = nullptr;     // [128][40]  policy_conv_1 (32) + value_conv (8), transposed, BN folded
+    float* f_b40 = nullptr;      // [40]
+    float* f_wp2t = nullptr;     // [32][64]   policy_conv_2 transposed
+    float* f_bp2 = nullptr;      // [64]
+    float* f_wl1 = nullptr;      // [512][64]  value_linear_1 (burn layout [d_in][d_out])
+    float* f_bl1 = nullptr;      // [64]
+    float* f_wl2 = nullptr;      // [64]
+    float* f_bl2 = nullptr;      // [1]
+    // ---- bf16 tensor-core operands: [tap][co][ci]
+    __nv_bfloat16* h_w_in = nullptr;     // [9][128][64]  (19 channels zero-padded to 64)
+    __nv_bfloat16* h_w_tower = nullptr;  // [20][9][128][128]
+    CUtensorMap map_w_in;
+    CUtensorMap map_w_tower[20];
+    // ---- activations
+    __nv_bfloat16* a_in = nullptr;       // [max_boards][64 squares][64 ch]
+    __nv_bfloat16* a_buf[3] = {nullptr, nullptr, nullptr};  // [max_boards][64][128]
+    CUtensorMap map_a_in;
+    CUtensorMap map_a[3];
+    float* g_buf[3] = {nullptr, nullptr, nullptr};          // fp32 path, NCHW [max_boards][128][64] (allocated lazily)
+};
+
+int net_create(az_engine* e);
+void net_destroy(az_engine* e);
+
+// Forward over boards whose bf16 NHWC planes are already in net->a_in (n read from n_dev when non-null).
+// policy_out [n][4096] f32 (nullable), value_out [n] f32.  Returns the buffer index holding the tower output.
+int net_forward_bf16(az_engine* e, const int* n_dev, int n_static, float* policy_out, float* value_out);
+// fp32 parity path from NCHW f32 planes [n][19][64]
+int net_forward_fp32(az_engine* e, const float* planes, const int* n_dev, int n_static, float* policy_out, float* value_out);
+// f32 NCHW planes -> bf16 NHWC (64 channels) into net->a_in
+void launch_planes_to_bf16(cudaStream_t s, const float* planes, __nv_bfloat16* out, int n);
+// positions -> bf16 NHWC planes (to_tensor fused with the layout the first convolution wants)
+void launch_encode_bf16_wire(cudaStream_t s, const az_position* wire, __nv_bfloat16* out, int n);
+
+// device helper used by the search kernels: writes the 64x64 bf16 plane tile of one position (one warp)
+#ifdef __CUDACC__
+__device__ __forceinline__ void encode_bf16_warp(const DPos& p, __nv_bfloat16* out /*[64][64]*/, int lane) {
+    const u64 occ = occupied(p);
+    const u64 ours = meta_turn(p.meta) == 0 ? p.white : occ ^ p.white;
+    const u64 theirs = occ ^ ours;
+    const int pep = pseudo_legal_ep(p);
+    // 64 squares x 8 chunks of 8 channels (16 B each); channels >= 19 are zero
+    for (int item = lane; item < 512; item += 32) {
+        const int sq = item >> 3, chunk = item & 7;
+        uint32_t packed[4] = {0, 0, 0, 0};
+        if (chunk < 3) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                int c = chunk * 8 + j;
+                float v = c < AZ_NUM_PLANES ? plane_value(p, c, sq, pep, ours, theirs) : 0.0f;
+                __nv_bfloat16 h = __float2bfloat16_rn(v);
+                packed[j >> 1] |= (uint32_t)(*reinterpret_cast<unsigned short*>(&h)) << ((j & 1) * 16);
+            }
+        }
+        reinterpret_cast<uint4*>(out)[item] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    }
+}
+#endif
+
+}  // namespace azb
