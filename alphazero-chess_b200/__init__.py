@@ -295,6 +295,42 @@ class Engine:
         return out[: n.value]
 
 
+class Profile(ctypes.Structure):
+    _fields_ = [("tower_ms", ctypes.c_double), ("tower_samples", ctypes.c_uint64), ("tower_boards", ctypes.c_uint64)]
+
+
+def _engine_measurement_methods():
+    def timer_start(self):
+        self._check(self._L.az_timer_start(self._h), "az_timer_start")
+
+    def timer_stop(self):
+        ms = ctypes.c_float(0)
+        self._check(self._L.az_timer_stop(self._h, ctypes.byref(ms)), "az_timer_stop")
+        return ms.value
+
+    def profile_enable(self, every):
+        self._check(self._L.az_profile_enable(self._h, int(every)), "az_profile_enable")
+
+    def profile_read(self):
+        p = Profile()
+        self._check(self._L.az_profile_read(self._h, ctypes.byref(p)), "az_profile_read")
+        return p
+
+    def launch_count(self):
+        self._L.az_launch_count.restype = ctypes.c_uint64
+        return int(self._L.az_launch_count(self._h))
+
+    for f in (timer_start, timer_stop, profile_enable, profile_read, launch_count):
+        setattr(Engine, f.__name__, f)
+
+
+_engine_measurement_methods()
+
+# algorithmic FLOPs of one network evaluation (2 x MAC, direct convolution)
+FLOPS_PER_EVAL = 381_272_192
+FLOPS_PER_TOWER_CONV = 2 * 64 * 128 * 1152  # one 3x3 128->128 convolution on one board
+
+
 def improved_policy(sample, num_simulations):
     """Dense EpisodeStep::improved_policy (Box<[f32; 4096]>) of a drained sample."""
     dense = np.zeros(ACTION_SPACE, np.float32)

@@ -140,6 +140,9 @@ void az_engine_destroy(az_engine* e) {
     cudaFree(e->d_value); cudaFree(e->d_scores); cudaFree(e->d_perft_count); cudaFree(e->d_perft_nodes);
     for (auto p : e->perft_pos) cudaFree(p);
     for (auto p : e->perft_root) cudaFree(p);
+    for (auto& ps : e->prof_pending) { cudaEventDestroy(ps.a); cudaEventDestroy(ps.b); }
+    if (e->prof_counts_host) cudaFreeHost(e->prof_counts_host);
+    if (e->timer0) { cudaEventDestroy(e->timer0); cudaEventDestroy(e->timer1); }
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -152,11 +155,53 @@ static int check_batch(az_engine* e, int n) {
     return 0;
 }
 
+int az_timer_start(az_engine* e) {
+    if (!e) return AZ_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(e->cfg.device);
+    if (!e->timer0) { AZ_CUDA(e, cudaEventCreate(&e->timer0)); AZ_CUDA(e, cudaEventCreate(&e->timer1)); }
+    AZ_CUDA(e, cudaEventRecord(e->timer0, e->stream));
+    return AZ_OK;
+}
+int az_timer_stop(az_engine* e, float* ms_out) {
+    if (!e || !ms_out || !e->timer0) return AZ_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(e->cfg.device);
+    AZ_CUDA(e, cudaEventRecord(e->timer1, e->stream));
+    AZ_CUDA(e, cudaEventSynchronize(e->timer1));
+    AZ_CUDA(e, cudaEventElapsedTime(ms_out, e->timer0, e->timer1));
+    return AZ_OK;
+}
+int az_profile_enable(az_engine* e, int every) {
+    if (!e || every < 0) return AZ_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(e->cfg.device);
+    if (every > 0 && !e->prof_counts_host) AZ_CUDA(e, cudaMallocHost(&e->prof_counts_host, 4096 * sizeof(int)));
+    e->prof_every = every;
+    e->prof_counter = 0;
+    return AZ_OK;
+}
+int az_profile_read(az_engine* e, az_profile* out) {
+    if (!e || !out) return AZ_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(e->cfg.device);
+    AZ_CUDA(e, cudaStreamSynchronize(e->stream));
+    for (auto& ps : e->prof_pending) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ps.a, ps.b) == cudaSuccess) {
+            e->prof_ms += ms; e->prof_samples++; e->prof_boards += (uint64_t)e->prof_counts_host[ps.slot];
+        }
+        cudaEventDestroy(ps.a); cudaEventDestroy(ps.b);
+    }
+    e->prof_pending.clear();
+    out->tower_ms = e->prof_ms; out->tower_samples = e->prof_samples; out->tower_boards = e->prof_boards;
+    e->prof_ms = 0; e->prof_samples = 0; e->prof_boards = 0;
+    return AZ_OK;
+}
+uint64_t az_launch_count(const az_engine* e) { return e ? e->n_launches : 0; }
+
 int az_movegen(az_engine* e, int n, const az_position* pos, az_move* moves_out, uint16_t* index_out, int32_t* count_out) {
     int r = check_batch(e, n);
     if (r || n == 0) return r;
     if (!pos || !moves_out || !count_out) return set_err(e, AZ_ERR_INVALID_ARGUMENT, "null buffer");
     AZ_CUDA(e, cudaMemcpyAsync(e->d_wire, pos, (size_t)n * sizeof(az_position), cudaMemcpyHostToDevice, e->stream));
+    e->n_launches++;
     launch_movegen(e->stream, e->d_wire, n, e->d_moves, index_out ? e->d_index : nullptr, e->d_count);
     AZ_CUDA(e, cudaGetLastError());
     AZ_CUDA(e, cudaMemcpyAsync(moves_out, e->d_moves, (size_t)n * AZ_MAX_MOVES * 2, cudaMemcpyDeviceToHost, e->stream));
@@ -186,6 +231,7 @@ int az_play_move(az_engine* e, int n, az_position* pos_inout, const az_position*
     AZ_CUDA(e, cudaMemcpyAsync(e->d_wire, pos_inout, (size_t)n * sizeof(az_position), cudaMemcpyHostToDevice, e->stream));
     AZ_CUDA(e, cudaMemcpyAsync(e->d_u16a, action_index, (size_t)n * 2, cudaMemcpyHostToDevice, e->stream));
     RuleParams rp{(int)e->cfg.num_halfmoves, (int)e->cfg.num_fullmoves, (int)e->cfg.repetitions};
+    e->n_launches++;
     launch_play_move(e->stream, e->d_wire, d_hist, e->d_hist_off, e->d_u16a, e->d_count, n, rp);
     AZ_CUDA(e, cudaGetLastError());
     AZ_CUDA(e, cudaMemcpyAsync(pos_inout, e->d_wire, (size_t)n * sizeof(az_position), cudaMemcpyDeviceToHost, e->stream));
@@ -200,6 +246,7 @@ int az_move_to_index(az_engine* e, int n, const az_position* pos, const az_move*
     if (!pos || !moves || !index_out) return set_err(e, AZ_ERR_INVALID_ARGUMENT, "null buffer");
     AZ_CUDA(e, cudaMemcpyAsync(e->d_wire, pos, (size_t)n * sizeof(az_position), cudaMemcpyHostToDevice, e->stream));
     AZ_CUDA(e, cudaMemcpyAsync(e->d_u16a, moves, (size_t)n * 2, cudaMemcpyHostToDevice, e->stream));
+    e->n_launches++;
     launch_move_to_index(e->stream, e->d_wire, e->d_u16a, e->d_u16b, n);
     AZ_CUDA(e, cudaGetLastError());
     AZ_CUDA(e, cudaMemcpyAsync(index_out, e->d_u16b, (size_t)n * 2, cudaMemcpyDeviceToHost, e->stream));
@@ -213,6 +260,7 @@ int az_index_to_move(az_engine* e, int n, const az_position* pos, const uint16_t
     if (!pos || !index || !moves_out) return set_err(e, AZ_ERR_INVALID_ARGUMENT, "null buffer");
     AZ_CUDA(e, cudaMemcpyAsync(e->d_wire, pos, (size_t)n * sizeof(az_position), cudaMemcpyHostToDevice, e->stream));
     AZ_CUDA(e, cudaMemcpyAsync(e->d_u16a, index, (size_t)n * 2, cudaMemcpyHostToDevice, e->stream));
+    e->n_launches++;
     launch_index_to_move(e->stream, e->d_wire, e->d_u16a, e->d_u16b, n);
     AZ_CUDA(e, cudaGetLastError());
     AZ_CUDA(e, cudaMemcpyAsync(moves_out, e->d_u16b, (size_t)n * 2, cudaMemcpyDeviceToHost, e->stream));
@@ -225,6 +273,7 @@ int az_encode(az_engine* e, int n, const az_position* pos, float* planes_out) {
     if (r || n == 0) return r;
     if (!pos || !planes_out) return set_err(e, AZ_ERR_INVALID_ARGUMENT, "null buffer");
     AZ_CUDA(e, cudaMemcpyAsync(e->d_wire, pos, (size_t)n * sizeof(az_position), cudaMemcpyHostToDevice, e->stream));
+    e->n_launches++;
     launch_encode_f32(e->stream, e->d_wire, e->d_planes, n);
     AZ_CUDA(e, cudaGetLastError());
     AZ_CUDA(e, cudaMemcpyAsync(planes_out, e->d_planes, (size_t)n * AZ_NUM_PLANES * 64 * 4, cudaMemcpyDeviceToHost, e->stream));
@@ -239,7 +288,7 @@ static int perft_level(az_engine* e, int level, size_t n, int depth_remaining) {
     if (depth_remaining == 1) {
         const size_t step = 1u << 24;
         for (size_t s = 0; s < n; s += step)
-            launch_perft_count(e->stream, e->perft_pos[level] + s, e->perft_root[level] + s, (int)std::min(step, n - s), e->d_perft_nodes);
+            e->n_launches++, launch_perft_count(e->stream, e->perft_pos[level] + s, e->perft_root[level] + s, (int)std::min(step, n - s), e->d_perft_nodes);
         AZ_CUDA(e, cudaGetLastError());
         return 0;
     }
@@ -254,6 +303,7 @@ static int perft_level(az_engine* e, int level, size_t n, int depth_remaining) {
     for (size_t s = 0; s < n; s += chunk) {
         size_t m = std::min(chunk, n - s);
         AZ_CUDA(e, cudaMemsetAsync(e->d_perft_count, 0, sizeof(unsigned long long), e->stream));
+        e->n_launches++;
         launch_perft_expand(e->stream, e->perft_pos[level] + s, e->perft_root[level] + s, (int)m, e->perft_pos[level + 1],
                             e->perft_root[level + 1], e->d_perft_count);
         AZ_CUDA(e, cudaGetLastError());

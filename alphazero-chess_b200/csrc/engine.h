@@ -47,6 +47,18 @@ struct az_engine {
     unsigned long long* d_perft_nodes = nullptr;
     size_t perft_cap = 0;
 
+    // measurement
+    uint64_t n_launches = 0;
+    cudaEvent_t timer0 = nullptr, timer1 = nullptr;
+    int prof_every = 0;
+    uint64_t prof_counter = 0;
+    struct ProfSample { cudaEvent_t a, b; int slot; };
+    std::vector<ProfSample> prof_pending;
+    int* prof_counts_host = nullptr;   // pinned ring of batch sizes
+    int prof_slot = 0;
+    double prof_ms = 0.0;
+    uint64_t prof_samples = 0, prof_boards = 0;
+
     azb::NetWeights* net = nullptr;
     azb::SearchState* search = nullptr;
     int stub_kind = 0;

@@ -759,6 +759,7 @@ static int evaluate_batch(az_engine* e, SearchState* st) {
     const SearchPtrs& q = st->ptr;
     if (e->stub_kind == 1) {
         const int warps = e->max_batch;
+        e->n_launches++;
         k_stub_eval<<<(warps + 3) / 4, 128, 0, e->stream>>>(q.req_pos, q.batch_count, 0, e->stub_seed, e->d_policy, e->d_value);
         return check_cuda(e, cudaGetLastError(), "k_stub_eval");
     }
@@ -769,6 +770,7 @@ static int evaluate_batch(az_engine* e, SearchState* st) {
 static int run_wave(az_engine* e, SearchState* st) {
     const int blocks = (st->prm.n_games + WARPS - 1) / WARPS;
     AZ_CUDA(e, cudaMemsetAsync(st->ptr.batch_count, 0, sizeof(int), e->stream));
+    e->n_launches++;
     k_advance<<<blocks, WARPS * 32, 0, e->stream>>>(st->prm, st->ptr);
     AZ_CUDA(e, cudaGetLastError());
     return evaluate_batch(e, st);
@@ -829,6 +831,7 @@ int az_search(az_engine* e, int n, const az_position* roots, const az_position* 
     }
     const int blocks = (n + WARPS - 1) / WARPS;
     AZ_CUDA(e, cudaMemsetAsync(run.ptr.batch_count, 0, 16, e->stream));
+    e->n_launches++;
     k_init_search<<<blocks, WARPS * 32, 0, e->stream>>>(run.prm, run.ptr, e->d_wire, d_hist, e->d_hist_off, d_ids, d_plies);
     AZ_CUDA(e, cudaGetLastError());
     int r = evaluate_batch(e, &run);
@@ -905,6 +908,7 @@ int az_selfplay_begin(az_engine* e, int n_games, uint64_t first_game_id) {
     if (r) return r;
     k_start_prior<<<1, 32, 0, e->stream>>>(e->d_policy, q.start_prior);
     const int blocks = (n_games + WARPS - 1) / WARPS;
+    e->n_launches += 2;
     k_init_selfplay<<<blocks, WARPS * 32, 0, e->stream>>>(st->prm, st->ptr, first_game_id);
     AZ_CUDA(e, cudaGetLastError());
     AZ_CUDA(e, cudaStreamSynchronize(e->stream));

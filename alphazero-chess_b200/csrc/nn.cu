@@ -333,8 +333,18 @@ int net_forward_bf16(az_engine* e, const int* n_dev, int n_static, float* policy
     NetWeights* w = e->net;
     if (!w->loaded) return set_err(e, AZ_ERR_NO_WEIGHTS, "az_load_weights has not been called");
     const int grid = e->sm_count & ~1;
+    e->n_launches += 22;
+    const bool sample = e->prof_every > 0 && (e->prof_counter++ % (uint64_t)e->prof_every) == 0 && e->prof_pending.size() < 4000;
+    az_engine::ProfSample ps{nullptr, nullptr, 0};
     int r = tc_conv3x3_launch(e->stream, &w->map_a_in, &w->map_w_in, 64, w->f_b_in, nullptr, w->a_buf[0], n_dev, n_static, 1, grid);
     if (r) return set_err(e, AZ_ERR_CUDA, "tc conv (input) launch failed");
+    if (sample) {
+        cudaEventCreate(&ps.a); cudaEventCreate(&ps.b);
+        ps.slot = e->prof_slot; e->prof_slot = (e->prof_slot + 1) % 4096;
+        if (n_dev) cudaMemcpyAsync(&e->prof_counts_host[ps.slot], n_dev, sizeof(int), cudaMemcpyDeviceToHost, e->stream);
+        else e->prof_counts_host[ps.slot] = n_static;
+        cudaEventRecord(ps.a, e->stream);
+    }
     int x = 0;  // buffer holding the block input
     for (int blk = 0; blk < 10; blk++) {
         const int y = (x + 1) % 3, z = (x + 2) % 3;
@@ -346,6 +356,7 @@ int net_forward_bf16(az_engine* e, const int* n_dev, int n_static, float* policy
         if (r) return set_err(e, AZ_ERR_CUDA, "tc conv launch failed");
         x = z;
     }
+    if (sample) { cudaEventRecord(ps.b, e->stream); e->prof_pending.push_back(ps); }
     const int hgrid = n_dev ? w->max_boards : n_static;
     return launch_heads<true, false>(e, w->a_buf[x], n_dev, n_static, hgrid, policy_out, value_out);
 }
@@ -359,6 +370,7 @@ int net_forward_fp32(az_engine* e, const float* planes, const int* n_dev, int n_
     if (!attr) { cudaFuncSetAttribute(k_conv3x3_f32<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 64 * 4); attr = true; }
     const int grid = n_dev ? w->max_boards : n_static;
     if (grid <= 0) return 0;
+    e->n_launches += 22;
     k_conv3x3_f32<19><<<grid, 256, 19 * 64 * 4, e->stream>>>(planes, w->f_w_in, w->f_b_in, nullptr, w->g_buf[0], n_dev, n_static, 1);
     int x = 0;
     for (int blk = 0; blk < 10; blk++) {

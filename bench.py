@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""Benchmark of the self-play hot path (BASELINE.json metric: MCTS simulations/s and self-play positions/s).
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun, one rank per GPU)
+    python bench.py --impl reference ...                       (the reference algorithm's CPU restatement on host cores)
+
+A step = one ply for every resident game: `sims` network waves, in which each of the `games` concurrent games completes
+its PUCT search of `sims` simulations (one simulation in flight per game, as the reference) and plays a move.
+Workload at N = 1: BASELINE configs[2] (4096 games x 800 sims/move, random-init net); every extra GPU adds another 4096
+games (N = 8 is configs[3], 32768 games), so scaling is weak and there is no data-path collective: NCCL only broadcasts
+the weights at the start of the timed region (one generation).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def load_pkg():
+    import importlib.util
+
+    name = "alphazero_chess_b200"
+    if name in sys.modules:
+        return sys.modules[name]
+    d = os.path.join(ROOT, "alphazero-chess_b200")
+    spec = importlib.util.spec_from_file_location(name, os.path.join(d, "__init__.py"), submodule_search_locations=[d])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) >= 8:
+                self.rows.append(parts)
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+            except ValueError:
+                continue
+            for k, nme in enumerate(names):
+                if r[4 + k].lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_port_run(weights, sims, seed, games, plies, cores, first_game_id=0):
+    """The oracle (CPU restatement of tree.rs / chess.rs / agent.rs / run_episode) on `cores` host threads: `games`
+    self-play games x `plies` plies x `sims` simulations, sharing one evaluation cache like the reference."""
+    from oracle import pyoracle as orc
+
+    net = orc.Net(weights)
+    prm = orc.make_params(num_simulations=sims, seed=seed)
+    ev = orc.make_evaluator("net", net=net)
+    cache = orc.cache_create()
+    stats = [None] * games
+    nxt = [0]
+    lock = threading.Lock()
+
+    def work():
+        while True:
+            with lock:
+                g = nxt[0]
+                nxt[0] += 1
+            if g >= games:
+                return
+            stats[g] = orc.selfplay_episode(prm, ev, game_id=first_game_id + g, max_steps=plies, cache=cache, want_visits=False)["stats"]
+
+    t0 = time.perf_counter()
+    th = [threading.Thread(target=work) for _ in range(cores)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    dt = time.perf_counter() - t0
+    orc.cache_destroy(cache)
+    sims_done = sum(s.simulations for s in stats)
+    positions = sum(s.n_steps for s in stats)
+    evals = sum(s.evals for s in stats)
+    return dict(seconds=dt, simulations=sims_done, positions=positions, evals=evals)
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own algorithm on the host cores.  The Rust reference cannot be built in this image
+    (no cargo/rustc, CUDA backend hard-coded in main.rs:68), so this arm times the oracle port (kind "port")."""
+    if rank != 0:
+        return
+    az = load_pkg()
+    cores = os.cpu_count() or 1
+    weights = az.random_weights(seed=42)
+    games, plies = cores, 1
+    sims_total, t_total = 0, 0.0
+    for step in range(args.warmup + args.steps):
+        r = cpu_port_run(weights, args.sims, 42, games, plies, cores, first_game_id=step * games)
+        if step >= args.warmup:
+            sims_total += r["simulations"]
+            t_total += r["seconds"]
+    value = sims_total / t_total if t_total > 0 else 0.0
+    sample = f"{games} games x {plies} ply x {args.sims} sims per step (one game per host thread, shared evaluation cache)"
+    line = {
+        "impl": "reference", "metric": "mcts_simulations_per_sec", "value": value, "unit": "sims/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (random-init 10x128 net, seed 42; start position)",
+        "config": {"workload": f"reference self-play restated on CPU: {sample}", "sims_per_move": args.sims},
+        "cpu_baseline": {"value": value, "unit": "sims/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+
+    az = load_pkg()
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    G, S = args.games, args.sims
+    eng = az.Engine(device=local_rank, max_games=G, num_simulations=S, seed=42)
+
+    # ---- weights: rank 0 owns them; one flat NCCL broadcast per generation, then an on-device import
+    sizes = az.weight_sizes()
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    flat = torch.zeros(int(offs[-1]), dtype=torch.float32, device=dev)
+    if rank == 0:
+        flat.copy_(torch.from_numpy(np.concatenate(az.random_weights(seed=42))))
+
+    def broadcast_and_load():
+        if dist is not None:
+            dist.broadcast(flat, src=0)
+        torch.cuda.synchronize()
+        eng.load_weights_dev([flat.data_ptr() + 4 * int(o) for o in offs[:-1]])
+
+    broadcast_and_load()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident self-play: W warm-up steps, K timed steps
+    eng.selfplay_begin(G, first_game_id=rank * (1 << 40))
+    for _ in range(args.warmup):
+        eng.selfplay_step(S)
+    st0 = eng.selfplay_step(0)
+    eng.profile_enable(16)
+    eng.profile_read()
+    sampler = ClockSampler(local_rank)
+    launches0 = eng.launch_count()
+    barrier()
+    sampler.start()
+    eng.timer_start()
+    if world > 1:
+        broadcast_and_load()  # the per-generation weight broadcast is inside the timed region
+    for _ in range(args.steps):
+        st1 = eng.selfplay_step(S)
+    ms = eng.timer_stop()
+    barrier()
+    clocks = sampler.stop()
+    launches = eng.launch_count() - launches0
+    prof = eng.profile_read()
+    eng.profile_enable(0)
+    d = {k: getattr(st1, k) - getattr(st0, k) for k in ("simulations", "positions", "evaluations", "terminal_leaves", "games_finished",
+                                                       "sum_leaf_depth", "sum_edges")}
+    eng.selfplay_drain()
+
+    # ---- end to end through the reference-facing call: MCTree::init + monte_carlo_tree_search for G host-resident roots
+    roots = np.repeat(np.array([az.start_position()], az.POSITION_DTYPE), G)
+    ids = np.arange(G, dtype=np.uint64) + rank * (1 << 40)
+    e2e_steps = max(1, args.steps // 3)
+    eng.search(roots[: min(G, 256)], num_simulations=min(S, 32), noise_game_ids=ids[: min(G, 256)])  # warm the path
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        visits, _, _ = eng.search(roots, num_simulations=S, noise_game_ids=ids)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    assert float(visits.sum()) == float(G) * S
+    h2d = roots.nbytes + ids.nbytes + 4 * G
+    d2h = visits.nbytes + 4 * G
+
+    # ---- aggregate over ranks: sums of work, max of time
+    vec = torch.tensor([d["simulations"], d["positions"], d["evaluations"], float(G * S * e2e_steps), launches, d["terminal_leaves"],
+                        d["sum_leaf_depth"], d["sum_edges"]], dtype=torch.float64, device=dev)
+    tmax = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(vec, op=dist.ReduceOp.SUM)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    vec, tmax = vec.cpu().numpy(), tmax.cpu().numpy()
+    sims, positions, evals, e2e_sims = vec[0], vec[1], vec[2], vec[3]
+    ms_all, e2e_ms = float(tmax[0]), float(tmax[1])
+
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        roof = None
+        if prof.tower_samples:
+            launch_ms = prof.tower_ms / (prof.tower_samples * 20)
+            boards = prof.tower_boards / prof.tower_samples
+            achieved = az.FLOPS_PER_TOWER_CONV * boards / (launch_ms * 1e-3) / 1e12
+            traffic = None
+            tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+            if os.path.exists(tp):
+                with open(tp) as f:
+                    traffic = json.load(f).get("conv3x3_tc_dram_bytes_per_launch")
+            roof = {"bound": "tensor", "kernel": "conv3x3_tc_kernel<2> (tcgen05 3x3 128->128 convolution, 20 of 23 launches per wave)",
+                    "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
+                    "peak_source": f"{peak_kind} bf16_tflops_sustained", "us_per_launch": launch_ms * 1e3, "boards_per_launch": boards,
+                    "flops_per_launch": az.FLOPS_PER_TOWER_CONV * boards}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            r = cpu_port_run(az.random_weights(seed=42), S, 42, cores, 1, cores)
+            cpu = {"value": r["simulations"] / r["seconds"], "unit": "sims/s", "cores": cores, "kind": "port",
+                   "sample": f"{cores} games x 1 ply x {S} sims on {cores} host threads, shared evaluation cache ({r['seconds']:.1f} s)",
+                   "positions_per_sec": r["positions"] / r["seconds"], "evals_per_sec": r["evals"] / r["seconds"]}
+        value = sims / (ms_all * 1e-3)
+        line = {
+            "metric": "mcts_simulations_per_sec", "value": value, "unit": "sims/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_all / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic (random-init 10x128 net, seed 42; games from the start position with Dirichlet noise)",
+            "config": {"workload": f"{G} concurrent games x {S} sims/move per GPU (BASELINE configs[2]; x N GPUs = configs[3] at N=8)",
+                       "games_per_gpu": G, "sims_per_move": S, "step": "one ply for every game (sims waves)",
+                       "l2": "working set (tree pools + 3 x 64 MiB activation buffers per 4096 boards) exceeds the 126 MB L2; no flush needed",
+                       "parallelism": f"games sharded {world} x {G}, no data-path collective"},
+            "positions_per_sec": positions / (ms_all * 1e-3),
+            "nn_evals_per_sec": evals / (ms_all * 1e-3),
+            "eval_avoidance_ratio": 1.0 - evals / max(sims, 1.0),
+            "mean_leaf_depth": vec[6] / max(sims, 1.0),
+            "mean_edges_per_level": vec[7] / max(vec[6], 1.0),
+            "nn_tensor_frac_whole_step": evals * az.FLOPS_PER_EVAL / (ms_all * 1e-3) / 1e12 / (peak_tf * world),
+            "e2e": {"value": e2e_sims / (e2e_ms * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "steps": e2e_steps, "api": "az_search: G host-resident roots in, dense visit counts out"},
+            "gpu_launches": int(vec[4]),
+            "clocks": clocks,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--games", type=int, default=4096, help="concurrent games per GPU")
+    ap.add_argument("--sims", type=int, default=800, help="simulations per move")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

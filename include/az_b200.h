@@ -164,6 +164,20 @@ int az_selfplay_begin(az_engine* eng, int n_games, uint64_t first_game_id);
 int az_selfplay_step(az_engine* eng, int waves, az_selfplay_stats* stats_out);
 int az_selfplay_drain(az_engine* eng, az_sample* out, int max_samples, int* n_out);
 
+/* ---- measurement hooks (bench.py) -------------------------------------------------------------------------------
+ * az_timer_*: CUDA events on the engine's own stream.  az_profile_enable(k): every k-th network forward brackets the
+ * 20 tower convolutions with events and records the batch size; az_profile_read sums what has completed. */
+typedef struct az_profile {
+    double tower_ms;        /* summed duration of the sampled 20-convolution towers */
+    uint64_t tower_samples; /* number of sampled forwards */
+    uint64_t tower_boards;  /* summed batch sizes of the sampled forwards */
+} az_profile;
+int az_timer_start(az_engine* eng);
+int az_timer_stop(az_engine* eng, float* ms_out);
+int az_profile_enable(az_engine* eng, int every_n_forwards);
+int az_profile_read(az_engine* eng, az_profile* out);
+uint64_t az_launch_count(const az_engine* eng); /* kernels launched by this engine so far */
+
 /* ---- unit-test entry points (device pointers) ------------------------------------------------------------------ */
 int az_dbg_conv3x3_tc(const void* in_bf16, int cin, const void* w_bf16, const float* bias, const void* residual,
                       void* out_bf16, int n_boards, int relu, int iters, float* ms_out);

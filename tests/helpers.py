@@ -70,3 +70,32 @@ def uci_to_wire(pos, uci):
         if (m & 63) == f and ((m >> 6) & 63) == t and ((m >> 12) & 7) == promo:
             return int(m)
     raise AssertionError(f"{uci} is not legal")
+
+
+def torch_reference_forward(arrays, planes):
+    """Plain PyTorch fp32 restatement of AlphaZero::forward (agent.rs:112-144) from the 144 burn-layout arrays."""
+    import torch
+    import torch.nn.functional as F
+
+    a = [torch.from_numpy(np.asarray(x, np.float32)) for x in arrays]
+    x = torch.from_numpy(np.asarray(planes, np.float32)).reshape(-1, 19, 8, 8)
+
+    def bn(x, i):
+        return F.batch_norm(x, a[i + 2], a[i + 3], a[i], a[i + 1], training=False, eps=1e-5)  # arrays: gamma, beta, mean, var
+
+    with torch.no_grad():
+        x = torch.relu(bn(F.conv2d(x, a[0].view(128, 19, 3, 3), a[1], padding=1), 2))
+        for b in range(10):
+            o = 6 + b * 12
+            r = x
+            y = torch.relu(bn(F.conv2d(x, a[o].view(128, 128, 3, 3), a[o + 1], padding=1), o + 2))
+            y = bn(F.conv2d(y, a[o + 6].view(128, 128, 3, 3), a[o + 7], padding=1), o + 8)
+            x = torch.relu(y + r)
+        h = 6 + 120
+        p = torch.relu(bn(F.conv2d(x, a[h].view(32, 128, 1, 1), a[h + 1]), h + 2))
+        logits = F.conv2d(p, a[h + 6].view(64, 32, 1, 1), a[h + 7]).reshape(x.shape[0], -1)
+        policy = torch.softmax(logits, 1)
+        v = torch.relu(bn(F.conv2d(x, a[h + 8].view(8, 128, 1, 1), a[h + 9]), h + 10)).reshape(x.shape[0], -1)
+        v = torch.relu(v @ a[h + 14].view(512, 64) + a[h + 15])
+        v = torch.tanh(v @ a[h + 16].view(64, 1) + a[h + 17]).squeeze(1)
+    return policy.numpy(), v.numpy()

@@ -1,0 +1,46 @@
+"""The C-ABI shared library loads without a GPU and exports every symbol include/az_b200.h declares."""
+import ctypes
+import os
+import re
+
+import alphazero_chess_b200 as az
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_every_declared_symbol_is_exported():
+    with open(os.path.join(ROOT, "include", "az_b200.h")) as f:
+        text = f.read()
+    names = sorted(set(re.findall(r"^(?:int|void|const char\*|int64_t|uint64_t)\s+(az_[a-z0-9_]+)\(", text, re.M)))
+    assert len(names) >= 25
+    L = az.lib()
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+
+
+def test_struct_layouts_and_host_helpers():
+    assert ctypes.sizeof(az.Config) == 72
+    assert az.POSITION_DTYPE.itemsize == 72 and az.SAMPLE_DTYPE.itemsize == 1120
+    c = az.default_config()
+    assert (c.num_simulations, c.temperature_annealing, c.num_halfmoves, c.num_fullmoves, c.repetitions, c.seed) == (256, 15, 100, 200, 3, 42)
+    assert abs(c.c_puct - 3.0) < 1e-7 and abs(c.dirichlet_alpha - 0.3) < 1e-7 and abs(c.dirichlet_epsilon - 0.25) < 1e-7
+    p = az.start_position()
+    assert int(p["roles"][0]) == 0x00FF00000000FF00 and p["castling"] == 15 and p["fullmoves"] == 1 and p["ep_square"] == -1
+    names, sizes = az.weight_names(), az.weight_sizes()
+    assert len(names) == 144 and names[0] == "input_conv.weight" and names[-1] == "value_linear_2.bias"
+    assert sum(sizes) == 3_024_777  # parameter count of the 10x128 network incl. BatchNorm statistics
+    w = az.random_weights(seed=1)
+    assert [a.size for a in w] == sizes
+
+
+def test_no_gpu_means_an_error_not_a_fallback():
+    import torch
+
+    if torch.cuda.is_available():
+        return
+    try:
+        az.Engine(max_games=4)
+    except az.EngineError as e:
+        assert "az_engine_create" in str(e)
+    else:
+        raise AssertionError("an engine was created without a GPU")

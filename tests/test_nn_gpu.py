@@ -1,0 +1,87 @@
+"""agent.rs forward on the GPU: fp32 path within 1e-5, bf16 tensor-core path within 1e-2 (absolute) of a plain
+PyTorch fp32 reference, on random-init weights with randomised BatchNorm statistics."""
+import numpy as np
+import pytest
+
+import alphazero_chess_b200 as az
+from helpers import orc, random_playouts, torch_reference_forward
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def weights():
+    return az.random_weights(seed=3, randomize_bn=True)
+
+
+@pytest.fixture(scope="module")
+def positions():
+    p, _ = random_playouts(200, seed=8, max_plies=100)
+    return p
+
+
+def test_fp32_path_matches_torch(weights, positions):
+    with az.Engine(max_games=256, precision=1) as e:
+        e.load_weights(weights)
+        planes = e.encode(positions)
+        pol, val = e.forward_planes(planes)
+        rp, rv = torch_reference_forward(weights, planes)
+        assert np.abs(pol - rp).max() <= 1e-5
+        assert np.abs(val - rv).max() <= 1e-5
+        assert np.allclose(pol.sum(1), 1.0, atol=1e-4)
+        pol2, val2 = e.forward(positions)  # to_tensor + forward in one call
+        assert np.array_equal(pol, pol2) and np.array_equal(val, val2)
+
+
+def test_bf16_path_matches_torch(weights, positions):
+    with az.Engine(max_games=256, precision=0) as e:
+        e.load_weights(weights)
+        planes = e.encode(positions)
+        pol, val = e.forward(positions)
+        rp, rv = torch_reference_forward(weights, planes)
+        assert np.abs(pol - rp).max() <= 1e-2
+        assert np.abs(val - rv).max() <= 1e-2
+        # the tolerance above is loose for a ~1/4096 policy; the relative error is what bf16 really costs
+        rel = np.abs(pol - rp).max() / rp.max()
+        print(f"\nbf16 path: max |dp| {np.abs(pol - rp).max():.2e} (rel to max p {rel:.2e}), max |dv| {np.abs(val - rv).max():.2e}")
+        assert rel < 0.2
+        # batch invariance: a row does not depend on what else is in the batch (needed for visit-count parity)
+        for i in (0, 1, 77, 199):
+            p1, v1 = e.forward(positions[i])
+            assert np.array_equal(p1[0], pol[i]) and v1[0] == val[i]
+        p3, v3 = e.forward(positions[5:8])
+        assert np.array_equal(p3, pol[5:8]) and np.array_equal(v3, val[5:8])
+        pp, vv = e.forward_planes(planes[:9])
+        assert np.array_equal(pp, pol[:9]) and np.array_equal(vv, val[:9])
+
+
+def test_no_weights_is_an_error(positions):
+    with az.Engine(max_games=16) as e:
+        with pytest.raises(az.EngineError):
+            e.forward(positions[:2])
+        with pytest.raises(az.EngineError):
+            e.search(positions[:2], num_simulations=4)
+
+
+def test_search_with_network_matches_oracle_given_identical_outputs(weights):
+    """Visit counts are bit-exact when the oracle's tree is fed the very outputs the GPU network produces."""
+    roots, histories = random_playouts(24, seed=31, max_plies=60)
+    keep = [i for i in range(len(roots)) if orc.outcome(roots[i]) == 0][:12]
+    with az.Engine(max_games=64, num_simulations=48, precision=0) as e:
+        e.load_weights(weights)
+
+        def cb(ctx, pos_ptr, pol_ptr, val_ptr):
+            pos = np.ctypeslib.as_array((np.ctypeslib.ctypes.c_uint8 * 72).from_address(pos_ptr)).view(az.POSITION_DTYPE)
+            p, v = e.forward(pos)
+            np.ctypeslib.as_array(pol_ptr, (4096,))[:] = p[0]
+            val_ptr[0] = float(v[0])
+
+        ev = orc.make_evaluator("callback", callback=orc.EVAL_FN(cb))
+        prm = orc.make_params(num_simulations=48)
+        r = roots[keep]
+        visits, scores, depth = e.search(r, num_simulations=48, want_scores=True)
+        for k, i in enumerate(keep):
+            v, s, d, _ = orc.search(roots[i], prm, ev)
+            assert np.array_equal(visits[k], v), k
+            assert np.array_equal(scores[k], s), k
+            assert depth[k] == d

@@ -1,0 +1,60 @@
+"""training.rs run_episode on the GPU against the oracle: with the shared synthetic evaluator and the shared counter-based
+generator the complete game records (positions, visit counts, moves, depths, back-filled values) are identical."""
+import numpy as np
+import pytest
+
+import alphazero_chess_b200 as az
+from helpers import orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _collect(e, n_games, target_games, max_waves=40000, chunk=64):
+    e.selfplay_begin(n_games, first_game_id=0)
+    samples = []
+    waves = 0
+    while waves < max_waves:
+        st = e.selfplay_step(chunk)
+        waves += chunk
+        if st.pending_samples:
+            samples.append(e.selfplay_drain())
+        if st.games_finished >= target_games:
+            break
+    return np.concatenate(samples) if samples else np.zeros(0, az.SAMPLE_DTYPE), st
+
+
+def test_selfplay_records_identical_to_oracle():
+    sims, seed, stub_seed = 24, 42, 17
+    with az.Engine(max_games=16, num_simulations=sims, seed=seed) as e:
+        e.set_evaluator_stub(1, stub_seed)
+        samples, st = _collect(e, 16, 16)
+        assert st.games_finished >= 16 and st.positions >= len(samples)
+    prm = orc.make_params(num_simulations=sims, seed=seed)
+    ev = orc.make_evaluator("stub", stub_seed=stub_seed)
+    finished = sorted(set(int(g) for g in samples["game_id"]))
+    checked = 0
+    for gid in finished[:12]:
+        rec = samples[samples["game_id"] == gid]
+        rec = rec[np.argsort(rec["ply"])]
+        ep = orc.selfplay_episode(prm, ev, game_id=gid, max_steps=512)
+        assert len(rec) == ep["stats"].n_steps, gid
+        for k in range(len(rec)):
+            assert rec[k]["position"].tobytes() == ep["positions"][k].tobytes(), (gid, k)
+            assert np.array_equal(az.improved_policy(rec[k], sims) * np.float32(sims), ep["visits"][k]), (gid, k)
+            assert rec[k]["action"] == ep["action"][k], (gid, k)
+            assert rec[k]["search_depth"] == ep["depth"][k], (gid, k)
+            assert rec[k]["final_value"] == ep["final_value"][k], (gid, k)
+        checked += 1
+    assert checked >= 8
+
+
+def test_selfplay_counters_and_network_path():
+    w = az.random_weights(seed=5)
+    with az.Engine(max_games=64, num_simulations=16) as e:
+        e.load_weights(w)
+        e.selfplay_begin(64)
+        st = e.selfplay_step(40)
+        assert st.simulations >= 64 * 30 and st.evaluations > 0
+        assert st.positions >= 64  # every game has made at least one move after 40 waves of 16-simulation searches
+        s = e.selfplay_drain()
+        assert len(s) == st.pending_samples
