@@ -14,6 +14,7 @@
 #include "nn_tc.h"
 #include <cuda_bf16.h>
 #include <cstdio>
+#include <cstdlib>
 
 namespace azb {
 
@@ -36,7 +37,7 @@ template <int HALVES>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap w_map,
                   const float* __restrict__ bias, const __nv_bfloat16* __restrict__ residual,
-                  __nv_bfloat16* __restrict__ out, const int* __restrict__ n_boards_ptr, int n_boards_static, int relu) {
+                  __nv_bfloat16* __restrict__ out, const int* __restrict__ n_boards_ptr, int n_boards_static, int relu, int dbg) {
     using S = ConvSmem<HALVES>;
     constexpr int NS = S::kStages;
     extern __shared__ uint8_t smem_raw[];
@@ -88,8 +89,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
                             }
                         }
                         mbar_wait(&empty_bar[stage], phase ^ 1, 1);
-                        mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
-                        tma_load_4d(a_sm + stage * kStageBytes, &in_map, &full_bar[stage], half * 64, dxi - 1, mt * 2, -1);
+                        if (dbg & 1) { mbar_arrive(&full_bar[stage]); }
+                        else {
+                            mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+                            tma_load_4d(a_sm + stage * kStageBytes, &in_map, &full_bar[stage], half * 64, dxi - 1, mt * 2, -1);
+                        }
                         if (++stage == NS) { stage = 0; phase ^= 1; }
                     }
                 first = false;
@@ -120,7 +124,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
                             for (int k = 0; k < 4; k++) {
                                 uint64_t ad = umma_smem_desc_sw128(a_base + dyi * 2048 + k * 32);
                                 uint64_t bd = umma_smem_desc_sw128(w_base + wt * kWTileBytes + k * 32);
-                                umma_bf16(d_tmem, ad, bd, idesc, accumulate);
+                                if (!(dbg & 2)) umma_bf16(d_tmem, ad, bd, idesc, accumulate);
                                 accumulate = 1;
                             }
                         }
@@ -141,6 +145,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
             const int board = mt * 2 + b;
             const bool valid = board < n_boards;
             const size_t off = ((size_t)board * 64 + h * 8 + w) * 128 + nhalf * 64;
+            if (dbg & 4) {
+                mbar_wait(&tfull_bar[acc], accphase, 5);
+                tc_fence_before();
+                mbar_arrive(&tempty_bar[acc]);
+                continue;
+            }
             uint4 res[8];
             if (residual != nullptr && valid) {
                 const uint4* rp = reinterpret_cast<const uint4*>(residual + off);
@@ -184,6 +194,190 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
     tc_fence_before();
     __syncthreads();
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
+}
+
+// ================================================================================================================
+// CTA-pair version (cta_group::2): the two SMs of a pair compute one 256-row tile (4 boards) against all 128 output
+// channels.  Each CTA stages its own 128 rows of A and keeps HALF of the weights (64 output channels) resident; the
+// leader CTA issues M=256 x N=128 x K=16 MMAs that read both CTAs' shared memory.  Per SM this halves the TMA traffic
+// and the shared-memory operand bandwidth of the single-CTA kernel and doubles the work per issued instruction
+// (the single-CTA kernel was bound by the issue rate of its N=64 MMAs: profiles/r1_conv_ablation.md).
+constexpr int kTmemCols2 = 256;  // 2 accumulator stages x 128 fp32 columns
+
+template <int HALVES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap w_map,
+                   const float* __restrict__ bias, const __nv_bfloat16* __restrict__ residual,
+                   __nv_bfloat16* __restrict__ out, const int* __restrict__ n_boards_ptr, int n_boards_static, int relu) {
+    using S = ConvSmem<HALVES>;
+    constexpr int NS = S::kStages;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* w_sm = smem;
+    uint8_t* a_sm = smem + S::kWBytes;
+    uint8_t* misc = a_sm + S::kABytes;
+    float* bias_s = reinterpret_cast<float*>(misc);                     // 128 floats
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(misc + 512);       // NS        (leader's copy is the live one)
+    uint64_t* empty_bar = full_bar + NS;                                // NS        (per CTA, multicast commit)
+    uint64_t* wfull_bar = empty_bar + NS;                               // kWTiles   (leader)
+    uint64_t* tfull_bar = wfull_bar + S::kWTiles;                       // 2         (per CTA, multicast commit)
+    uint64_t* tempty_bar = tfull_bar + 2;                               // 2         (leader, 8 warp arrivals)
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int n_boards = n_boards_ptr ? *n_boards_ptr : n_boards_static;
+    const int n_tiles = (n_boards + 3) >> 2;
+    const int first_tile = blockIdx.x >> 1, tile_step = gridDim.x >> 1;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&in_map);
+        tma_prefetch_desc(&w_map);
+        for (int i = 0; i < NS; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < S::kWTiles; i++) mbar_init(&wfull_bar[i], 1);
+        for (int i = 0; i < 2; i++) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
+        fence_barrier_init();
+    }
+    if (threadIdx.x >= 64) bias_s[threadIdx.x - 64] = bias[threadIdx.x - 64];
+    if (warp == 1) tmem2_alloc(tmem_ptr_s, kTmemCols2);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_s;
+
+    if (warp == 0) {
+        // ---------------------------------------------------------------- TMA producer (both CTAs, warp-uniform)
+        int stage = 0; uint32_t phase = 0; bool first = true;
+        for (int t = first_tile; t < n_tiles; t += tile_step) {
+            for (int half = 0; half < HALVES; half++)
+                for (int dxi = 0; dxi < 3; dxi++) {
+                    if (first && elect_one()) {
+                        for (int dyi = 0; dyi < 3; dyi++) {
+                            const int wt = (half * 3 + dxi) * 3 + dyi, tap = dyi * 3 + dxi;
+                            if (rank == 0) mbar_arrive_expect_tx(&wfull_bar[wt], 2 * kWTileBytes);
+                            tma2_load_2d(w_sm + wt * kWTileBytes, &w_map, &wfull_bar[wt], half * 64, tap * 128 + (int)rank * 64);
+                        }
+                    }
+                    mbar_wait(&empty_bar[stage], phase ^ 1, 11);
+                    if (elect_one()) {
+                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);
+                        tma2_load_4d(a_sm + stage * kStageBytes, &in_map, &full_bar[stage], half * 64, dxi - 1, t * 4 + (int)rank * 2, -1);
+                    }
+                    __syncwarp();
+                    if (++stage == NS) { stage = 0; phase ^= 1; }
+                }
+            first = false;
+        }
+    } else if (warp == 1) {
+        if (rank == 0) {
+            // ------------------------------------------------------------ MMA issuer (leader CTA, warp-uniform loop)
+            constexpr uint32_t idesc = umma_idesc_bf16(256, 128);
+            const uint64_t dbase = umma_desc_base_sw128();
+            const uint32_t w_lo = (smem_u32(w_sm) & 0x3FFFF) >> 4;
+            int stage = 0; uint32_t phase = 0; int lt = 0;
+            for (int t = first_tile; t < n_tiles; t += tile_step, lt++) {
+                const int acc = lt & 1; const uint32_t accphase = (lt >> 1) & 1;
+                mbar_wait(&tempty_bar[acc], accphase ^ 1, 12);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * 128;
+                for (int half = 0; half < HALVES; half++)
+                    for (int dxi = 0; dxi < 3; dxi++) {
+                        mbar_wait(&full_bar[stage], phase, 13);
+                        if (lt == 0)
+                            for (int dyi = 0; dyi < 3; dyi++) mbar_wait(&wfull_bar[(half * 3 + dxi) * 3 + dyi], 0, 14);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint32_t a_lo = (smem_u32(a_sm + stage * kStageBytes) & 0x3FFFF) >> 4;
+                            const uint32_t b_lo = w_lo + (uint32_t)((half * 3 + dxi) * 3) * (kWTileBytes >> 4);
+#pragma unroll
+                            for (int dyi = 0; dyi < 3; dyi++) {
+#pragma unroll
+                                for (int k = 0; k < 4; k++) {
+                                    const uint64_t ad = dbase | (uint64_t)(a_lo + dyi * (2048 >> 4) + k * 2);
+                                    const uint64_t bd = dbase | (uint64_t)(b_lo + dyi * (kWTileBytes >> 4) + k * 2);
+                                    umma2_bf16(d_tmem, ad, bd, idesc, (half | dxi | dyi | k) != 0 ? 1u : 0u);
+                                }
+                            }
+                            umma2_commit_mc(&empty_bar[stage]);
+                        }
+                        __syncwarp();
+                        if (++stage == NS) { stage = 0; phase ^= 1; }
+                    }
+                if (elect_one()) umma2_commit_mc(&tfull_bar[acc]);
+                __syncwarp();
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------- epilogue (4 warps = this CTA's 128 TMEM lanes)
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int h = row >> 4, b = (row >> 3) & 1, w = row & 7;
+        int lt = 0;
+        for (int t = first_tile; t < n_tiles; t += tile_step, lt++) {
+            const int acc = lt & 1; const uint32_t accphase = (lt >> 1) & 1;
+            const int board = t * 4 + (int)rank * 2 + b;
+            const bool valid = board < n_boards;
+            const size_t off = ((size_t)board * 64 + h * 8 + w) * 128;
+            const bool has_res = residual != nullptr && valid;
+            uint4 res[4];
+            if (has_res) {
+                const uint4* rp = reinterpret_cast<const uint4*>(residual + off);
+#pragma unroll
+                for (int i = 0; i < 4; i++) res[i] = __ldg(rp + i);
+            }
+            mbar_wait(&tfull_bar[acc], accphase, 15);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 128;
+#pragma unroll
+            for (int chunk = 0; chunk < 4; chunk++) {
+                uint32_t r[32];
+                tmem_ld32(taddr + chunk * 32, r);
+                uint4 res_next[4];
+                if (has_res && chunk < 3) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(residual + off + (chunk + 1) * 32);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) res_next[i] = __ldg(rp + i);
+                }
+                tmem_ld_wait();
+                if (chunk == 3) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);
+                }
+                if (valid) {
+                    uint4* op = reinterpret_cast<uint4*>(out + off + chunk * 32);
+#pragma unroll
+                    for (int v = 0; v < 4; v++) {
+                        uint32_t packed[4];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const int c = v * 8 + j * 2;
+                            float x0 = __uint_as_float(r[c]) + bias_s[chunk * 32 + c];
+                            float x1 = __uint_as_float(r[c + 1]) + bias_s[chunk * 32 + c + 1];
+                            if (residual != nullptr) {
+                                const uint32_t rr = reinterpret_cast<const uint32_t*>(&res[v])[j];
+                                x0 += __uint_as_float(rr << 16);
+                                x1 += __uint_as_float(rr & 0xFFFF0000u);
+                            }
+                            if (relu) { x0 = fmaxf(x0, 0.0f); x1 = fmaxf(x1, 0.0f); }
+                            __nv_bfloat162 pk = __floats2bfloat162_rn(x0, x1);
+                            packed[j] = *reinterpret_cast<uint32_t*>(&pk);
+                        }
+                        op[v] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                    }
+                }
+                if (chunk < 3) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) res[i] = res_next[i];
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) { tc_fence_after(); tmem2_dealloc(tmem_base, kTmemCols2); }
 }
 
 // ---------------------------------------------------------------------------------------------- host side
@@ -230,7 +424,7 @@ int tc_make_weight_map(CUtensorMap* map, const void* base, int cin) {
 }
 
 int tc_conv3x3_launch(cudaStream_t stream, const CUtensorMap* in_map, const CUtensorMap* w_map, int cin, const float* bias,
-                      const void* residual, void* out, const int* n_boards_dev, int n_boards_static, int relu, int grid) {
+                      const void* residual, void* out, const int* n_boards_dev, int n_boards_static, int relu, int grid, int dbg) {
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e1 = cudaFuncSetAttribute(conv3x3_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<1>::kTotal);
@@ -240,12 +434,32 @@ int tc_conv3x3_launch(cudaStream_t stream, const CUtensorMap* in_map, const CUte
     }
     if (grid <= 0) grid = 148;
     grid &= ~1;
+    static int variant = -1;
+    if (variant < 0) { const char* v = getenv("AZ_CONV_VARIANT"); variant = v ? atoi(v) : 2; }
+    if (variant == 2 && dbg == 0) {
+        static bool attr2 = false;
+        if (!attr2) {
+            cudaError_t e1 = cudaFuncSetAttribute(conv3x3_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<1>::kTotal);
+            cudaError_t e2 = cudaFuncSetAttribute(conv3x3_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<2>::kTotal);
+            if (e1 != cudaSuccess || e2 != cudaSuccess) return -2;
+            attr2 = true;
+        }
+        if (cin == 64)
+            conv3x3_tc2_kernel<1><<<grid, kThreads, ConvSmem<1>::kTotal, stream>>>(*in_map, *w_map, bias, (const __nv_bfloat16*)residual,
+                                                                                   (__nv_bfloat16*)out, n_boards_dev, n_boards_static, relu);
+        else if (cin == 128)
+            conv3x3_tc2_kernel<2><<<grid, kThreads, ConvSmem<2>::kTotal, stream>>>(*in_map, *w_map, bias, (const __nv_bfloat16*)residual,
+                                                                                   (__nv_bfloat16*)out, n_boards_dev, n_boards_static, relu);
+        else
+            return -3;
+        return cudaGetLastError() == cudaSuccess ? 0 : -4;
+    }
     if (cin == 64)
         conv3x3_tc_kernel<1><<<grid, kThreads, ConvSmem<1>::kTotal, stream>>>(*in_map, *w_map, bias, (const __nv_bfloat16*)residual,
-                                                                              (__nv_bfloat16*)out, n_boards_dev, n_boards_static, relu);
+                                                                              (__nv_bfloat16*)out, n_boards_dev, n_boards_static, relu, dbg);
     else if (cin == 128)
         conv3x3_tc_kernel<2><<<grid, kThreads, ConvSmem<2>::kTotal, stream>>>(*in_map, *w_map, bias, (const __nv_bfloat16*)residual,
-                                                                              (__nv_bfloat16*)out, n_boards_dev, n_boards_static, relu);
+                                                                              (__nv_bfloat16*)out, n_boards_dev, n_boards_static, relu, dbg);
     else
         return -3;
     return cudaGetLastError() == cudaSuccess ? 0 : -4;

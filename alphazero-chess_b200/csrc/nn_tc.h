@@ -10,5 +10,5 @@ int tc_make_act_map(CUtensorMap* map, const void* base, int channels, int max_bo
 int tc_make_weight_map(CUtensorMap* map, const void* base, int cin);
 // out = act( conv3x3(in) + bias (+ residual) ); the board count is read from n_boards_dev when non-null
 int tc_conv3x3_launch(cudaStream_t stream, const CUtensorMap* in_map, const CUtensorMap* w_map, int cin, const float* bias,
-                      const void* residual, void* out, const int* n_boards_dev, int n_boards_static, int relu, int grid);
+                      const void* residual, void* out, const int* n_boards_dev, int n_boards_static, int relu, int grid, int dbg = 0);
 }  // namespace azb
