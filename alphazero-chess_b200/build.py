@@ -20,6 +20,7 @@ UNITS = [
     ("mcts.cu", ["-fmad=false"]),
     ("nn.cu", []),
     ("nn_tc.cu", []),
+    ("nn_heads.cu", []),
     ("dbg.cu", []),
 ]
 

@@ -6,6 +6,7 @@
 #include "nn_tc.h"
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 #include <vector>
 
 namespace azb {
@@ -63,6 +64,7 @@ int net_create(az_engine* e) {
     r |= dmalloc(e, &w->f_wl1, 512 * 64); r |= dmalloc(e, &w->f_bl1, 64);
     r |= dmalloc(e, &w->f_wl2, 64); r |= dmalloc(e, &w->f_bl2, 1);
     r |= dmalloc(e, &w->h_w_in, 9 * 128 * 64); r |= dmalloc(e, &w->h_w_tower, (size_t)20 * 9 * 128 * 128);
+    r |= dmalloc(e, &w->h_w40, 40 * 128); r |= dmalloc(e, &w->h_wp2, 64 * 32); r |= dmalloc(e, &w->h_wl1t, 64 * 512);
     r |= dmalloc(e, &w->a_in, nb * 64 * 64);
     for (int i = 0; i < 3; i++) r |= dmalloc(e, &w->a_buf[i], nb * 64 * 128);
     if (r) return AZ_ERR_OUT_OF_MEMORY;
@@ -82,7 +84,7 @@ void net_destroy(az_engine* e) {
     if (!w) return;
     cudaFree(w->f_w_in); cudaFree(w->f_b_in); cudaFree(w->f_w_tower); cudaFree(w->f_b_tower); cudaFree(w->f_w40t); cudaFree(w->f_b40);
     cudaFree(w->f_wp2t); cudaFree(w->f_bp2); cudaFree(w->f_wl1); cudaFree(w->f_bl1); cudaFree(w->f_wl2); cudaFree(w->f_bl2);
-    cudaFree(w->h_w_in); cudaFree(w->h_w_tower); cudaFree(w->a_in);
+    cudaFree(w->h_w_in); cudaFree(w->h_w_tower); cudaFree(w->a_in); cudaFree(w->h_w40); cudaFree(w->h_wp2); cudaFree(w->h_wl1t);
     for (int i = 0; i < 3; i++) { cudaFree(w->a_buf[i]); cudaFree(w->g_buf[i]); }
     delete w;
     e->net = nullptr;
@@ -139,6 +141,12 @@ static int load_from_host(az_engine* e, const float* const* a) {
     r |= upload(e, w->f_wp2t, wp2t.data(), 32 * 64 * 4); r |= upload(e, w->f_bp2, a[h + 7], 64 * 4);
     r |= upload(e, w->f_wl1, a[h + 14], 512 * 64 * 4); r |= upload(e, w->f_bl1, a[h + 15], 64 * 4);
     r |= upload(e, w->f_wl2, a[h + 16], 64 * 4); r |= upload(e, w->f_bl2, a[h + 17], 4);
+    std::vector<__nv_bfloat16> hw40(40 * 128), hwp2(64 * 32), hwl1t(64 * 512);
+    for (int i = 0; i < 40 * 128; i++) hw40[i] = __float2bfloat16_rn(w40[i]);
+    for (int i = 0; i < 64 * 32; i++) hwp2[i] = __float2bfloat16_rn(a[h + 6][i]);
+    for (int o = 0; o < 64; o++) for (int i = 0; i < 512; i++) hwl1t[o * 512 + i] = __float2bfloat16_rn(a[h + 14][i * 64 + o]);
+    r |= upload(e, w->h_w40, hw40.data(), 40 * 128 * 2); r |= upload(e, w->h_wp2, hwp2.data(), 64 * 32 * 2);
+    r |= upload(e, w->h_wl1t, hwl1t.data(), 64 * 512 * 2);
     AZ_CUDA(e, cudaStreamSynchronize(e->stream));
     if (r) return AZ_ERR_CUDA;
     w->loaded = true;
@@ -357,6 +365,9 @@ int net_forward_bf16(az_engine* e, const int* n_dev, int n_static, float* policy
         x = z;
     }
     if (sample) { cudaEventRecord(ps.b, e->stream); e->prof_pending.push_back(ps); }
+    static int heads_variant = -1;
+    if (heads_variant < 0) { const char* v = getenv("AZ_HEADS_VARIANT"); heads_variant = v ? atoi(v) : 1; }
+    if (heads_variant == 1) return launch_heads_mma(e, w->a_buf[x], n_dev, n_static, policy_out, value_out);
     const int hgrid = n_dev ? w->max_boards : n_static;
     return launch_heads<true, false>(e, w->a_buf[x], n_dev, n_static, hgrid, policy_out, value_out);
 }

@@ -25,6 +25,9 @@ struct NetWeights {
     // ---- bf16 tensor-core operands: [tap][co][ci]
     __nv_bfloat16* h_w_in = nullptr;     // [9][128][64]  (19 channels zero-padded to 64)
     __nv_bfloat16* h_w_tower = nullptr;  // [20][9][128][128]
+    __nv_bfloat16* h_w40 = nullptr;      // [40][128]  heads stage 1 (policy_conv_1 | value_conv), BN folded
+    __nv_bfloat16* h_wp2 = nullptr;      // [64][32]   policy_conv_2
+    __nv_bfloat16* h_wl1t = nullptr;     // [64][512]  value_linear_1 transposed
     CUtensorMap map_w_in;
     CUtensorMap map_w_tower[20];
     // ---- activations
@@ -43,6 +46,8 @@ void net_destroy(az_engine* e);
 int net_forward_bf16(az_engine* e, const int* n_dev, int n_static, float* policy_out, float* value_out);
 // fp32 parity path from NCHW f32 planes [n][19][64]
 int net_forward_fp32(az_engine* e, const float* planes, const int* n_dev, int n_static, float* policy_out, float* value_out);
+// fused heads on warp-level tensor-core MMAs (nn_heads.cu); tower = NHWC bf16 [n][64][128]
+int launch_heads_mma(az_engine* e, const __nv_bfloat16* tower, const int* n_dev, int n_static, float* policy_out, float* value_out);
 // f32 NCHW planes -> bf16 NHWC (64 channels) into net->a_in
 void launch_planes_to_bf16(cudaStream_t s, const float* planes, __nv_bfloat16* out, int n);
 // positions -> bf16 NHWC planes (to_tensor fused with the layout the first convolution wants)

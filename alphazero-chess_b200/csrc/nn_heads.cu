@@ -1,0 +1,191 @@
+// Policy and value heads of agent.rs:124-141 for the bf16 path, fused into one kernel on warp-level tensor-core MMAs:
+//   stage 1  [64 squares x 128 ch] x [128 x 40]   policy_conv_1 (32) and value_conv (8), BatchNorm folded, ReLU
+//   stage 2  [64 co x 32] x [32 x 64 squares]     policy_conv_2, kept transposed so that logits land as [co][square]
+//   softmax over the 4096 logits in registers (one warp owns one board), probabilities written as 32-byte sectors
+//   value    [8 boards x 512] x [512 x 64] -> ReLU -> 64 -> 1 -> tanh, one board group per block
+// The heads are 0.3 % of the network's FLOPs; they use mma.sync (one warp per board needs no shared-memory staging of
+// the activations) while the 99 % in the tower runs on tcgen05 (nn_tc.cu).
+#include "nn.h"
+#include <algorithm>
+
+namespace azb {
+
+constexpr int HW40_PITCH = 136;  // bf16 elements per row of W40 in shared memory (128 + 8: conflict-free fragment loads)
+constexpr int HW2_PITCH = 40;    // 32 + 8
+constexpr int HV1_PITCH = 520;   // 512 + 8
+
+__device__ __forceinline__ void mma_bf16_16816(float* d, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&p);
+}
+
+__global__ void __launch_bounds__(256, 1)
+k_heads_mma(const __nv_bfloat16* __restrict__ tower, const __nv_bfloat16* __restrict__ w40, const float* __restrict__ b40,
+            const __nv_bfloat16* __restrict__ wp2, const float* __restrict__ bp2, const __nv_bfloat16* __restrict__ wl1t,
+            const float* __restrict__ bl1, const float* __restrict__ wl2, const float* __restrict__ bl2, float* __restrict__ policy_out,
+            float* __restrict__ value_out, const int* __restrict__ n_dev, int n_static) {
+    __shared__ __align__(16) __nv_bfloat16 s_w40[40 * HW40_PITCH];
+    __shared__ __align__(16) __nv_bfloat16 s_w2[64 * HW2_PITCH];
+    __shared__ __align__(16) __nv_bfloat16 s_v1[8 * HV1_PITCH];
+    __shared__ float s_b40[40], s_b2[64], s_vsum[8][8];
+    const int n = n_dev ? *n_dev : n_static;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31, g = lane >> 2, tig = lane & 3;
+    for (int i = t; i < 40 * 128; i += 256) s_w40[(i >> 7) * HW40_PITCH + (i & 127)] = w40[i];
+    for (int i = t; i < 64 * 32; i += 256) s_w2[(i >> 5) * HW2_PITCH + (i & 31)] = wp2[i];
+    if (t < 40) s_b40[t] = b40[t];
+    if (t < 64) s_b2[t] = bp2[t];
+    __syncthreads();
+
+    for (int base = blockIdx.x * 8; base < n; base += gridDim.x * 8) {
+        const int b = base + warp;
+        const bool active = b < n;
+        if (active) {
+            // ---------------- stage 1: D1[square][40]
+            float d1[4][5][4];
+#pragma unroll
+            for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+                for (int nt = 0; nt < 5; nt++)
+#pragma unroll
+                    for (int i = 0; i < 4; i++) d1[mt][nt][i] = 0.0f;
+            const uint32_t* X = reinterpret_cast<const uint32_t*>(tower + (size_t)b * 64 * 128);  // [square][64 pairs]
+#pragma unroll 2
+            for (int ks = 0; ks < 8; ks++) {
+                uint32_t bf[5][2];
+#pragma unroll
+                for (int nt = 0; nt < 5; nt++) {
+                    const uint32_t* wp = reinterpret_cast<const uint32_t*>(s_w40 + (nt * 8 + g) * HW40_PITCH + ks * 16 + tig * 2);
+                    bf[nt][0] = wp[0];
+                    bf[nt][1] = wp[4];
+                }
+#pragma unroll
+                for (int mt = 0; mt < 4; mt++) {
+                    const uint32_t* xp = X + (mt * 16 + g) * 64 + ks * 8 + tig;
+                    const uint32_t a0 = __ldg(xp), a1 = __ldg(xp + 8 * 64), a2 = __ldg(xp + 4), a3 = __ldg(xp + 8 * 64 + 4);
+#pragma unroll
+                    for (int nt = 0; nt < 5; nt++) mma_bf16_16816(d1[mt][nt], a0, a1, a2, a3, bf[nt][0], bf[nt][1]);
+                }
+            }
+            // bias + ReLU; value hidden (columns 32..39) to shared memory as the flattened [c*64 + square] row
+#pragma unroll
+            for (int mt = 0; mt < 4; mt++) {
+#pragma unroll
+                for (int nt = 0; nt < 5; nt++) {
+                    const float bb0 = s_b40[nt * 8 + tig * 2], bb1 = s_b40[nt * 8 + tig * 2 + 1];
+                    d1[mt][nt][0] = fmaxf(d1[mt][nt][0] + bb0, 0.0f);
+                    d1[mt][nt][1] = fmaxf(d1[mt][nt][1] + bb1, 0.0f);
+                    d1[mt][nt][2] = fmaxf(d1[mt][nt][2] + bb0, 0.0f);
+                    d1[mt][nt][3] = fmaxf(d1[mt][nt][3] + bb1, 0.0f);
+                }
+                __nv_bfloat16* vr = s_v1 + warp * HV1_PITCH;
+                const int sq = mt * 16 + g, c = tig * 2;
+                vr[c * 64 + sq] = __float2bfloat16_rn(d1[mt][4][0]);
+                vr[(c + 1) * 64 + sq] = __float2bfloat16_rn(d1[mt][4][1]);
+                vr[c * 64 + sq + 8] = __float2bfloat16_rn(d1[mt][4][2]);
+                vr[(c + 1) * 64 + sq + 8] = __float2bfloat16_rn(d1[mt][4][3]);
+            }
+            // ---------------- stage 2 (transposed): D2[co][square] = W2[co][k] * P1[square][k]
+            float d2[4][8][4];
+#pragma unroll
+            for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+                for (int nt = 0; nt < 8; nt++)
+#pragma unroll
+                    for (int i = 0; i < 4; i++) d2[mt][nt][i] = 0.0f;
+#pragma unroll
+            for (int ks = 0; ks < 2; ks++) {
+                uint32_t bfr[8][2];
+#pragma unroll
+                for (int nt = 0; nt < 8; nt++) {  // squares 8nt..8nt+7 come from D1 m-tile nt>>1, row half nt&1
+                    const int h2 = (nt & 1) * 2;
+                    bfr[nt][0] = pack_bf16(d1[nt >> 1][2 * ks][h2], d1[nt >> 1][2 * ks][h2 + 1]);
+                    bfr[nt][1] = pack_bf16(d1[nt >> 1][2 * ks + 1][h2], d1[nt >> 1][2 * ks + 1][h2 + 1]);
+                }
+#pragma unroll
+                for (int mt = 0; mt < 4; mt++) {
+                    const uint32_t* wp = reinterpret_cast<const uint32_t*>(s_w2 + (mt * 16 + g) * HW2_PITCH + ks * 16 + tig * 2);
+                    const uint32_t a0 = wp[0], a1 = wp[8 * HW2_PITCH / 2], a2 = wp[4], a3 = wp[8 * HW2_PITCH / 2 + 4];
+#pragma unroll
+                    for (int nt = 0; nt < 8; nt++) mma_bf16_16816(d2[mt][nt], a0, a1, a2, a3, bfr[nt][0], bfr[nt][1]);
+                }
+            }
+            // ---------------- softmax over the board's 4096 logits (agent.rs:130)
+            float mx = -INFINITY;
+#pragma unroll
+            for (int mt = 0; mt < 4; mt++) {
+                const float c0 = s_b2[mt * 16 + g], c1 = s_b2[mt * 16 + g + 8];
+#pragma unroll
+                for (int nt = 0; nt < 8; nt++) {
+                    d2[mt][nt][0] += c0; d2[mt][nt][1] += c0; d2[mt][nt][2] += c1; d2[mt][nt][3] += c1;
+                    mx = fmaxf(mx, fmaxf(fmaxf(d2[mt][nt][0], d2[mt][nt][1]), fmaxf(d2[mt][nt][2], d2[mt][nt][3])));
+                }
+            }
+            for (int d = 16; d; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+            float sum = 0.0f;
+#pragma unroll
+            for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+                for (int nt = 0; nt < 8; nt++)
+#pragma unroll
+                    for (int i = 0; i < 4; i++) { d2[mt][nt][i] = __expf(d2[mt][nt][i] - mx); sum += d2[mt][nt][i]; }
+            for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+            if (policy_out) {
+                const float inv = __fdividef(1.0f, sum);
+                float* po = policy_out + (size_t)b * 4096;
+#pragma unroll
+                for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+                    for (int nt = 0; nt < 8; nt++) {
+                        const int co = mt * 16 + g, sq = nt * 8 + tig * 2;
+                        *reinterpret_cast<float2*>(po + co * 64 + sq) = make_float2(d2[mt][nt][0] * inv, d2[mt][nt][1] * inv);
+                        *reinterpret_cast<float2*>(po + (co + 8) * 64 + sq) = make_float2(d2[mt][nt][2] * inv, d2[mt][nt][3] * inv);
+                    }
+            }
+        } else {
+            for (int i = lane; i < 512; i += 32) s_v1[warp * HV1_PITCH + i] = __float2bfloat16_rn(0.0f);
+        }
+        __syncthreads();
+        // ---------------- value head: hidden[board][8w..8w+7] on warp w (rows 8..15 of the M=16 tile are unused)
+        {
+            float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            const uint32_t* W = reinterpret_cast<const uint32_t*>(wl1t + (size_t)(warp * 8 + g) * 512);
+            const uint32_t* V = reinterpret_cast<const uint32_t*>(s_v1 + g * HV1_PITCH);
+#pragma unroll 4
+            for (int ks = 0; ks < 32; ks++) {
+                const uint32_t a0 = V[ks * 8 + tig], a2 = V[ks * 8 + tig + 4];
+                const uint32_t b0 = __ldg(W + ks * 8 + tig), b1 = __ldg(W + ks * 8 + tig + 4);
+                mma_bf16_16816(acc, a0, 0u, a2, 0u, b0, b1);
+            }
+            const int hn = warp * 8 + tig * 2;
+            float part = fmaxf(acc[0] + bl1[hn], 0.0f) * wl2[hn] + fmaxf(acc[1] + bl1[hn + 1], 0.0f) * wl2[hn + 1];
+            part += __shfl_xor_sync(0xffffffffu, part, 1);
+            part += __shfl_xor_sync(0xffffffffu, part, 2);
+            if (tig == 0) s_vsum[warp][g] = part;
+        }
+        __syncthreads();
+        if (t < 8 && base + t < n) {
+            float v = bl2[0];
+#pragma unroll
+            for (int w = 0; w < 8; w++) v += s_vsum[w][t];
+            value_out[base + t] = tanhf(v);
+        }
+        __syncthreads();
+    }
+}
+
+int launch_heads_mma(az_engine* e, const __nv_bfloat16* tower, const int* n_dev, int n_static, float* policy_out, float* value_out) {
+    NetWeights* w = e->net;
+    const int n_max = n_dev ? w->max_boards : n_static;
+    if (n_max <= 0) return 0;
+    const int grid = std::min((n_max + 7) / 8, e->sm_count * 2);
+    k_heads_mma<<<grid, 256, 0, e->stream>>>(tower, w->h_w40, w->f_b40, w->h_wp2, w->f_bp2, w->h_wl1t, w->f_bl1, w->f_wl2, w->f_bl2,
+                                             policy_out, value_out, n_dev, n_static);
+    return check_cuda(e, cudaGetLastError(), "k_heads_mma");
+}
+
+}  // namespace azb
