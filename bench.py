@@ -175,15 +175,16 @@ def run_ours(args, rank, world, local_rank):
     eng = az.Engine(device=local_rank, max_games=G, num_simulations=S, seed=42)
 
     # ---- weights: rank 0 owns them; one flat NCCL broadcast per generation, then an on-device import
+    from alphazero_chess_b200 import sharding
+
     sizes = az.weight_sizes()
-    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    offs = sharding.weight_offsets(sizes)
     flat = torch.zeros(int(offs[-1]), dtype=torch.float32, device=dev)
     if rank == 0:
-        flat.copy_(torch.from_numpy(np.concatenate(az.random_weights(seed=42))))
+        flat.copy_(torch.from_numpy(sharding.flatten_weights(az.random_weights(seed=42))))
 
     def broadcast_and_load():
-        if dist is not None:
-            dist.broadcast(flat, src=0)
+        sharding.broadcast_weights(flat, dist, src=0)
         torch.cuda.synchronize()
         eng.load_weights_dev([flat.data_ptr() + 4 * int(o) for o in offs[:-1]])
 
@@ -195,7 +196,7 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     # ---- device-resident self-play: W warm-up steps, K timed steps
-    eng.selfplay_begin(G, first_game_id=rank * (1 << 40))
+    eng.selfplay_begin(G, first_game_id=sharding.first_game_id(rank))
     for _ in range(args.warmup):
         eng.selfplay_step(S)
     st0 = eng.selfplay_step(0)
@@ -222,7 +223,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- end to end through the reference-facing call: MCTree::init + monte_carlo_tree_search for G host-resident roots
     roots = np.repeat(np.array([az.start_position()], az.POSITION_DTYPE), G)
-    ids = np.arange(G, dtype=np.uint64) + rank * (1 << 40)
+    ids = np.arange(G, dtype=np.uint64) + np.uint64(sharding.first_game_id(rank))
     e2e_steps = max(1, args.steps // 3)
     eng.search(roots[: min(G, 256)], num_simulations=min(S, 32), noise_game_ids=ids[: min(G, 256)])  # warm the path
     barrier()
@@ -236,13 +237,8 @@ def run_ours(args, rank, world, local_rank):
     d2h = visits.nbytes + 4 * G
 
     # ---- aggregate over ranks: sums of work, max of time
-    vec = torch.tensor([d["simulations"], d["positions"], d["evaluations"], float(G * S * e2e_steps), launches, d["terminal_leaves"],
-                        d["sum_leaf_depth"], d["sum_edges"]], dtype=torch.float64, device=dev)
-    tmax = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(vec, op=dist.ReduceOp.SUM)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    vec, tmax = vec.cpu().numpy(), tmax.cpu().numpy()
+    vec, tmax = sharding.reduce_metrics([d["simulations"], d["positions"], d["evaluations"], float(G * S * e2e_steps), launches,
+                                         d["terminal_leaves"], d["sum_leaf_depth"], d["sum_edges"]], [ms, e2e_s * 1e3], dist)
     sims, positions, evals, e2e_sims = vec[0], vec[1], vec[2], vec[3]
     ms_all, e2e_ms = float(tmax[0]), float(tmax[1])
 
@@ -259,7 +255,7 @@ def run_ours(args, rank, world, local_rank):
             if os.path.exists(tp):
                 with open(tp) as f:
                     traffic = json.load(f).get("conv3x3_tc_dram_bytes_per_launch")
-            roof = {"bound": "tensor", "kernel": "conv3x3_tc_kernel<2> (tcgen05 3x3 128->128 convolution, 20 of 23 launches per wave)",
+            roof = {"bound": "tensor", "kernel": "conv3x3_tc2_kernel<2> (tcgen05 cta_group::2 3x3 128->128 convolution, 20 of 23 launches per wave)",
                     "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
                     "peak_source": f"{peak_kind} bf16_tflops_sustained", "us_per_launch": launch_ms * 1e3, "boards_per_launch": boards,
                     "flops_per_launch": az.FLOPS_PER_TOWER_CONV * boards}

@@ -1,27 +1,8 @@
-import importlib.util
 import os
 import sys
 
-import pytest
-
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT)
-
-
-def _load_pkg():
-    """The package directory is called `alphazero-chess_b200` (not an identifier); register it as alphazero_chess_b200."""
-    name = "alphazero_chess_b200"
-    if name in sys.modules:
-        return sys.modules[name]
-    pkg_dir = os.path.join(ROOT, "alphazero-chess_b200")
-    spec = importlib.util.spec_from_file_location(name, os.path.join(pkg_dir, "__init__.py"), submodule_search_locations=[pkg_dir])
-    mod = importlib.util.module_from_spec(spec)
-    sys.modules[name] = mod
-    spec.loader.exec_module(mod)
-    return mod
-
-
-_load_pkg()
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import _pkg  # noqa: E402,F401  (registers alphazero_chess_b200)
 
 
 def pytest_configure(config):
