@@ -23,6 +23,7 @@ struct WarpShared {
     uint16_t moves[AZ_MAX_MOVES];
     uint16_t sidx[AZ_MAX_MOVES];
     DPos child;
+    DPos key;       // cache key of `child` (pseudo-legal ep, counters; no repetition bits)
     int n_moves;
     int term;       // 0 ongoing, 1 draw, 2 decisive (side to move in the child is mated)
     int has_ep;
@@ -147,7 +148,7 @@ struct Ctx {
     size_t nbase, ebase;   // first node / edge of this game
     GameCtl c;
     // statistics accumulated by lane 0
-    unsigned int st_sims, st_pos, st_evals, st_term, st_games, st_depth, st_edges;
+    unsigned int st_sims, st_pos, st_evals, st_term, st_games, st_depth, st_edges, st_hits;
 };
 
 // Expands `mv` from `parent` on lane 0: child position, its legal moves (into shared memory), mate / stalemate /
@@ -350,6 +351,61 @@ __device__ __forceinline__ void select_leaf(Ctx& x, int& leaf_node, int& leaf_ed
     }
 }
 
+
+// ------------------------------------------------------------------------------------------- evaluation cache
+__device__ __forceinline__ DPos cache_key_of(const DPos& p) {
+    DPos k = p;
+    k.meta = (p.meta & 0x1FULL) | ((u64)(pseudo_legal_ep(p) + 1) << 8) | (p.meta & (0xFFFFFFFFULL << 16));
+    return k;
+}
+__device__ __forceinline__ u64 cache_hash(const DPos& k) {
+    u64 h = splitmix64(k.pawn);
+    h = splitmix64(h ^ k.knight); h = splitmix64(h ^ k.bishop); h = splitmix64(h ^ k.rook); h = splitmix64(h ^ k.queen);
+    h = splitmix64(h ^ k.king); h = splitmix64(h ^ k.white); h = splitmix64(h ^ k.meta);
+    return h;
+}
+__device__ __forceinline__ bool cache_key_equal(const CacheEntry* e, const DPos* key, int lane) {
+    bool eq = true;
+    if (lane < 8) eq = reinterpret_cast<const volatile u64*>(&e->key)[lane] == reinterpret_cast<const u64*>(key)[lane];
+    return __all_sync(0xffffffffu, eq);
+}
+constexpr int CACHE_PROBES = 8;
+// whole warp; the key is in sh->key.  Returns the slot holding it or -1.
+__device__ __forceinline__ int cache_lookup(Ctx& x, u64 h) {
+    const uint32_t tag = (uint32_t)(h >> 34);
+    for (int probe = 0; probe < CACHE_PROBES; probe++) {
+        const uint32_t slot = (uint32_t)(h + probe) & x.prm.cache_mask;
+        const uint32_t s = *reinterpret_cast<volatile uint32_t*>(&x.ptr.cache_state[slot]);
+        if (s == 0) return -1;
+        if ((s & 3) == 2 && (s >> 2) == tag && cache_key_equal(&x.ptr.cache_entry[slot], &x.sh->key, x.lane)) return (int)slot;
+    }
+    return -1;
+}
+// whole warp: publishes (sh->key -> priors of `node`, value) unless it is already there or the neighbourhood is full
+__device__ __forceinline__ void cache_insert(Ctx& x, u64 h, int node, float value) {
+    const uint32_t tag = (uint32_t)(h >> 34);
+    const size_t off = x.ebase + x.ptr.node_edge_off[x.nbase + node];
+    const int L = x.ptr.node_nedges[x.nbase + node];
+    for (int probe = 0; probe < CACHE_PROBES; probe++) {
+        const uint32_t slot = (uint32_t)(h + probe) & x.prm.cache_mask;
+        uint32_t s = *reinterpret_cast<volatile uint32_t*>(&x.ptr.cache_state[slot]);
+        if ((s & 3) == 2 && (s >> 2) == tag && cache_key_equal(&x.ptr.cache_entry[slot], &x.sh->key, x.lane)) return;
+        if (s != 0) continue;
+        uint32_t old = 1;
+        if (x.lane == 0) old = atomicCAS(&x.ptr.cache_state[slot], 0u, 1u);
+        old = __shfl_sync(0xffffffffu, old, 0);
+        if (old != 0) continue;
+        CacheEntry* e = &x.ptr.cache_entry[slot];
+        if (x.lane < 4) reinterpret_cast<uint4*>(&e->key)[x.lane] = reinterpret_cast<const uint4*>(&x.sh->key)[x.lane];
+        if (x.lane == 4) { e->value = value; e->n_priors = (uint32_t)L; }
+        for (int i = x.lane; i < L; i += 32) e->prior[i] = x.ptr.edge_P[off + i];
+        __threadfence();
+        __syncwarp();
+        if (x.lane == 0) atomicExch(&x.ptr.cache_state[slot], (tag << 2) | 2u);
+        return;
+    }
+}
+
 __device__ __forceinline__ void setup_root_from_shared(Ctx& x) {
     // fresh tree whose root is sh->child / sh->moves (priors are written by the caller)
     x.c.n_nodes = 0; x.c.n_edges = 0; x.c.sims_done = 0; x.c.max_depth = 0; x.c.pending_node = -1;
@@ -507,7 +563,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_advance(SearchParams prm, Search
     const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (g >= prm.n_games) return;
     Ctx x{prm, ptr, &shared[threadIdx.x >> 5], g, (int)(threadIdx.x & 31), (size_t)g * prm.node_cap, (size_t)g * prm.edge_cap,
-          ptr.ctl[g], 0, 0, 0, 0, 0, 0, 0};
+          ptr.ctl[g], 0, 0, 0, 0, 0, 0, 0, 0};
     if (x.c.status != 0) return;
 
     // ---- 1. the evaluation requested in the previous wave has arrived
@@ -518,6 +574,11 @@ __global__ void __launch_bounds__(WARPS * 32) k_advance(SearchParams prm, Search
         const float* pol = ptr.res_policy + (size_t)slot * AZ_ACTION_SPACE;
         for (int e = x.lane; e < L; e += 32) ptr.edge_P[off + e] = pol[ptr.edge_mv[off + e] >> 16];
         __syncwarp();
+        if (prm.cache_mask && prm.mode == 1) {  // cache.insert (training.rs:413)
+            if (x.lane == 0) x.sh->key = cache_key_of(ptr.node_pos[x.nbase + node]);
+            __syncwarp();
+            cache_insert(x, cache_hash(x.sh->key), node, ptr.res_value[slot]);
+        }
         if (node == 0) {  // MCTree::init (tree.rs:37-64): root priors, optional noise, no backup
             if (x.c.flags & 1) apply_noise(x, 0, x.c.game_id, x.c.noise_ply);
         } else {
@@ -555,6 +616,22 @@ __global__ void __launch_bounds__(WARPS * 32) k_advance(SearchParams prm, Search
         if (child < 0) { x.c.status = 2; if (x.lane == 0) atomicAdd(&ptr.counters->errors, 1ULL); break; }
         if (x.lane == 0) ptr.edge_child[pe] = child;
         x.c.max_depth = max(x.c.max_depth, (uint32_t)(depth + 1));
+        if (prm.cache_mask && prm.mode == 1) {  // cache.get (tree.rs:214-218): a hit needs no network evaluation
+            if (x.lane == 0) x.sh->key = cache_key_of(x.sh->child);
+            __syncwarp();
+            const int slot = cache_lookup(x, cache_hash(x.sh->key));
+            if (slot >= 0) {
+                const CacheEntry* ce = &ptr.cache_entry[slot];
+                const size_t coff = x.ebase + ptr.node_edge_off[x.nbase + child];
+                const int Lc = ptr.node_nedges[x.nbase + child];
+                for (int e = x.lane; e < Lc; e += 32) ptr.edge_P[coff + e] = ce->prior[e];
+                __syncwarp();
+                backup(x, ce->value, depth + 1);
+                x.c.sims_done++;
+                if (x.lane == 0) { x.st_sims++; x.st_hits++; }
+                continue;
+            }
+        }
         x.c.pending_node = child;
         x.c.pending_slot = submit_request(x);
         x.c.path_len = depth + 1;
@@ -571,6 +648,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_advance(SearchParams prm, Search
         if (x.st_games) atomicAdd(&ct->games_finished, (unsigned long long)x.st_games);
         if (x.st_depth) atomicAdd(&ct->sum_leaf_depth, (unsigned long long)x.st_depth);
         if (x.st_edges) atomicAdd(&ct->sum_edges, (unsigned long long)x.st_edges);
+        if (x.st_hits) atomicAdd(&ct->cache_hits, (unsigned long long)x.st_hits);
     }
 }
 
@@ -585,7 +663,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_init_search(SearchParams prm, Se
     GameCtl c;
     memset(&c, 0, sizeof c);
     Ctx x{prm, ptr, &shared[threadIdx.x >> 5], g, (int)(threadIdx.x & 31), (size_t)g * prm.node_cap, (size_t)g * prm.edge_cap, c,
-          0, 0, 0, 0, 0, 0, 0};
+          0, 0, 0, 0, 0, 0, 0, 0};
     x.c.game_id = noise_ids ? noise_ids[g] : 0;
     x.c.noise_ply = noise_plies ? noise_plies[g] : 0;
     x.c.flags = noise_ids ? 1 : 0;
@@ -631,7 +709,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_init_selfplay(SearchParams prm, 
     GameCtl c;
     memset(&c, 0, sizeof c);
     Ctx x{prm, ptr, &shared[threadIdx.x >> 5], g, (int)(threadIdx.x & 31), (size_t)g * prm.node_cap, (size_t)g * prm.edge_cap, c,
-          0, 0, 0, 0, 0, 0, 0};
+          0, 0, 0, 0, 0, 0, 0, 0};
     x.c.game_id = first_game_id + g;
     x.c.hist_len = 1;
     if (x.lane == 0) {
@@ -736,6 +814,14 @@ int search_create(az_engine* e) {
     r |= salloc(e, st, &q.req_f32, (size_t)e->max_batch * AZ_NUM_PLANES * 64);
     r |= salloc(e, st, &q.start_prior, 32); r |= salloc(e, st, &q.counters, 1);
     if (r) return AZ_ERR_OUT_OF_MEMORY;
+    p.cache_mask = 0; q.cache_state = nullptr; q.cache_entry = nullptr;
+    if (c.cache_log2 > 0) {
+        if (c.cache_log2 > 26) return set_err(e, AZ_ERR_INVALID_ARGUMENT, "cache_log2 must be <= 26");
+        const size_t slots = (size_t)1 << c.cache_log2;
+        if (salloc(e, st, &q.cache_state, slots) || salloc(e, st, &q.cache_entry, slots)) return AZ_ERR_OUT_OF_MEMORY;
+        cudaMemset(q.cache_state, 0, slots * sizeof(uint32_t));
+        p.cache_mask = (uint32_t)(slots - 1);
+    }
     q.req_bf16 = e->net->a_in;
     q.res_policy = e->d_policy;
     q.res_value = e->d_value;
@@ -884,6 +970,8 @@ int az_selfplay_begin(az_engine* e, int n_games, uint64_t first_game_id) {
         if (r) return AZ_ERR_OUT_OF_MEMORY;
     }
     st->prm.n_games = n_games; st->prm.mode = 1; st->prm.S = e->cfg.num_simulations;
+    if (st->prm.cache_mask)  // a new cache per generation (training.rs:342)
+        AZ_CUDA(e, cudaMemsetAsync(q.cache_state, 0, ((size_t)st->prm.cache_mask + 1) * sizeof(uint32_t), e->stream));
     Counters zero;
     std::memset(&zero, 0, sizeof zero);
     zero.next_game_id = first_game_id + n_games;

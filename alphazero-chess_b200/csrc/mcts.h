@@ -36,7 +36,20 @@ struct SearchParams {
     int max_iters;   // simulations a game may complete per wave without needing the network
     int fp32_planes; // 1: requests are written as f32 NCHW planes, 0: bf16 NHWC
     int sample_cap;
+    uint32_t cache_mask;  // slots - 1 (0: cache disabled)
 };
+
+// Position -> (legal-move priors, value) cache: the moka Cache<Fen, CacheEntry> of training.rs:342 / tree.rs:214-218.
+// Key = everything Fen::from_position(.., EnPassantMode::PseudoLegal) contains (board, turn, castling, pseudo-legal ep,
+// halfmove clock, fullmove number), compared exactly.  Entries are immutable once published.
+constexpr int CACHE_MAX_PRIORS = 238;
+struct __align__(16) CacheEntry {
+    DPos key;
+    float value;
+    uint32_t n_priors;
+    float prior[CACHE_MAX_PRIORS];
+};
+static_assert(sizeof(CacheEntry) == 1024, "one cache slot is 1 KiB");
 
 struct Counters {
     unsigned long long simulations, positions, evaluations, cache_hits, terminal_leaves, games_finished, sum_leaf_depth, sum_edges,
@@ -72,6 +85,8 @@ struct SearchPtrs {
     az_sample* game_samples;   // [G][MAX_SAMPLE_PLIES]
     az_sample* out_samples;    // [sample_cap]
     float* start_prior;        // [32] priors of the start position's legal moves (move order)
+    uint32_t* cache_state;     // [slots] 0 empty, 1 being written, (tag << 2) | 2 published
+    CacheEntry* cache_entry;   // [slots]
     Counters* counters;
 };
 

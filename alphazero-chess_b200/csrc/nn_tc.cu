@@ -203,12 +203,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
 // and the shared-memory operand bandwidth of the single-CTA kernel and doubles the work per issued instruction
 // (the single-CTA kernel was bound by the issue rate of its N=64 MMAs: profiles/r1_conv_ablation.md).
 constexpr int kTmemCols2 = 256;  // 2 accumulator stages x 128 fp32 columns
+constexpr int kThreads2 = 320;   // warp 0 TMA, warp 1 MMA/TMEM, warps 2-9 epilogue (two per TMEM lane quarter)
 
 template <int HALVES>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap w_map,
                    const float* __restrict__ bias, const __nv_bfloat16* __restrict__ residual,
-                   __nv_bfloat16* __restrict__ out, const int* __restrict__ n_boards_ptr, int n_boards_static, int relu) {
+                   __nv_bfloat16* __restrict__ out, const int* __restrict__ n_boards_ptr, int n_boards_static, int relu, int dbg) {
     using S = ConvSmem<HALVES>;
     constexpr int NS = S::kStages;
     extern __shared__ uint8_t smem_raw[];
@@ -235,10 +236,10 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
         tma_prefetch_desc(&w_map);
         for (int i = 0; i < NS; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
         for (int i = 0; i < S::kWTiles; i++) mbar_init(&wfull_bar[i], 1);
-        for (int i = 0; i < 2; i++) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
+        for (int i = 0; i < 2; i++) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 16); }
         fence_barrier_init();
     }
-    if (threadIdx.x >= 64) bias_s[threadIdx.x - 64] = bias[threadIdx.x - 64];
+    if (threadIdx.x >= 64 && threadIdx.x < 192) bias_s[threadIdx.x - 64] = bias[threadIdx.x - 64];
     if (warp == 1) tmem2_alloc(tmem_ptr_s, kTmemCols2);
     tc_fence_before();
     __syncthreads();
@@ -261,8 +262,11 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
                     }
                     mbar_wait(&empty_bar[stage], phase ^ 1, 11);
                     if (elect_one()) {
-                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);
-                        tma2_load_4d(a_sm + stage * kStageBytes, &in_map, &full_bar[stage], half * 64, dxi - 1, t * 4 + (int)rank * 2, -1);
+                        if (dbg & 1) { if (rank == 0) mbar_arrive(&full_bar[stage]); }
+                        else {
+                            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);
+                            tma2_load_4d(a_sm + stage * kStageBytes, &in_map, &full_bar[stage], half * 64, dxi - 1, t * 4 + (int)rank * 2, -1);
+                        }
                     }
                     __syncwarp();
                     if (++stage == NS) { stage = 0; phase ^= 1; }
@@ -296,7 +300,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
                                 for (int k = 0; k < 4; k++) {
                                     const uint64_t ad = dbase | (uint64_t)(a_lo + dyi * (2048 >> 4) + k * 2);
                                     const uint64_t bd = dbase | (uint64_t)(b_lo + dyi * (kWTileBytes >> 4) + k * 2);
-                                    umma2_bf16(d_tmem, ad, bd, idesc, (half | dxi | dyi | k) != 0 ? 1u : 0u);
+                                    if (!(dbg & 2)) umma2_bf16(d_tmem, ad, bd, idesc, (half | dxi | dyi | k) != 0 ? 1u : 0u);
                                 }
                             }
                             umma2_commit_mc(&empty_bar[stage]);
@@ -309,8 +313,9 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
             }
         }
     } else {
-        // ---------------------------------------------------------------- epilogue (4 warps = this CTA's 128 TMEM lanes)
+        // ------------------------------------------------ epilogue (8 warps: TMEM lane quarter q, column half ch)
         const int q = warp & 3;
+        const int ch = (warp - 2) >> 2;
         const int row = q * 32 + lane;
         const int h = row >> 4, b = (row >> 3) & 1, w = row & 7;
         int lt = 0;
@@ -318,45 +323,46 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
             const int acc = lt & 1; const uint32_t accphase = (lt >> 1) & 1;
             const int board = t * 4 + (int)rank * 2 + b;
             const bool valid = board < n_boards;
-            const size_t off = ((size_t)board * 64 + h * 8 + w) * 128;
-            const bool has_res = residual != nullptr && valid;
-            uint4 res[4];
+            const size_t off = ((size_t)board * 64 + h * 8 + w) * 128 + ch * 64;
+            if (dbg & 4) {
+                mbar_wait(&tfull_bar[acc], accphase, 15);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);
+                continue;
+            }
+            const bool has_res = residual != nullptr && valid && !(dbg & 8);
+            // the 128-byte residual half-row is requested before waiting for the accumulator (4 x 32-byte loads in flight)
+            uint32_t res[32];
             if (has_res) {
-                const uint4* rp = reinterpret_cast<const uint4*>(residual + off);
 #pragma unroll
-                for (int i = 0; i < 4; i++) res[i] = __ldg(rp + i);
+                for (int i = 0; i < 4; i++) ld_global_v8(residual + off + i * 16, &res[i * 8]);
             }
             mbar_wait(&tfull_bar[acc], accphase, 15);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 128;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 128 + ch * 64;
 #pragma unroll
-            for (int chunk = 0; chunk < 4; chunk++) {
+            for (int chunk = 0; chunk < 2; chunk++) {
                 uint32_t r[32];
                 tmem_ld32(taddr + chunk * 32, r);
-                uint4 res_next[4];
-                if (has_res && chunk < 3) {
-                    const uint4* rp = reinterpret_cast<const uint4*>(residual + off + (chunk + 1) * 32);
-#pragma unroll
-                    for (int i = 0; i < 4; i++) res_next[i] = __ldg(rp + i);
-                }
                 tmem_ld_wait();
-                if (chunk == 3) {
+                if (chunk == 1) {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);
                 }
                 if (valid) {
-                    uint4* op = reinterpret_cast<uint4*>(out + off + chunk * 32);
 #pragma unroll
-                    for (int v = 0; v < 4; v++) {
-                        uint32_t packed[4];
+                    for (int v = 0; v < 2; v++) {  // 16 channels = 32 bytes per store
+                        uint32_t packed[8];
 #pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            const int c = v * 8 + j * 2;
-                            float x0 = __uint_as_float(r[c]) + bias_s[chunk * 32 + c];
-                            float x1 = __uint_as_float(r[c + 1]) + bias_s[chunk * 32 + c + 1];
-                            if (residual != nullptr) {
-                                const uint32_t rr = reinterpret_cast<const uint32_t*>(&res[v])[j];
+                        for (int j = 0; j < 8; j++) {
+                            const int c = v * 16 + j * 2;
+                            const float2 bb = *reinterpret_cast<const float2*>(&bias_s[ch * 64 + chunk * 32 + c]);
+                            float x0 = __uint_as_float(r[c]) + bb.x;
+                            float x1 = __uint_as_float(r[c + 1]) + bb.y;
+                            if (has_res) {
+                                const uint32_t rr = res[chunk * 16 + v * 8 + j];
                                 x0 += __uint_as_float(rr << 16);
                                 x1 += __uint_as_float(rr & 0xFFFF0000u);
                             }
@@ -364,12 +370,9 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
                             __nv_bfloat162 pk = __floats2bfloat162_rn(x0, x1);
                             packed[j] = *reinterpret_cast<uint32_t*>(&pk);
                         }
-                        op[v] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                        if (!(dbg & 16)) st_global_v8(out + off + chunk * 32 + v * 16, packed);
+                        else if (packed[0] == 0x12345678u && packed[7] == 0x9abcdef0u) st_global_v8(out + off, packed);
                     }
-                }
-                if (chunk < 3) {
-#pragma unroll
-                    for (int i = 0; i < 4; i++) res[i] = res_next[i];
                 }
             }
         }
@@ -436,7 +439,7 @@ int tc_conv3x3_launch(cudaStream_t stream, const CUtensorMap* in_map, const CUte
     grid &= ~1;
     static int variant = -1;
     if (variant < 0) { const char* v = getenv("AZ_CONV_VARIANT"); variant = v ? atoi(v) : 2; }
-    if (variant == 2 && dbg == 0) {
+    if (variant == 2) {
         static bool attr2 = false;
         if (!attr2) {
             cudaError_t e1 = cudaFuncSetAttribute(conv3x3_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<1>::kTotal);
@@ -445,11 +448,11 @@ int tc_conv3x3_launch(cudaStream_t stream, const CUtensorMap* in_map, const CUte
             attr2 = true;
         }
         if (cin == 64)
-            conv3x3_tc2_kernel<1><<<grid, kThreads, ConvSmem<1>::kTotal, stream>>>(*in_map, *w_map, bias, (const __nv_bfloat16*)residual,
-                                                                                   (__nv_bfloat16*)out, n_boards_dev, n_boards_static, relu);
+            conv3x3_tc2_kernel<1><<<grid, kThreads2, ConvSmem<1>::kTotal, stream>>>(*in_map, *w_map, bias, (const __nv_bfloat16*)residual,
+                                                                                   (__nv_bfloat16*)out, n_boards_dev, n_boards_static, relu, dbg);
         else if (cin == 128)
-            conv3x3_tc2_kernel<2><<<grid, kThreads, ConvSmem<2>::kTotal, stream>>>(*in_map, *w_map, bias, (const __nv_bfloat16*)residual,
-                                                                                   (__nv_bfloat16*)out, n_boards_dev, n_boards_static, relu);
+            conv3x3_tc2_kernel<2><<<grid, kThreads2, ConvSmem<2>::kTotal, stream>>>(*in_map, *w_map, bias, (const __nv_bfloat16*)residual,
+                                                                                   (__nv_bfloat16*)out, n_boards_dev, n_boards_static, relu, dbg);
         else
             return -3;
         return cudaGetLastError() == cudaSuccess ? 0 : -4;

@@ -172,7 +172,7 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     G, S = args.games, args.sims
-    eng = az.Engine(device=local_rank, max_games=G, num_simulations=S, seed=42)
+    eng = az.Engine(device=local_rank, max_games=G, num_simulations=S, seed=42, cache_log2=args.cache_log2)
 
     # ---- weights: rank 0 owns them; one flat NCCL broadcast per generation, then an on-device import
     from alphazero_chess_b200 import sharding
@@ -218,7 +218,7 @@ def run_ours(args, rank, world, local_rank):
     prof = eng.profile_read()
     eng.profile_enable(0)
     d = {k: getattr(st1, k) - getattr(st0, k) for k in ("simulations", "positions", "evaluations", "terminal_leaves", "games_finished",
-                                                       "sum_leaf_depth", "sum_edges")}
+                                                       "sum_leaf_depth", "sum_edges", "cache_hits")}
     eng.selfplay_drain()
 
     # ---- end to end through the reference-facing call: MCTree::init + monte_carlo_tree_search for G host-resident roots
@@ -278,6 +278,7 @@ def run_ours(args, rank, world, local_rank):
             "positions_per_sec": positions / (ms_all * 1e-3),
             "nn_evals_per_sec": evals / (ms_all * 1e-3),
             "eval_avoidance_ratio": 1.0 - evals / max(sims, 1.0),
+            "cache": {"log2_slots": args.cache_log2, "hits_rank0": int(d["cache_hits"])},
             "mean_leaf_depth": vec[6] / max(sims, 1.0),
             "mean_edges_per_level": vec[7] / max(vec[6], 1.0),
             "nn_tensor_frac_whole_step": evals * az.FLOPS_PER_EVAL / (ms_all * 1e-3) / 1e12 / (peak_tf * world),
@@ -304,6 +305,7 @@ def main():
     ap.add_argument("--games", type=int, default=4096, help="concurrent games per GPU")
     ap.add_argument("--sims", type=int, default=800, help="simulations per move")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cache-log2", type=int, default=0, help="log2 slots of the GPU evaluation cache (0 = off)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

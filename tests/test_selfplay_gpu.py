@@ -23,12 +23,16 @@ def _collect(e, n_games, target_games, max_waves=40000, chunk=64):
     return np.concatenate(samples) if samples else np.zeros(0, az.SAMPLE_DTYPE), st
 
 
-def test_selfplay_records_identical_to_oracle():
+@pytest.mark.parametrize("cache_log2", [0, 14])
+def test_selfplay_records_identical_to_oracle(cache_log2):
     sims, seed, stub_seed = 24, 42, 17
-    with az.Engine(max_games=16, num_simulations=sims, seed=seed) as e:
+    with az.Engine(max_games=16, num_simulations=sims, seed=seed, cache_log2=cache_log2) as e:
         e.set_evaluator_stub(1, stub_seed)
         samples, st = _collect(e, 16, 16)
         assert st.games_finished >= 16 and st.positions >= len(samples)
+        # the evaluation cache (training.rs:342) is semantically transparent: same records, fewer evaluations
+        assert (st.cache_hits > 0) == (cache_log2 > 0)
+        assert st.cache_hits + st.evaluations + st.terminal_leaves >= st.simulations
     prm = orc.make_params(num_simulations=sims, seed=seed)
     ev = orc.make_evaluator("stub", stub_seed=stub_seed)
     finished = sorted(set(int(g) for g in samples["game_id"]))
