@@ -275,12 +275,16 @@ __device__ __forceinline__ int create_node(Ctx& x, int depth) {
 }
 
 // Queues the position in sh->child for evaluation; returns the batch slot.
-__device__ __forceinline__ int submit_request(Ctx& x) {
+__device__ __forceinline__ int submit_request(Ctx& x, int node) {
     int slot = 0;
     if (x.lane == 0) slot = atomicAdd(x.ptr.batch_count, 1);
     slot = __shfl_sync(0xffffffffu, slot, 0);
     const DPos child = x.sh->child;
-    if (x.lane == 0) x.ptr.req_pos[slot] = child;
+    if (x.lane == 0) {
+        x.ptr.req_pos[slot] = child;
+        x.ptr.req_edge_off[slot] = (unsigned long long)(x.ebase + x.ptr.node_edge_off[x.nbase + node]);
+        x.ptr.req_nedges[slot] = (int)x.ptr.node_nedges[x.nbase + node];
+    }
     if (x.prm.fp32_planes) {
         const u64 occ = occupied(child);
         const u64 ours = meta_turn(child.meta) == 0 ? child.white : occ ^ child.white;
@@ -571,8 +575,10 @@ __global__ void __launch_bounds__(WARPS * 32) k_advance(SearchParams prm, Search
         const int node = x.c.pending_node, slot = x.c.pending_slot;
         const size_t off = x.ebase + ptr.node_edge_off[x.nbase + node];
         const int L = ptr.node_nedges[x.nbase + node];
-        const float* pol = ptr.res_policy + (size_t)slot * AZ_ACTION_SPACE;
-        for (int e = x.lane; e < L; e += 32) ptr.edge_P[off + e] = pol[ptr.edge_mv[off + e] >> 16];
+        if (!prm.priors_scattered) {
+            const float* pol = ptr.res_policy + (size_t)slot * AZ_ACTION_SPACE;
+            for (int e = x.lane; e < L; e += 32) ptr.edge_P[off + e] = pol[ptr.edge_mv[off + e] >> 16];
+        }
         __syncwarp();
         if (prm.cache_mask && prm.mode == 1) {  // cache.insert (training.rs:413)
             if (x.lane == 0) x.sh->key = cache_key_of(ptr.node_pos[x.nbase + node]);
@@ -633,7 +639,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_advance(SearchParams prm, Search
             }
         }
         x.c.pending_node = child;
-        x.c.pending_slot = submit_request(x);
+        x.c.pending_slot = submit_request(x, child);
         x.c.path_len = depth + 1;
         break;
     }
@@ -696,7 +702,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_init_search(SearchParams prm, Se
     x.c.hist_len = hl;
     setup_root_from_shared(x);
     x.c.pending_node = 0;
-    x.c.pending_slot = submit_request(x);
+    x.c.pending_slot = submit_request(x, 0);
     if (x.sh->n_moves == 0) x.c.status = 1;  // nothing to search in a terminal position
     if (x.lane == 0) ptr.ctl[g] = x.c;
 }
@@ -812,6 +818,7 @@ int search_create(az_engine* e) {
     r |= salloc(e, st, &q.ctl, (size_t)G); r |= salloc(e, st, &q.path, NN); r |= salloc(e, st, &q.hist, (size_t)G * HIST_CAP);
     r |= salloc(e, st, &q.batch_count, 4); r |= salloc(e, st, &q.req_pos, (size_t)e->max_batch);
     r |= salloc(e, st, &q.req_f32, (size_t)e->max_batch * AZ_NUM_PLANES * 64);
+    r |= salloc(e, st, &q.req_edge_off, (size_t)e->max_batch); r |= salloc(e, st, &q.req_nedges, (size_t)e->max_batch);
     r |= salloc(e, st, &q.start_prior, 32); r |= salloc(e, st, &q.counters, 1);
     if (r) return AZ_ERR_OUT_OF_MEMORY;
     p.cache_mask = 0; q.cache_state = nullptr; q.cache_entry = nullptr;
@@ -850,11 +857,13 @@ static int evaluate_batch(az_engine* e, SearchState* st) {
         return check_cuda(e, cudaGetLastError(), "k_stub_eval");
     }
     if (e->cfg.precision == 1) return net_forward_fp32(e, q.req_f32, q.batch_count, 0, e->d_policy, e->d_value);
-    return net_forward_bf16(e, q.batch_count, 0, e->d_policy, e->d_value);
+    HeadScatter sc{q.req_edge_off, q.req_nedges, q.edge_mv, q.edge_P};
+    return net_forward_bf16(e, q.batch_count, 0, nullptr, e->d_value, &sc);
 }
 
 static int run_wave(az_engine* e, SearchState* st) {
     const int blocks = (st->prm.n_games + WARPS - 1) / WARPS;
+    st->prm.priors_scattered = (e->stub_kind == 0 && e->cfg.precision != 1) ? 1 : 0;
     AZ_CUDA(e, cudaMemsetAsync(st->ptr.batch_count, 0, sizeof(int), e->stream));
     e->n_launches++;
     k_advance<<<blocks, WARPS * 32, 0, e->stream>>>(st->prm, st->ptr);

@@ -37,6 +37,7 @@ struct SearchParams {
     int fp32_planes; // 1: requests are written as f32 NCHW planes, 0: bf16 NHWC
     int sample_cap;
     uint32_t cache_mask;  // slots - 1 (0: cache disabled)
+    int priors_scattered; // 1: the evaluator already wrote the legal-move priors into edge_P (fused heads)
 };
 
 // Position -> (legal-move priors, value) cache: the moka Cache<Fen, CacheEntry> of training.rs:342 / tree.rs:214-218.
@@ -79,6 +80,8 @@ struct SearchPtrs {
     DPos* req_pos;             // [max_batch]
     __nv_bfloat16* req_bf16;   // [max_batch][64][64]
     float* req_f32;            // [max_batch][19][64]
+    unsigned long long* req_edge_off;  // [max_batch] first edge (global index) of the node each request will fill
+    int* req_nedges;           // [max_batch]
     const float* res_policy;   // [max_batch][4096]
     const float* res_value;    // [max_batch]
     // self-play

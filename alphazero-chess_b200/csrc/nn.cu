@@ -76,6 +76,11 @@ int net_create(az_engine* e) {
     for (int l = 0; l < 20; l++)
         if (tc_make_weight_map(&w->map_w_tower[l], w->h_w_tower + (size_t)l * 9 * 128 * 128, 128))
             return set_err(e, AZ_ERR_CUDA, "cuTensorMapEncodeTiled(w_tower)");
+    CUtensorMap host_maps[23];
+    for (int i = 0; i < 3; i++) host_maps[i] = w->map_a[i];
+    for (int l = 0; l < 20; l++) host_maps[3 + l] = w->map_w_tower[l];
+    if (dmalloc(e, &w->d_maps, 23)) return AZ_ERR_OUT_OF_MEMORY;
+    AZ_CUDA(e, cudaMemcpy(w->d_maps, host_maps, sizeof host_maps, cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -84,6 +89,7 @@ void net_destroy(az_engine* e) {
     if (!w) return;
     cudaFree(w->f_w_in); cudaFree(w->f_b_in); cudaFree(w->f_w_tower); cudaFree(w->f_b_tower); cudaFree(w->f_w40t); cudaFree(w->f_b40);
     cudaFree(w->f_wp2t); cudaFree(w->f_bp2); cudaFree(w->f_wl1); cudaFree(w->f_bl1); cudaFree(w->f_wl2); cudaFree(w->f_bl2);
+    cudaFree(w->d_maps);
     cudaFree(w->h_w_in); cudaFree(w->h_w_tower); cudaFree(w->a_in); cudaFree(w->h_w40); cudaFree(w->h_wp2); cudaFree(w->h_wl1t);
     for (int i = 0; i < 3; i++) { cudaFree(w->a_buf[i]); cudaFree(w->g_buf[i]); }
     delete w;
@@ -337,7 +343,7 @@ static int launch_heads(az_engine* e, const void* tower, const int* n_dev, int n
     return check_cuda(e, cudaGetLastError(), "k_heads");
 }
 
-int net_forward_bf16(az_engine* e, const int* n_dev, int n_static, float* policy_out, float* value_out) {
+int net_forward_bf16(az_engine* e, const int* n_dev, int n_static, float* policy_out, float* value_out, const HeadScatter* scatter) {
     NetWeights* w = e->net;
     if (!w->loaded) return set_err(e, AZ_ERR_NO_WEIGHTS, "az_load_weights has not been called");
     const int grid = e->sm_count & ~1;
@@ -354,7 +360,15 @@ int net_forward_bf16(az_engine* e, const int* n_dev, int n_static, float* policy
         cudaEventRecord(ps.a, e->stream);
     }
     int x = 0;  // buffer holding the block input
-    for (int blk = 0; blk < 10; blk++) {
+    static int fused = -1;
+    if (fused < 0) { const char* v = getenv("AZ_TOWER_FUSED"); fused = v ? atoi(v) : 0; }  // opt-in: correct but currently slower than 20 launches (profiles/README.md)
+    if (fused) {
+        void* act[3] = {w->a_buf[0], w->a_buf[1], w->a_buf[2]};
+        r = tc_tower_launch(e->stream, w->d_maps, w->f_b_tower, act, n_dev, n_static, 20, grid);
+        if (r) return set_err(e, AZ_ERR_CUDA, "tower launch failed");
+        x = 2;  // ten blocks rotate the three buffers: (0 + 10 * 2) % 3
+    }
+    for (int blk = 0; blk < (fused ? 0 : 10); blk++) {
         const int y = (x + 1) % 3, z = (x + 2) % 3;
         r = tc_conv3x3_launch(e->stream, &w->map_a[x], &w->map_w_tower[2 * blk], 128, w->f_b_tower + (2 * blk) * 128, nullptr, w->a_buf[y],
                               n_dev, n_static, 1, grid);
@@ -367,7 +381,7 @@ int net_forward_bf16(az_engine* e, const int* n_dev, int n_static, float* policy
     if (sample) { cudaEventRecord(ps.b, e->stream); e->prof_pending.push_back(ps); }
     static int heads_variant = -1;
     if (heads_variant < 0) { const char* v = getenv("AZ_HEADS_VARIANT"); heads_variant = v ? atoi(v) : 1; }
-    if (heads_variant == 1) return launch_heads_mma(e, w->a_buf[x], n_dev, n_static, policy_out, value_out);
+    if (heads_variant == 1) return launch_heads_mma(e, w->a_buf[x], n_dev, n_static, policy_out, value_out, scatter);
     const int hgrid = n_dev ? w->max_boards : n_static;
     return launch_heads<true, false>(e, w->a_buf[x], n_dev, n_static, hgrid, policy_out, value_out);
 }

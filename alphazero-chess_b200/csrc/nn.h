@@ -6,6 +6,15 @@
 
 namespace azb {
 
+// Optional fused epilogue of the heads: write the priors of each board's legal moves straight into the search tree
+// (edge_P[edge_off[b] + e] = softmax[policy index of edge e]) instead of materialising the 16 KB policy row.
+struct HeadScatter {
+    const unsigned long long* edge_off;  // [n] first edge of the node waiting for board b
+    const int* n_edges;                  // [n]
+    const uint32_t* edge_mv;             // wire move | policy index << 16
+    float* edge_P;
+};
+
 struct NetWeights {
     bool loaded = false;
     int max_boards = 0;
@@ -35,6 +44,7 @@ struct NetWeights {
     __nv_bfloat16* a_buf[3] = {nullptr, nullptr, nullptr};  // [max_boards][64][128]
     CUtensorMap map_a_in;
     CUtensorMap map_a[3];
+    CUtensorMap* d_maps = nullptr;       // device copy {map_a[0..2], map_w_tower[0..19]} for the fused tower kernel
     float* g_buf[3] = {nullptr, nullptr, nullptr};          // fp32 path, NCHW [max_boards][128][64] (allocated lazily)
 };
 
@@ -43,11 +53,12 @@ void net_destroy(az_engine* e);
 
 // Forward over boards whose bf16 NHWC planes are already in net->a_in (n read from n_dev when non-null).
 // policy_out [n][4096] f32 (nullable), value_out [n] f32.  Returns the buffer index holding the tower output.
-int net_forward_bf16(az_engine* e, const int* n_dev, int n_static, float* policy_out, float* value_out);
+int net_forward_bf16(az_engine* e, const int* n_dev, int n_static, float* policy_out, float* value_out, const HeadScatter* scatter = nullptr);
 // fp32 parity path from NCHW f32 planes [n][19][64]
 int net_forward_fp32(az_engine* e, const float* planes, const int* n_dev, int n_static, float* policy_out, float* value_out);
 // fused heads on warp-level tensor-core MMAs (nn_heads.cu); tower = NHWC bf16 [n][64][128]
-int launch_heads_mma(az_engine* e, const __nv_bfloat16* tower, const int* n_dev, int n_static, float* policy_out, float* value_out);
+int launch_heads_mma(az_engine* e, const __nv_bfloat16* tower, const int* n_dev, int n_static, float* policy_out, float* value_out,
+                     const HeadScatter* scatter);
 // f32 NCHW planes -> bf16 NHWC (64 channels) into net->a_in
 void launch_planes_to_bf16(cudaStream_t s, const float* planes, __nv_bfloat16* out, int n);
 // positions -> bf16 NHWC planes (to_tensor fused with the layout the first convolution wants)
@@ -60,20 +71,19 @@ __device__ __forceinline__ void encode_bf16_warp(const DPos& p, __nv_bfloat16* o
     const u64 ours = meta_turn(p.meta) == 0 ? p.white : occ ^ p.white;
     const u64 theirs = occ ^ ours;
     const int pep = pseudo_legal_ep(p);
-    // 64 squares x 8 chunks of 8 channels (16 B each); channels >= 19 are zero
-    for (int item = lane; item < 512; item += 32) {
-        const int sq = item >> 3, chunk = item & 7;
+    // 64 squares x 3 chunks of 8 channels (16 B each) hold the 19 planes; chunks 3..7 of every square stay zero
+    // (the buffer is zero-filled when it is allocated and nothing ever writes there)
+    for (int item = lane; item < 192; item += 32) {
+        const int sq = item / 3, chunk = item - sq * 3;
         uint32_t packed[4] = {0, 0, 0, 0};
-        if (chunk < 3) {
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                int c = chunk * 8 + j;
-                float v = c < AZ_NUM_PLANES ? plane_value(p, c, sq, pep, ours, theirs) : 0.0f;
-                __nv_bfloat16 h = __float2bfloat16_rn(v);
-                packed[j >> 1] |= (uint32_t)(*reinterpret_cast<unsigned short*>(&h)) << ((j & 1) * 16);
-            }
+        for (int j = 0; j < 8; j++) {
+            const int c = chunk * 8 + j;
+            const float v = c < AZ_NUM_PLANES ? plane_value(p, c, sq, pep, ours, theirs) : 0.0f;
+            __nv_bfloat16 h = __float2bfloat16_rn(v);
+            packed[j >> 1] |= (uint32_t)(*reinterpret_cast<unsigned short*>(&h)) << ((j & 1) * 16);
         }
-        reinterpret_cast<uint4*>(out)[item] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        reinterpret_cast<uint4*>(out)[sq * 8 + chunk] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
     }
 }
 #endif

@@ -13,6 +13,8 @@ namespace azb {
 constexpr int HW40_PITCH = 136;  // bf16 elements per row of W40 in shared memory (128 + 8: conflict-free fragment loads)
 constexpr int HW2_PITCH = 40;    // 32 + 8
 constexpr int HV1_PITCH = 520;   // 512 + 8
+constexpr int HEXP_PITCH = 68;   // floats per output-channel row of the per-warp softmax tile (64 + 4)
+constexpr int HEADS_DYN_SMEM = 8 * 64 * HEXP_PITCH * 4;
 
 __device__ __forceinline__ void mma_bf16_16816(float* d, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -28,7 +30,8 @@ __global__ void __launch_bounds__(256, 1)
 k_heads_mma(const __nv_bfloat16* __restrict__ tower, const __nv_bfloat16* __restrict__ w40, const float* __restrict__ b40,
             const __nv_bfloat16* __restrict__ wp2, const float* __restrict__ bp2, const __nv_bfloat16* __restrict__ wl1t,
             const float* __restrict__ bl1, const float* __restrict__ wl2, const float* __restrict__ bl2, float* __restrict__ policy_out,
-            float* __restrict__ value_out, const int* __restrict__ n_dev, int n_static) {
+            float* __restrict__ value_out, const int* __restrict__ n_dev, int n_static, HeadScatter sc) {
+    extern __shared__ float s_exp_all[];  // [8 warps][64 co][HEXP_PITCH]: exp(logit - max) of one board per warp
     __shared__ __align__(16) __nv_bfloat16 s_w40[40 * HW40_PITCH];
     __shared__ __align__(16) __nv_bfloat16 s_w2[64 * HW2_PITCH];
     __shared__ __align__(16) __nv_bfloat16 s_v1[8 * HV1_PITCH];
@@ -134,8 +137,27 @@ k_heads_mma(const __nv_bfloat16* __restrict__ tower, const __nv_bfloat16* __rest
 #pragma unroll
                     for (int i = 0; i < 4; i++) { d2[mt][nt][i] = __expf(d2[mt][nt][i] - mx); sum += d2[mt][nt][i]; }
             for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+            const float inv = __fdividef(1.0f, sum);
+            if (sc.edge_P) {  // priors of the legal moves only, written into the tree (tree.rs:84-104 reads nothing else)
+                float* se = s_exp_all + warp * 64 * HEXP_PITCH;
+#pragma unroll
+                for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+                    for (int nt = 0; nt < 8; nt++) {
+                        const int co = mt * 16 + g, sq = nt * 8 + tig * 2;
+                        *reinterpret_cast<float2*>(se + co * HEXP_PITCH + sq) = make_float2(d2[mt][nt][0], d2[mt][nt][1]);
+                        *reinterpret_cast<float2*>(se + (co + 8) * HEXP_PITCH + sq) = make_float2(d2[mt][nt][2], d2[mt][nt][3]);
+                    }
+                __syncwarp();
+                const unsigned long long eo = sc.edge_off[b];
+                const int L = sc.n_edges[b];
+                for (int e2 = lane; e2 < L; e2 += 32) {
+                    const uint32_t idx = sc.edge_mv[eo + e2] >> 16;
+                    sc.edge_P[eo + e2] = se[(idx >> 6) * HEXP_PITCH + (idx & 63)] * inv;
+                }
+                __syncwarp();
+            }
             if (policy_out) {
-                const float inv = __fdividef(1.0f, sum);
                 float* po = policy_out + (size_t)b * 4096;
 #pragma unroll
                 for (int mt = 0; mt < 4; mt++)
@@ -178,13 +200,18 @@ k_heads_mma(const __nv_bfloat16* __restrict__ tower, const __nv_bfloat16* __rest
     }
 }
 
-int launch_heads_mma(az_engine* e, const __nv_bfloat16* tower, const int* n_dev, int n_static, float* policy_out, float* value_out) {
+int launch_heads_mma(az_engine* e, const __nv_bfloat16* tower, const int* n_dev, int n_static, float* policy_out, float* value_out,
+                     const HeadScatter* scatter) {
     NetWeights* w = e->net;
     const int n_max = n_dev ? w->max_boards : n_static;
     if (n_max <= 0) return 0;
-    const int grid = std::min((n_max + 7) / 8, e->sm_count * 2);
-    k_heads_mma<<<grid, 256, 0, e->stream>>>(tower, w->h_w40, w->f_b40, w->h_wp2, w->f_bp2, w->h_wl1t, w->f_bl1, w->f_wl2, w->f_bl2,
-                                             policy_out, value_out, n_dev, n_static);
+    const int grid = std::min((n_max + 7) / 8, e->sm_count);
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(k_heads_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, HEADS_DYN_SMEM); attr = true; }
+    HeadScatter sc{nullptr, nullptr, nullptr, nullptr};
+    if (scatter) sc = *scatter;
+    k_heads_mma<<<grid, 256, HEADS_DYN_SMEM, e->stream>>>(tower, w->h_w40, w->f_b40, w->h_wp2, w->f_bp2, w->h_wl1t, w->f_bl1, w->f_wl2, w->f_bl2,
+                                             policy_out, value_out, n_dev, n_static, sc);
     return check_cuda(e, cudaGetLastError(), "k_heads_mma");
 }
 

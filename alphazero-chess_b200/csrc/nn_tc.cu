@@ -383,6 +383,260 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
     if (warp == 1) { tc_fence_after(); tmem2_dealloc(tmem_base, kTmemCols2); }
 }
 
+// ================================================================================================================
+// Fused residual tower: all 20 3x3 convolutions (agent.rs:118-120) in ONE persistent launch.
+// A convolution is local to a board, and a CTA pair keeps the same boards in every layer, so no grid-wide
+// synchronisation is needed between layers: a pair runs layer after layer over its own tiles.  Only the weights change,
+// so each CTA re-streams its 144 KB half of the next layer's weights through shared memory as soon as the last tile of
+// the current layer has consumed them (per weight-group empty barriers), which keeps the MMA pipe busy across layer
+// boundaries and removes 19 launch fill/drain phases.  Tile t of layer l+1 reads what this CTA's own epilogue wrote for
+// tile t of layer l: the epilogue warps publish per-warp completion counters after a generic->async proxy fence and the
+// TMA producer checks them (they are normally many tiles ahead).
+struct TowerParams {
+    const CUtensorMap* maps;   // device memory: [0..2] activation buffers, [3..22] weights of the 20 layers
+    const float* bias;         // [20][128]
+    __nv_bfloat16* act[3];
+    const int* n_boards_ptr;
+    int n_boards_static;
+    int n_layers;              // 20
+};
+
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
+conv_tower_kernel(const TowerParams prm) {
+    using S = ConvSmem<2>;
+    constexpr int NS = S::kStages;
+    constexpr int kGroupBytes = 3 * kWTileBytes;  // the three dy taps of one (channel half, dx)
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* w_sm = smem;
+    uint8_t* a_sm = smem + S::kWBytes;
+    uint8_t* misc = a_sm + S::kABytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(misc);             // NS   (leader)
+    uint64_t* empty_bar = full_bar + NS;                                // NS   (per CTA)
+    uint64_t* wfull_bar = empty_bar + NS;                               // 6    (leader)
+    uint64_t* wempty_bar = wfull_bar + 6;                               // 6    (per CTA)
+    uint64_t* tfull_bar = wempty_bar + 6;                               // 2    (per CTA)
+    uint64_t* tempty_bar = tfull_bar + 2;                               // 2    (leader)
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    volatile uint32_t* epi_done = reinterpret_cast<volatile uint32_t*>(tmem_ptr_s + 4);  // 8 per-warp tile counters
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int n_boards = prm.n_boards_ptr ? *prm.n_boards_ptr : prm.n_boards_static;
+    const int n_tiles = (n_boards + 3) >> 2;
+    const int first_tile = blockIdx.x >> 1, tile_step = gridDim.x >> 1;
+    const int T = first_tile < n_tiles ? (n_tiles - first_tile + tile_step - 1) / tile_step : 0;  // tiles of this pair
+    const int NL = prm.n_layers;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NS; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 6; i++) { mbar_init(&wfull_bar[i], 1); mbar_init(&wempty_bar[i], 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 16); }
+        fence_barrier_init();
+    }
+    if (threadIdx.x < 8) epi_done[threadIdx.x] = 0;
+    if (warp == 1) tmem2_alloc(tmem_ptr_s, kTmemCols2);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_s;
+
+    if (warp == 0) {
+        // ---------------------------------------------------------------- TMA producer (both CTAs)
+        int stage = 0; uint32_t phase = 0;
+        int x = 0;
+        for (int layer = 0; layer < NL; layer++) {
+            const int blk_second = layer & 1;
+            const int in_buf = blk_second ? (x + 1) % 3 : x;
+            const CUtensorMap* in_map = &prm.maps[in_buf];
+            const CUtensorMap* w_map = &prm.maps[3 + layer];
+            for (int i = 0; i < T; i++) {
+                const int t = first_tile + i * tile_step;
+                if (layer > 0) {  // this tile's input was written by this CTA's epilogue one layer ago
+                    const uint32_t need = (uint32_t)((layer - 1) * T + i + 1);
+                    long long t0 = clock64();
+                    for (;;) {
+                        bool ok = lane >= 8 || epi_done[lane & 7] >= need;
+                        if (__all_sync(0xffffffffu, ok)) break;
+                        if (clock64() - t0 > 4000000000LL) { if (lane == 0) printf("azb: tower epilogue wait timeout\n"); __trap(); }
+                    }
+                    fence_proxy_async();
+                }
+                for (int half = 0; half < 2; half++)
+                    for (int dxi = 0; dxi < 3; dxi++) {
+                        const int grp = half * 3 + dxi;
+                        if (i == 0) {  // (re)load this group's three weight tiles for the new layer
+                            if (layer > 0) mbar_wait(&wempty_bar[grp], (uint32_t)((layer - 1) & 1), 21);
+                            if (elect_one()) {
+                                if (rank == 0) mbar_arrive_expect_tx(&wfull_bar[grp], 2 * kGroupBytes);
+                                for (int dyi = 0; dyi < 3; dyi++)
+                                    tma2_load_2d(w_sm + (grp * 3 + dyi) * kWTileBytes, w_map, &wfull_bar[grp], half * 64,
+                                                 (dyi * 3 + dxi) * 128 + (int)rank * 64);
+                            }
+                            __syncwarp();
+                        }
+                        mbar_wait(&empty_bar[stage], phase ^ 1, 22);
+                        if (elect_one()) {
+                            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);
+                            tma2_load_4d(a_sm + stage * kStageBytes, in_map, &full_bar[stage], half * 64, dxi - 1, t * 4 + (int)rank * 2, -1);
+                        }
+                        __syncwarp();
+                        if (++stage == NS) { stage = 0; phase ^= 1; }
+                    }
+            }
+            if (blk_second) x = (x + 2) % 3;
+        }
+    } else if (warp == 1) {
+        if (rank == 0) {
+            // ------------------------------------------------------------ MMA issuer (leader CTA)
+            constexpr uint32_t idesc = umma_idesc_bf16(256, 128);
+            const uint64_t dbase = umma_desc_base_sw128();
+            const uint32_t w_lo = (smem_u32(w_sm) & 0x3FFFF) >> 4;
+            int stage = 0; uint32_t phase = 0; int lt = 0;
+            for (int layer = 0; layer < NL; layer++) {
+                for (int i = 0; i < T; i++, lt++) {
+                    const int acc = lt & 1; const uint32_t accphase = (lt >> 1) & 1;
+                    mbar_wait(&tempty_bar[acc], accphase ^ 1, 23);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * 128;
+                    for (int half = 0; half < 2; half++)
+                        for (int dxi = 0; dxi < 3; dxi++) {
+                            const int grp = half * 3 + dxi;
+                            mbar_wait(&full_bar[stage], phase, 24);
+                            if (i == 0) mbar_wait(&wfull_bar[grp], (uint32_t)(layer & 1), 25);
+                            tc_fence_after();
+                            if (elect_one()) {
+                                const uint32_t a_lo = (smem_u32(a_sm + stage * kStageBytes) & 0x3FFFF) >> 4;
+                                const uint32_t b_lo = w_lo + (uint32_t)(grp * 3) * (kWTileBytes >> 4);
+#pragma unroll
+                                for (int dyi = 0; dyi < 3; dyi++) {
+#pragma unroll
+                                    for (int k = 0; k < 4; k++) {
+                                        const uint64_t ad = dbase | (uint64_t)(a_lo + dyi * (2048 >> 4) + k * 2);
+                                        const uint64_t bd = dbase | (uint64_t)(b_lo + dyi * (kWTileBytes >> 4) + k * 2);
+                                        umma2_bf16(d_tmem, ad, bd, idesc, (half | dxi | dyi | k) != 0 ? 1u : 0u);
+                                    }
+                                }
+                                umma2_commit_mc(&empty_bar[stage]);
+                                if (i == T - 1) umma2_commit_mc(&wempty_bar[grp]);  // weights of this group are free for the next layer
+                            }
+                            __syncwarp();
+                            if (++stage == NS) { stage = 0; phase ^= 1; }
+                        }
+                    if (elect_one()) umma2_commit_mc(&tfull_bar[acc]);
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------ epilogue (8 warps: TMEM lane quarter q, column half ch)
+        const int q = warp & 3;
+        const int ch = (warp - 2) >> 2;
+        const int row = q * 32 + lane;
+        const int h = row >> 4, b = (row >> 3) & 1, w = row & 7;
+        int lt = 0, x = 0;
+        uint32_t done = 0;
+        const bool lazy = T >= 3;
+        for (int layer = 0; layer < NL; layer++) {
+            const int blk_second = layer & 1;
+            const int out_buf = blk_second ? (x + 2) % 3 : (x + 1) % 3;
+            __nv_bfloat16* out = prm.act[out_buf];
+            const __nv_bfloat16* residual = blk_second ? prm.act[x] : nullptr;
+            const float* bias = prm.bias + layer * 128 + ch * 64;
+            for (int i = 0; i < T; i++, lt++) {
+                const int t = first_tile + i * tile_step;
+                const int acc = lt & 1; const uint32_t accphase = (lt >> 1) & 1;
+                const int board = t * 4 + (int)rank * 2 + b;
+                const bool valid = board < n_boards;
+                const size_t off = ((size_t)board * 64 + h * 8 + w) * 128 + ch * 64;
+                const bool has_res = residual != nullptr && valid;
+                uint32_t res[32];
+                if (has_res) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) ld_global_v8(residual + off + k * 16, &res[k * 8]);
+                }
+                mbar_wait(&tfull_bar[acc], accphase, 26);
+                tc_fence_after();
+                if (lazy && done > 0) {  // the previous tile's stores have had a whole tile time to land
+                    fence_proxy_async();
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) epi_done[warp - 2] = done;
+                }
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 128 + ch * 64;
+#pragma unroll
+                for (int chunk = 0; chunk < 2; chunk++) {
+                    uint32_t r[32];
+                    tmem_ld32(taddr + chunk * 32, r);
+                    tmem_ld_wait();
+                    if (chunk == 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);
+                    }
+                    if (valid) {
+#pragma unroll
+                        for (int v = 0; v < 2; v++) {
+                            uint32_t packed[8];
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                const int c = v * 16 + j * 2;
+                                const float2 bb = __ldg(reinterpret_cast<const float2*>(bias + chunk * 32 + c));
+                                float x0 = __uint_as_float(r[c]) + bb.x;
+                                float x1 = __uint_as_float(r[c + 1]) + bb.y;
+                                if (has_res) {
+                                    const uint32_t rr = res[chunk * 16 + v * 8 + j];
+                                    x0 += __uint_as_float(rr << 16);
+                                    x1 += __uint_as_float(rr & 0xFFFF0000u);
+                                }
+                                x0 = fmaxf(x0, 0.0f); x1 = fmaxf(x1, 0.0f);
+                                __nv_bfloat162 pk = __floats2bfloat162_rn(x0, x1);
+                                packed[j] = *reinterpret_cast<uint32_t*>(&pk);
+                            }
+                            st_global_v8(out + off + chunk * 32 + v * 16, packed);
+                        }
+                    }
+                }
+                // Publish "this warp's part of tile i is in global memory and visible to the TMA (async proxy)".  The
+                // fence waits for the stores to land, so with enough tiles in flight it is deferred until the next
+                // accumulator is ready (the producer needs tile i only T tiles later); tiny batches publish eagerly.
+                done++;
+                if (!lazy) {
+                    fence_proxy_async();
+                    __threadfence();
+                    __syncwarp();
+                    if (lane == 0) epi_done[warp - 2] = done;
+                }
+            }
+            if (blk_second) x = (x + 2) % 3;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) { tc_fence_after(); tmem2_dealloc(tmem_base, kTmemCols2); }
+}
+
+int tc_tower_launch(cudaStream_t stream, const CUtensorMap* maps_dev, const float* bias, void* const* act, const int* n_boards_dev,
+                    int n_boards_static, int n_layers, int grid) {
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(conv_tower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<2>::kTotal) != cudaSuccess) return -2;
+        attr = true;
+    }
+    if (grid <= 0) grid = 148;
+    grid &= ~1;
+    TowerParams p;
+    p.maps = maps_dev; p.bias = bias;
+    for (int i = 0; i < 3; i++) p.act[i] = (__nv_bfloat16*)act[i];
+    p.n_boards_ptr = n_boards_dev; p.n_boards_static = n_boards_static; p.n_layers = n_layers;
+    conv_tower_kernel<<<grid, kThreads2, ConvSmem<2>::kTotal, stream>>>(p);
+    return cudaGetLastError() == cudaSuccess ? 0 : -4;
+}
+
 // ---------------------------------------------------------------------------------------------- host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
