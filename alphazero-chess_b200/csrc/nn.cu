@@ -347,7 +347,7 @@ int net_forward_bf16(az_engine* e, const int* n_dev, int n_static, float* policy
     NetWeights* w = e->net;
     if (!w->loaded) return set_err(e, AZ_ERR_NO_WEIGHTS, "az_load_weights has not been called");
     const int grid = e->sm_count & ~1;
-    e->n_launches += 22;
+    e->n_launches += 2;  // input convolution + heads; the tower adds 1 (fused) or 20 below
     const bool sample = e->prof_every > 0 && (e->prof_counter++ % (uint64_t)e->prof_every) == 0 && e->prof_pending.size() < 4000;
     az_engine::ProfSample ps{nullptr, nullptr, 0};
     int r = tc_conv3x3_launch(e->stream, &w->map_a_in, &w->map_w_in, 64, w->f_b_in, nullptr, w->a_buf[0], n_dev, n_static, 1, grid);
@@ -361,14 +361,16 @@ int net_forward_bf16(az_engine* e, const int* n_dev, int n_static, float* policy
     }
     int x = 0;  // buffer holding the block input
     static int fused = -1;
-    if (fused < 0) { const char* v = getenv("AZ_TOWER_FUSED"); fused = v ? atoi(v) : 0; }  // opt-in: correct but currently slower than 20 launches (profiles/README.md)
+    if (fused < 0) { const char* v = getenv("AZ_TOWER_FUSED"); fused = v ? atoi(v) : 1; }
     if (fused) {
         void* act[3] = {w->a_buf[0], w->a_buf[1], w->a_buf[2]};
+        e->n_launches += 1;
         r = tc_tower_launch(e->stream, w->d_maps, w->f_b_tower, act, n_dev, n_static, 20, grid);
         if (r) return set_err(e, AZ_ERR_CUDA, "tower launch failed");
         x = 2;  // ten blocks rotate the three buffers: (0 + 10 * 2) % 3
     }
     for (int blk = 0; blk < (fused ? 0 : 10); blk++) {
+        e->n_launches += 2;
         const int y = (x + 1) % 3, z = (x + 2) % 3;
         r = tc_conv3x3_launch(e->stream, &w->map_a[x], &w->map_w_tower[2 * blk], 128, w->f_b_tower + (2 * blk) * 128, nullptr, w->a_buf[y],
                               n_dev, n_static, 1, grid);

@@ -29,7 +29,7 @@ struct ConvSmem {
     static constexpr int kWTiles = HALVES * 9;
     static constexpr int kWBytes = kWTiles * kWTileBytes;
     static constexpr int kABytes = kStages * kStageBytes;
-    static constexpr int kMisc = 1024;
+    static constexpr int kMisc = 2048;
     static constexpr int kTotal = kWBytes + kABytes + kMisc + 1024;  // + alignment slack
 };
 
@@ -399,6 +399,7 @@ struct TowerParams {
     const int* n_boards_ptr;
     int n_boards_static;
     int n_layers;              // 20
+    int dbg;                   // timing experiments only (AZ_DBG_TOWER): 1 no weight reload, 2 no epilogue wait, 4 bias of layer 0
 };
 
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -437,6 +438,7 @@ conv_tower_kernel(const TowerParams prm) {
         fence_barrier_init();
     }
     if (threadIdx.x < 8) epi_done[threadIdx.x] = 0;
+    float* bias_s = reinterpret_cast<float*>(misc + 512);  // [2][128]: bias of the current layer, double buffered by layer parity
     if (warp == 1) tmem2_alloc(tmem_ptr_s, kTmemCols2);
     tc_fence_before();
     __syncthreads();
@@ -455,7 +457,7 @@ conv_tower_kernel(const TowerParams prm) {
             const CUtensorMap* w_map = &prm.maps[3 + layer];
             for (int i = 0; i < T; i++) {
                 const int t = first_tile + i * tile_step;
-                if (layer > 0) {  // this tile's input was written by this CTA's epilogue one layer ago
+                if (layer > 0 && !(prm.dbg & 2)) {  // this tile's input was written by this CTA's epilogue one layer ago
                     const uint32_t need = (uint32_t)((layer - 1) * T + i + 1);
                     long long t0 = clock64();
                     for (;;) {
@@ -468,7 +470,7 @@ conv_tower_kernel(const TowerParams prm) {
                 for (int half = 0; half < 2; half++)
                     for (int dxi = 0; dxi < 3; dxi++) {
                         const int grp = half * 3 + dxi;
-                        if (i == 0) {  // (re)load this group's three weight tiles for the new layer
+                        if (i == 0 && (layer == 0 || !(prm.dbg & 1))) {  // (re)load this group's three weight tiles for the new layer
                             if (layer > 0) mbar_wait(&wempty_bar[grp], (uint32_t)((layer - 1) & 1), 21);
                             if (elect_one()) {
                                 if (rank == 0) mbar_arrive_expect_tx(&wfull_bar[grp], 2 * kGroupBytes);
@@ -506,7 +508,7 @@ conv_tower_kernel(const TowerParams prm) {
                         for (int dxi = 0; dxi < 3; dxi++) {
                             const int grp = half * 3 + dxi;
                             mbar_wait(&full_bar[stage], phase, 24);
-                            if (i == 0) mbar_wait(&wfull_bar[grp], (uint32_t)(layer & 1), 25);
+                            if (i == 0 && (layer == 0 || !(prm.dbg & 1))) mbar_wait(&wfull_bar[grp], (uint32_t)(layer & 1), 25);
                             tc_fence_after();
                             if (elect_one()) {
                                 const uint32_t a_lo = (smem_u32(a_sm + stage * kStageBytes) & 0x3FFFF) >> 4;
@@ -539,13 +541,18 @@ conv_tower_kernel(const TowerParams prm) {
         const int h = row >> 4, b = (row >> 3) & 1, w = row & 7;
         int lt = 0, x = 0;
         uint32_t done = 0;
-        const bool lazy = T >= 3;
+        // completion is published lazily (after the next accumulator wait) and only every 4th tile when the pair has
+        // enough tiles in flight; the producer needs tile i of this layer only T tiles later (T >= 8 leaves slack >= 4)
+        const bool lazy = T >= 8;
         for (int layer = 0; layer < NL; layer++) {
             const int blk_second = layer & 1;
             const int out_buf = blk_second ? (x + 2) % 3 : (x + 1) % 3;
             __nv_bfloat16* out = prm.act[out_buf];
             const __nv_bfloat16* residual = blk_second ? prm.act[x] : nullptr;
-            const float* bias = prm.bias + layer * 128 + ch * 64;
+            // the 8 epilogue warps switch layers together: whoever arrives refills the buffer last used two layers ago
+            if (threadIdx.x - 64 < 128) bias_s[(layer & 1) * 128 + threadIdx.x - 64] = prm.bias[layer * 128 + threadIdx.x - 64];
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const float* bias = bias_s + (layer & 1) * 128 + ch * 64;
             for (int i = 0; i < T; i++, lt++) {
                 const int t = first_tile + i * tile_step;
                 const int acc = lt & 1; const uint32_t accphase = (lt >> 1) & 1;
@@ -560,11 +567,10 @@ conv_tower_kernel(const TowerParams prm) {
                 }
                 mbar_wait(&tfull_bar[acc], accphase, 26);
                 tc_fence_after();
-                if (lazy && done > 0) {  // the previous tile's stores have had a whole tile time to land
+                if (lazy && done > 0 && (done & 3) == 0 && !(prm.dbg & 8)) {  // earlier tiles' stores have had time to land
                     fence_proxy_async();
-                    __threadfence();
                     __syncwarp();
-                    if (lane == 0) epi_done[warp - 2] = done;
+                    if (lane == 0) { __threadfence(); epi_done[warp - 2] = done; }
                 }
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 128 + ch * 64;
 #pragma unroll
@@ -584,7 +590,7 @@ conv_tower_kernel(const TowerParams prm) {
 #pragma unroll
                             for (int j = 0; j < 8; j++) {
                                 const int c = v * 16 + j * 2;
-                                const float2 bb = __ldg(reinterpret_cast<const float2*>(bias + chunk * 32 + c));
+                                const float2 bb = *reinterpret_cast<const float2*>(bias + chunk * 32 + c);
                                 float x0 = __uint_as_float(r[c]) + bb.x;
                                 float x1 = __uint_as_float(r[c + 1]) + bb.y;
                                 if (has_res) {
@@ -604,11 +610,10 @@ conv_tower_kernel(const TowerParams prm) {
                 // fence waits for the stores to land, so with enough tiles in flight it is deferred until the next
                 // accumulator is ready (the producer needs tile i only T tiles later); tiny batches publish eagerly.
                 done++;
-                if (!lazy) {
+                if (!lazy && !(prm.dbg & 8)) {
                     fence_proxy_async();
-                    __threadfence();
                     __syncwarp();
-                    if (lane == 0) epi_done[warp - 2] = done;
+                    if (lane == 0) { __threadfence(); epi_done[warp - 2] = done; }
                 }
             }
             if (blk_second) x = (x + 2) % 3;
@@ -633,6 +638,7 @@ int tc_tower_launch(cudaStream_t stream, const CUtensorMap* maps_dev, const floa
     p.maps = maps_dev; p.bias = bias;
     for (int i = 0; i < 3; i++) p.act[i] = (__nv_bfloat16*)act[i];
     p.n_boards_ptr = n_boards_dev; p.n_boards_static = n_boards_static; p.n_layers = n_layers;
+    { const char* v = getenv("AZ_DBG_TOWER"); p.dbg = v ? atoi(v) : 0; }
     conv_tower_kernel<<<grid, kThreads2, ConvSmem<2>::kTotal, stream>>>(p);
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
