@@ -67,23 +67,44 @@ void launch_encode_bf16_wire(cudaStream_t s, const az_position* wire, __nv_bfloa
 // device helper used by the search kernels: writes the 64x64 bf16 plane tile of one position (one warp)
 #ifdef __CUDACC__
 __device__ __forceinline__ void encode_bf16_warp(const DPos& p, __nv_bfloat16* out /*[64][64]*/, int lane) {
+    // to_tensor (chess.rs:191-245) in the layout the first convolution reads: [square][64 channels] bf16, 19 channels used.
+    // Each lane builds two squares: one piece plane at most, four constant castling planes, ep, two constant counters.
+    // Channels 24..63 of every square stay zero (zero-filled at allocation, never written).
+    const int turn = meta_turn(p.meta);
     const u64 occ = occupied(p);
-    const u64 ours = meta_turn(p.meta) == 0 ? p.white : occ ^ p.white;
-    const u64 theirs = occ ^ ours;
+    const u64 ours = turn == 0 ? p.white : occ ^ p.white;
     const int pep = pseudo_legal_ep(p);
-    // 64 squares x 3 chunks of 8 channels (16 B each) hold the 19 planes; chunks 3..7 of every square stay zero
-    // (the buffer is zero-filled when it is allocated and nothing ever writes there)
-    for (int item = lane; item < 192; item += 32) {
-        const int sq = item / 3, chunk = item - sq * 3;
-        uint32_t packed[4] = {0, 0, 0, 0};
+    const int c = meta_castling(p.meta);
+    const int us_r = (c >> (turn * 2)) & 3, th_r = (c >> ((turn ^ 1) * 2)) & 3;
+    const uint32_t ONE = 0x3F80u;  // bf16 1.0
+    // planes 12..15 as two packed words (12|13, 14|15)
+    const uint32_t castle_lo = ((us_r & 1) ? ONE : 0u) | ((us_r & 2) ? ONE << 16 : 0u);
+    const uint32_t castle_hi = ((th_r & 1) ? ONE : 0u) | ((th_r & 2) ? ONE << 16 : 0u);
+    __nv_bfloat16 hm = __float2bfloat16_rn(__fdiv_rn((float)meta_halfmoves(p.meta), 100.0f));
+    __nv_bfloat16 fm = __float2bfloat16_rn(__fdiv_rn((float)meta_fullmoves(p.meta), 200.0f));
+    const uint32_t hm_bits = *reinterpret_cast<unsigned short*>(&hm), fm_bits = *reinterpret_cast<unsigned short*>(&fm);
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int c = chunk * 8 + j;
-            const float v = c < AZ_NUM_PLANES ? plane_value(p, c, sq, pep, ours, theirs) : 0.0f;
-            __nv_bfloat16 h = __float2bfloat16_rn(v);
-            packed[j >> 1] |= (uint32_t)(*reinterpret_cast<unsigned short*>(&h)) << ((j & 1) * 16);
+    for (int k = 0; k < 2; k++) {
+        const int sqc = lane + 32 * k;               // canonical square (rank flipped for Black)
+        const int sq = turn ? (sqc ^ 56) : sqc;
+        const u64 b = bit(sq);
+        int plane = -1;
+        if (occ & b) {
+            const int role = (p.pawn & b) ? 0 : (p.knight & b) ? 1 : (p.bishop & b) ? 2 : (p.rook & b) ? 3 : (p.queen & b) ? 4 : 5;
+            plane = role + ((ours & b) ? 0 : 6);
         }
-        reinterpret_cast<uint4*>(out)[sq * 8 + chunk] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        uint32_t w[10];
+        const uint32_t pv = (plane & 1) ? ONE << 16 : ONE;
+#pragma unroll
+        for (int j = 0; j < 6; j++) w[j] = (plane >= 0 && (plane >> 1) == j) ? pv : 0u;   // planes 0..11 live in words 0..5
+        w[6] = castle_lo;
+        w[7] = castle_hi;
+        w[8] = (sq == pep ? ONE : 0u) | (hm_bits << 16);                    // planes 16, 17
+        w[9] = fm_bits;                                                    // plane 18 (19 is padding)
+        uint4* o = reinterpret_cast<uint4*>(out) + sqc * 8;
+        o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+        o[2] = make_uint4(w[8], w[9], 0u, 0u);
     }
 }
 #endif
