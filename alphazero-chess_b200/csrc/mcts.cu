@@ -443,10 +443,15 @@ __device__ void move_step(Ctx& x) {
     az_sample* smp = nullptr;
     if (sidx_slot < MAX_SAMPLE_PLIES) {
         smp = x.ptr.game_samples + (size_t)x.g * MAX_SAMPLE_PLIES + sidx_slot;
-        for (int i = x.lane; i < nv; i += 32) {
-            const size_t e = off + x.sh->sidx[i];
-            smp->index[i] = (uint16_t)(x.ptr.edge_mv[e] >> 16);
-            smp->count[i] = (uint16_t)x.ptr.edge_N[e];
+        for (int i = x.lane; i < AZ_MAX_MOVES; i += 32) {  // unused tail entries are zero (deterministic records)
+            uint16_t si = 0, sc = 0;
+            if (i < nv) {
+                const size_t e = off + x.sh->sidx[i];
+                si = (uint16_t)(x.ptr.edge_mv[e] >> 16);
+                sc = (uint16_t)x.ptr.edge_N[e];
+            }
+            smp->index[i] = si;
+            smp->count[i] = sc;
         }
     }
     // ---- action (training.rs:310-321)

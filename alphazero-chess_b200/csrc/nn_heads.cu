@@ -56,22 +56,29 @@ k_heads_mma(const __nv_bfloat16* __restrict__ tower, const __nv_bfloat16* __rest
                 for (int nt = 0; nt < 5; nt++)
 #pragma unroll
                     for (int i = 0; i < 4; i++) d1[mt][nt][i] = 0.0f;
-            const uint32_t* X = reinterpret_cast<const uint32_t*>(tower + (size_t)b * 64 * 128);  // [square][64 pairs]
+            // A fragments with 16-byte loads: thread (g, tig) fetches channels blk*32 + tig*8 .. +7 of its two rows and
+            // uses them for TWO k-steps.  The K order inside a 32-channel block is therefore permuted (k-step A takes
+            // sub-channels 0-3 of every thread's group, k-step B 4-7); the weight fragments below use the same
+            // permutation, which leaves the dot products unchanged.
+            const uint4* X = reinterpret_cast<const uint4*>(tower + (size_t)b * 64 * 128);  // [square][16 x 16 B]
 #pragma unroll 2
-            for (int ks = 0; ks < 8; ks++) {
-                uint32_t bf[5][2];
+            for (int blk = 0; blk < 4; blk++) {
+                uint2 bfA[5], bfB[5];
 #pragma unroll
                 for (int nt = 0; nt < 5; nt++) {
-                    const uint32_t* wp = reinterpret_cast<const uint32_t*>(s_w40 + (nt * 8 + g) * HW40_PITCH + ks * 16 + tig * 2);
-                    bf[nt][0] = wp[0];
-                    bf[nt][1] = wp[4];
+                    const uint4 wv = *reinterpret_cast<const uint4*>(s_w40 + (nt * 8 + g) * HW40_PITCH + blk * 32 + tig * 8);
+                    bfA[nt] = make_uint2(wv.x, wv.y);
+                    bfB[nt] = make_uint2(wv.z, wv.w);
                 }
 #pragma unroll
                 for (int mt = 0; mt < 4; mt++) {
-                    const uint32_t* xp = X + (mt * 16 + g) * 64 + ks * 8 + tig;
-                    const uint32_t a0 = __ldg(xp), a1 = __ldg(xp + 8 * 64), a2 = __ldg(xp + 4), a3 = __ldg(xp + 8 * 64 + 4);
+                    const uint4 lo = __ldg(X + (mt * 16 + g) * 16 + blk * 4 + tig);
+                    const uint4 hi = __ldg(X + (mt * 16 + g + 8) * 16 + blk * 4 + tig);
 #pragma unroll
-                    for (int nt = 0; nt < 5; nt++) mma_bf16_16816(d1[mt][nt], a0, a1, a2, a3, bf[nt][0], bf[nt][1]);
+                    for (int nt = 0; nt < 5; nt++) {
+                        mma_bf16_16816(d1[mt][nt], lo.x, hi.x, lo.y, hi.y, bfA[nt].x, bfA[nt].y);
+                        mma_bf16_16816(d1[mt][nt], lo.z, hi.z, lo.w, hi.w, bfB[nt].x, bfB[nt].y);
+                    }
                 }
             }
             // bias + ReLU; value hidden (columns 32..39) to shared memory as the flattened [c*64 + square] row

@@ -257,7 +257,7 @@ def run_ours(args, rank, world, local_rank):
             tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
             if os.path.exists(tp):
                 with open(tp) as f:
-                    traffic = json.load(f).get("conv3x3_tc_dram_bytes_per_launch")
+                    traffic = json.load(f).get("conv_tower_kernel_dram_bytes_per_launch" if fused else "conv3x3_tc2_dram_bytes_per_launch")
             kname = ("conv_tower_kernel (the 20 3x3 128->128 convolutions of the tower in one persistent tcgen05 cta_group::2 launch)"
                      if fused else "conv3x3_tc2_kernel<2> (tcgen05 cta_group::2 3x3 128->128 convolution, 20 of 23 launches per wave)")
             roof = {"bound": "tensor", "kernel": kname,

@@ -62,3 +62,47 @@ def test_selfplay_counters_and_network_path():
         assert st.positions >= 64  # every game has made at least one move after 40 waves of 16-simulation searches
         s = e.selfplay_drain()
         assert len(s) == st.pending_samples
+
+
+def test_sharded_games_equal_unsharded():
+    """Multi-GPU parity on one device: a game's record depends only on (seed, game id), so two engines that own disjoint
+    id ranges (what two ranks do) produce exactly the records one engine produces for the union."""
+    sims, stub_seed = 16, 23
+
+    def run(first_id, n):
+        with az.Engine(max_games=n, num_simulations=sims, seed=7) as e:
+            e.set_evaluator_stub(1, stub_seed)
+            e.selfplay_begin(n, first_game_id=first_id)
+            out = []
+            for _ in range(400):
+                st = e.selfplay_step(64)
+                if st.pending_samples:
+                    out.append(e.selfplay_drain())
+                if st.games_finished >= 2 * n:
+                    break
+            return np.concatenate(out)
+
+    whole = run(100, 8)
+    parts = np.concatenate([run(100, 4), run(104, 4)])
+
+    def records(samples, gid):
+        r = samples[samples["game_id"] == gid]
+        r = r[np.argsort(r["ply"], kind="stable")]
+        # a finished game restarts under the next free id, so two shards may both have played the same id: the copies
+        # must be identical (the record depends on the id only); keep one
+        keep = [0] if len(r) else []
+        for k in range(1, len(r)):
+            if r[k]["ply"] == r[k - 1]["ply"]:
+                assert r[k].tobytes() == r[k - 1].tobytes()
+            else:
+                keep.append(k)
+        return r[keep]
+
+    compared = 0
+    for gid in range(100, 108):
+        a, b = records(whole, gid), records(parts, gid)
+        if len(a) == 0 or len(b) == 0:
+            continue
+        assert a.tobytes() == b.tobytes(), gid
+        compared += 1
+    assert compared >= 6
