@@ -140,7 +140,7 @@ void az_engine_destroy(az_engine* e) {
     cudaFree(e->d_value); cudaFree(e->d_scores); cudaFree(e->d_perft_count); cudaFree(e->d_perft_nodes);
     for (auto p : e->perft_pos) cudaFree(p);
     for (auto p : e->perft_root) cudaFree(p);
-    for (auto& ps : e->prof_pending) { cudaEventDestroy(ps.a); cudaEventDestroy(ps.b); }
+    for (auto& ps : e->prof_pending) { if (ps.adv) cudaEventDestroy(ps.adv); cudaEventDestroy(ps.in0); cudaEventDestroy(ps.a); cudaEventDestroy(ps.b); cudaEventDestroy(ps.h1); }
     if (e->prof_counts_host) cudaFreeHost(e->prof_counts_host);
     if (e->timer0) { cudaEventDestroy(e->timer0); cudaEventDestroy(e->timer1); }
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -186,12 +186,17 @@ int az_profile_read(az_engine* e, az_profile* out) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, ps.a, ps.b) == cudaSuccess) {
             e->prof_ms += ms; e->prof_samples++; e->prof_boards += (uint64_t)e->prof_counts_host[ps.slot];
+            if (cudaEventElapsedTime(&ms, ps.in0, ps.a) == cudaSuccess) e->prof_input_ms += ms;
+            if (cudaEventElapsedTime(&ms, ps.b, ps.h1) == cudaSuccess) e->prof_heads_ms += ms;
+            if (ps.adv && cudaEventElapsedTime(&ms, ps.adv, ps.in0) == cudaSuccess) e->prof_adv_ms += ms;
         }
-        cudaEventDestroy(ps.a); cudaEventDestroy(ps.b);
+        if (ps.adv) cudaEventDestroy(ps.adv);
+        cudaEventDestroy(ps.in0); cudaEventDestroy(ps.a); cudaEventDestroy(ps.b); cudaEventDestroy(ps.h1);
     }
     e->prof_pending.clear();
     out->tower_ms = e->prof_ms; out->tower_samples = e->prof_samples; out->tower_boards = e->prof_boards;
-    e->prof_ms = 0; e->prof_samples = 0; e->prof_boards = 0;
+    out->input_ms = e->prof_input_ms; out->heads_ms = e->prof_heads_ms; out->advance_ms = e->prof_adv_ms;
+    e->prof_ms = 0; e->prof_samples = 0; e->prof_boards = 0; e->prof_input_ms = 0; e->prof_heads_ms = 0; e->prof_adv_ms = 0;
     return AZ_OK;
 }
 uint64_t az_launch_count(const az_engine* e) { return e ? e->n_launches : 0; }

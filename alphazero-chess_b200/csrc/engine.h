@@ -52,11 +52,12 @@ struct az_engine {
     cudaEvent_t timer0 = nullptr, timer1 = nullptr;
     int prof_every = 0;
     uint64_t prof_counter = 0;
-    struct ProfSample { cudaEvent_t a, b; int slot; };
+    struct ProfSample { cudaEvent_t adv, in0, a, b, h1; int slot; };  // advance start, input conv start, tower start/end, heads end
+    cudaEvent_t prof_adv_event = nullptr;  // recorded before k_advance when the coming forward will be sampled
     std::vector<ProfSample> prof_pending;
     int* prof_counts_host = nullptr;   // pinned ring of batch sizes
     int prof_slot = 0;
-    double prof_ms = 0.0;
+    double prof_ms = 0.0, prof_input_ms = 0.0, prof_heads_ms = 0.0, prof_adv_ms = 0.0;
     uint64_t prof_samples = 0, prof_boards = 0;
 
     azb::NetWeights* net = nullptr;

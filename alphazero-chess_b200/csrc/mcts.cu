@@ -870,6 +870,11 @@ static int run_wave(az_engine* e, SearchState* st) {
     const int blocks = (st->prm.n_games + WARPS - 1) / WARPS;
     st->prm.priors_scattered = (e->stub_kind == 0 && e->cfg.precision != 1) ? 1 : 0;
     AZ_CUDA(e, cudaMemsetAsync(st->ptr.batch_count, 0, sizeof(int), e->stream));
+    if (e->prof_every > 0 && e->stub_kind == 0 && e->cfg.precision != 1 && (e->prof_counter % (uint64_t)e->prof_every) == 0 &&
+        !e->prof_adv_event) {
+        cudaEventCreate(&e->prof_adv_event);
+        cudaEventRecord(e->prof_adv_event, e->stream);
+    }
     e->n_launches++;
     k_advance<<<blocks, WARPS * 32, 0, e->stream>>>(st->prm, st->ptr);
     AZ_CUDA(e, cudaGetLastError());

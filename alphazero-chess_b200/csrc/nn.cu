@@ -349,7 +349,11 @@ int net_forward_bf16(az_engine* e, const int* n_dev, int n_static, float* policy
     const int grid = e->sm_count & ~1;
     e->n_launches += 2;  // input convolution + heads; the tower adds 1 (fused) or 20 below
     const bool sample = e->prof_every > 0 && (e->prof_counter++ % (uint64_t)e->prof_every) == 0 && e->prof_pending.size() < 4000;
-    az_engine::ProfSample ps{nullptr, nullptr, 0};
+    az_engine::ProfSample ps{nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+    if (sample) {
+        ps.adv = e->prof_adv_event; e->prof_adv_event = nullptr;
+        cudaEventCreate(&ps.in0); cudaEventRecord(ps.in0, e->stream);
+    }
     int r = tc_conv3x3_launch(e->stream, &w->map_a_in, &w->map_w_in, 64, w->f_b_in, nullptr, w->a_buf[0], n_dev, n_static, 1, grid);
     if (r) return set_err(e, AZ_ERR_CUDA, "tc conv (input) launch failed");
     if (sample) {
@@ -380,12 +384,14 @@ int net_forward_bf16(az_engine* e, const int* n_dev, int n_static, float* policy
         if (r) return set_err(e, AZ_ERR_CUDA, "tc conv launch failed");
         x = z;
     }
-    if (sample) { cudaEventRecord(ps.b, e->stream); e->prof_pending.push_back(ps); }
+    if (sample) cudaEventRecord(ps.b, e->stream);
     static int heads_variant = -1;
     if (heads_variant < 0) { const char* v = getenv("AZ_HEADS_VARIANT"); heads_variant = v ? atoi(v) : 1; }
-    if (heads_variant == 1) return launch_heads_mma(e, w->a_buf[x], n_dev, n_static, policy_out, value_out, scatter);
-    const int hgrid = n_dev ? w->max_boards : n_static;
-    return launch_heads<true, false>(e, w->a_buf[x], n_dev, n_static, hgrid, policy_out, value_out);
+    int hr;
+    if (heads_variant == 1) hr = launch_heads_mma(e, w->a_buf[x], n_dev, n_static, policy_out, value_out, scatter);
+    else hr = launch_heads<true, false>(e, w->a_buf[x], n_dev, n_static, n_dev ? w->max_boards : n_static, policy_out, value_out);
+    if (sample) { cudaEventCreate(&ps.h1); cudaEventRecord(ps.h1, e->stream); e->prof_pending.push_back(ps); }
+    return hr;
 }
 
 int net_forward_fp32(az_engine* e, const float* planes, const int* n_dev, int n_static, float* policy_out, float* value_out) {

@@ -38,8 +38,11 @@ k_heads_mma(const __nv_bfloat16* __restrict__ tower, const __nv_bfloat16* __rest
     __shared__ float s_b40[40], s_b2[64], s_vsum[8][8];
     const int n = n_dev ? *n_dev : n_static;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31, g = lane >> 2, tig = lane & 3;
-    for (int i = t; i < 40 * 128; i += 256) s_w40[(i >> 7) * HW40_PITCH + (i & 127)] = w40[i];
-    for (int i = t; i < 64 * 32; i += 256) s_w2[(i >> 5) * HW2_PITCH + (i & 31)] = wp2[i];
+    // weights to shared memory with 16-byte copies (8 bf16): 40 rows x 16 chunks and 64 rows x 4 chunks
+    for (int i = t; i < 40 * 16; i += 256)
+        *reinterpret_cast<uint4*>(s_w40 + (i >> 4) * HW40_PITCH + (i & 15) * 8) = __ldg(reinterpret_cast<const uint4*>(w40) + i);
+    for (int i = t; i < 64 * 4; i += 256)
+        *reinterpret_cast<uint4*>(s_w2 + (i >> 2) * HW2_PITCH + (i & 3) * 8) = __ldg(reinterpret_cast<const uint4*>(wp2) + i);
     if (t < 40) s_b40[t] = b40[t];
     if (t < 64) s_b2[t] = bp2[t];
     __syncthreads();

@@ -289,6 +289,10 @@ def run_ours(args, rank, world, local_rank):
             "nn_tensor_frac_whole_step": evals * az.FLOPS_PER_EVAL / (ms_all * 1e-3) / 1e12 / (peak_tf * world),
             "e2e": {"value": e2e_sims / (e2e_ms * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "api": "az_search: G host-resident roots in, dense visit counts out"},
+            "wave_phases_us": None if not prof.tower_samples else {
+                "k_advance": 1e3 * prof.advance_ms / prof.tower_samples, "input_conv": 1e3 * prof.input_ms / prof.tower_samples,
+                "tower": 1e3 * prof.tower_ms / prof.tower_samples, "heads": 1e3 * prof.heads_ms / prof.tower_samples,
+                "wave_total": 1e3 * ms_all / max(args.steps * S, 1)},
             "gpu_launches": int(vec[4]),
             "clocks": clocks,
             "roofline": roof,

@@ -171,6 +171,9 @@ typedef struct az_profile {
     double tower_ms;        /* summed duration of the sampled 20-convolution towers */
     uint64_t tower_samples; /* number of sampled forwards */
     uint64_t tower_boards;  /* summed batch sizes of the sampled forwards */
+    double input_ms;        /* input convolution of the sampled forwards */
+    double heads_ms;        /* policy/value heads of the sampled forwards */
+    double advance_ms;      /* search kernel (k_advance) that produced the sampled batches (0 outside search/self-play) */
 } az_profile;
 int az_timer_start(az_engine* eng);
 int az_timer_stop(az_engine* eng, float* ms_out);
