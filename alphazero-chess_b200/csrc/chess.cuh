@@ -275,6 +275,197 @@ __device__ __forceinline__ GenInfo gen_legal(const DPos& p, Sink& s) {
     return gi;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Warp-cooperative legal move generation (same list, same order as gen_legal<ListSink>).
+// Every lane owns one "query square" and computes the same five attack sets from it (rook-, bishop-, knight-, king- and
+// pawn-pattern) without divergence; what the sets mean depends on the lane's job:
+//   lanes  0..15  our i-th non-king piece (ascending square): its move targets
+//   lanes 16..23  the king's eight neighbour squares: is the square attacked (king removed from the occupancy)?
+//   lane  24      the king square: checkers              lane 25  snipers -> slider blockers (pins)
+//   lanes 26,27   castling transit / destination squares (king side), lanes 28,29,30 (queen side)
+//   lane  31      en passant: the king square with the capture played
+// Items are then ordered exactly like shakmaty's generator (category, from) by a prefix sum over lanes.
+__device__ __forceinline__ int nth_set_bit(u64 bb, int n) {  // position of the n-th (0-based) set bit, bb has more than n bits
+    const unsigned lo = (unsigned)bb, hi = (unsigned)(bb >> 32);
+    const int cl = __popc(lo);
+    return n < cl ? (int)__fns(lo, 0, n + 1) : 32 + (int)__fns(hi, 0, n - cl + 1);
+}
+__device__ __forceinline__ u64 shfl_u64(u64 v, int src) {
+    const unsigned lo = __shfl_sync(0xffffffffu, (unsigned)v, src), hi = __shfl_sync(0xffffffffu, (unsigned)(v >> 32), src);
+    return ((u64)hi << 32) | lo;
+}
+
+__device__ __forceinline__ GenInfo warp_gen_legal(const DPos& p, uint16_t* __restrict__ moves, int lane, int& n_out) {
+    const int us = meta_turn(p.meta);
+    const u64 occ = occupied(p);
+    const u64 ours = us == 0 ? p.white : occ ^ p.white;
+    const u64 theirs = occ ^ ours;
+    const int ksq = lsb(p.king & ours);
+    const u64 kbit = bit(ksq);
+    const u64 occ_nok = occ ^ kbit;
+    const int base = us * 56;
+    const int ep = meta_ep(p.meta);
+    const u64 pieces = ours ^ kbit;  // our non-king pieces
+    const int n_pieces = popc(pieces);
+
+    // ---- phase A: query square + occupancy of every lane
+    int sq = ksq;
+    u64 o = occ;
+    bool job = false;
+    int ep_from = -1, ep_from2 = -1;
+    if (lane < 16) {
+        job = lane < n_pieces;
+        if (job) sq = nth_set_bit(pieces, lane);
+    } else if (lane < 24) {
+        const int d = lane - 16;
+        const int df = (d == 0 || d == 3 || d == 5) ? -1 : (d == 1 || d == 6) ? 0 : 1;   // a1-relative 3x3 ring
+        const int dr = d < 3 ? -1 : d < 5 ? 0 : 1;
+        const int f = (ksq & 7) + df, r = (ksq >> 3) + dr;
+        job = f >= 0 && f < 8 && r >= 0 && r < 8 && !(ours & bit((r & 7) * 8 + (f & 7)));
+        if (job) sq = r * 8 + f;
+        o = occ_nok;
+    } else if (lane == 24) {
+        job = true;
+    } else if (lane == 25) {
+        job = true; o = 0;
+    } else if (lane <= 30) {
+        // castling squares: 26: f-file, 27: g-file (rook hopped), 28: d-file, 29: c-file, 30: c-file (rook hopped)
+        const int file = lane == 26 ? 5 : lane == 27 ? 6 : lane == 28 ? 3 : 2;
+        sq = base + file;
+        o = occ_nok;
+        if (lane == 27) o ^= bit(base + 7) ^ bit(base + 5);
+        if (lane == 30) o ^= bit(base) ^ bit(base + 3);
+        job = true;
+    } else {
+        // en passant: up to two capturing pawns; the second is checked by re-using this lane after the first
+        if (ep >= 0) {
+            u64 c = p.pawn & ours & pawn_attacks_bb(us ^ 1, bit(ep));
+            if (c) { ep_from = lsb(c); c &= c - 1; if (c) ep_from2 = lsb(c); }
+        }
+        job = ep_from >= 0;
+        if (job) o = (occ ^ bit(ep_from) ^ bit((ep_from & 56) | (ep & 7))) | bit(ep);
+    }
+    // ---- the five attack patterns from (sq, o): identical instruction stream on every lane
+    const u64 sb = bit(sq);
+    u64 R = rook_attacks(sq, o);
+    u64 B = bishop_attacks(sq, o);
+    const u64 N = knight_attacks_bb(sb);
+    const u64 K = king_attacks_bb(sb);
+    const u64 P = pawn_attacks_bb(us, sb);
+    const u64 attackers = theirs & ((R & (p.rook | p.queen)) | (B & (p.bishop | p.queen)) | (N & p.knight) | (K & p.king) | (P & p.pawn));
+
+    // second en-passant candidate (rare): same test with the other pawn
+    bool ep_ok1 = false, ep_ok2 = false;
+    if (lane == 31 && job) {
+        const int cap = (ep_from & 56) | (ep & 7);
+        ep_ok1 = (attackers & ~bit(cap)) == 0;
+        if (ep_from2 >= 0) {
+            const u64 o2 = (occ ^ bit(ep_from2) ^ bit(cap)) | bit(ep);
+            ep_ok2 = (attackers_to(p, ksq, theirs, us ^ 1, o2) & ~bit(cap)) == 0;
+        }
+    }
+    // ---- phase B: checkers and blockers for everyone
+    const u64 checkers = shfl_u64(attackers, 24);
+    u64 blockers = 0;
+    if (lane == 25) {
+        u64 snipers = theirs & ((R & (p.rook | p.queen)) | (B & (p.bishop | p.queen)));
+        for (; snipers; snipers &= snipers - 1) {
+            const u64 b = between_bb(ksq, lsb(snipers)) & occ;
+            if ((b & (b - 1)) == 0) blockers |= b;
+        }
+    }
+    blockers = shfl_u64(blockers, 25);
+    const bool in_check = checkers != 0;
+    const bool single = in_check && (checkers & (checkers - 1)) == 0;
+    const u64 target = !in_check ? ~ours : single ? (between_bb(ksq, lsb(checkers)) | checkers) : 0ULL;
+    // king targets: neighbour lanes whose square is not attacked
+    const unsigned safe_mask = __ballot_sync(0xffffffffu, lane >= 16 && lane < 24 && job && attackers == 0);
+    u64 king_targets = 0;
+    {
+        u64 mine = (lane >= 16 && lane < 24 && job && attackers == 0) ? sb : 0ULL;
+        for (int d = 4; d; d >>= 1) mine |= shfl_u64(mine, (lane ^ d));   // OR over the 8 lanes 16..23 (xor stays inside)
+        king_targets = shfl_u64(mine, 16);
+        (void)safe_mask;
+    }
+    // castling: gathered from lanes 26..30
+    const unsigned att_mask = __ballot_sync(0xffffffffu, attackers != 0);
+    const int rights = meta_castling(p.meta) >> (us * 2);
+    const bool castle_k = (rights & 1) && ksq == base + 4 && !in_check && !(occ & (0x60ULL << base)) && !(att_mask & (3u << 26));
+    const bool castle_q = (rights & 2) && ksq == base + 4 && !in_check && !(occ & (0x0EULL << base)) && !(att_mask & (7u << 28));
+    const bool e1 = __shfl_sync(0xffffffffu, (int)ep_ok1, 31) != 0, e2 = __shfl_sync(0xffffffffu, (int)ep_ok2, 31) != 0;
+    const int epf1 = __shfl_sync(0xffffffffu, ep_from, 31), epf2 = __shfl_sync(0xffffffffu, ep_from2, 31);
+
+    // ---- phase C: one item per lane = (category, from, targets, kind)
+    // categories: 0 ep, 1 king-in-check, 2 pawn captures, 3 promotion captures, 4 pushes, 5 promotion pushes, 6 double pushes,
+    //             7 N, 8 B, 9 R, 10 Q, 11 king (not in check), 12 O-O, 13 O-O-O
+    int cat = 15, from = 0, count = 0, kind = 0;   // kind: 0 targets, 1 promo targets, 2 pushes, 3 promo pushes, 4 single special
+    u64 tg = 0;
+    int delta = 0, special_to = 0;
+    if (lane < 16) {
+        if (job) {
+            from = sq;
+            const u64 pin = (blockers & sb) ? line_through(ksq, sq) : ~0ULL;
+            if (p.pawn & sb) {
+                tg = P & theirs & target & pin;
+                const bool seventh = (sq >> 3) == (us == 0 ? 6 : 1);
+                cat = seventh ? 3 : 2; kind = seventh ? 1 : 0;
+            } else if (p.knight & sb) { tg = (blockers & sb) ? 0ULL : (N & target); cat = 7; }
+            else if (p.bishop & sb) { tg = B & target & pin; cat = 8; }
+            else if (p.rook & sb) { tg = R & target & pin; cat = 9; }
+            else { tg = (R | B) & target & pin; cat = 10; }
+            count = popc(tg) * (kind == 1 ? 4 : 1);
+        }
+    } else if (lane == 16 || lane == 17 || lane == 18) {
+        // pawn pushes as sets (ordered by destination)
+        const u64 pawns = p.pawn & ours;
+        const u64 pushers = pawns & ~(blockers & ~file_mask(ksq));
+        const u64 single_p = (us == 0 ? pushers << 8 : pushers >> 8) & ~occ;
+        delta = us == 0 ? 8 : -8;
+        if (lane == 16) { tg = single_p & target & ~BACKRANKS; cat = 4; kind = 2; count = popc(tg); }
+        else if (lane == 17) { tg = single_p & target & BACKRANKS; cat = 5; kind = 3; count = 4 * popc(tg); }
+        else {
+            tg = (us == 0 ? single_p << 8 : single_p >> 8) & (us == 0 ? 0x00000000FF000000ULL : 0x000000FF00000000ULL) & ~occ & target;
+            cat = 6; kind = 2; delta *= 2; count = popc(tg);
+        }
+    } else if (lane == 19) {
+        tg = king_targets; from = ksq; cat = in_check ? 1 : 11; count = popc(tg);
+    } else if (lane == 20) {
+        if (castle_k) { cat = 12; kind = 4; from = ksq; special_to = base + 7; count = 1; }
+    } else if (lane == 21) {
+        if (castle_q) { cat = 13; kind = 4; from = ksq; special_to = base; count = 1; }
+    } else if (lane == 22) {
+        if (e1) { cat = 0; kind = 4; from = epf1; special_to = ep; count = 1; }
+    } else if (lane == 23) {
+        if (e2) { cat = 0; kind = 4; from = epf2; special_to = ep; count = 1; }
+    }
+    // ---- phase D: offsets in (category, from, lane) order
+    const int key = (cat << 12) | (from << 5) | lane;
+    int offset = 0, total = 0;
+#pragma unroll
+    for (int j = 0; j < 24; j++) {
+        const int kj = __shfl_sync(0xffffffffu, key, j), cj = __shfl_sync(0xffffffffu, count, j);
+        if (kj < key) offset += cj;
+        total += cj;
+    }
+    // ---- phase E: emit
+    if (count) {
+        uint16_t* out = moves + offset;
+        if (kind == 0) { for (u64 t = tg; t; t &= t - 1) *out++ = mk_move(from, lsb(t), 0, 0); }
+        else if (kind == 1) {
+            for (u64 t = tg; t; t &= t - 1) { const int to = lsb(t); *out++ = mk_move(from, to, 4, 0); *out++ = mk_move(from, to, 3, 0); *out++ = mk_move(from, to, 2, 0); *out++ = mk_move(from, to, 1, 0); }
+        } else if (kind == 2) { for (u64 t = tg; t; t &= t - 1) { const int to = lsb(t); *out++ = mk_move(to - delta, to, 0, 0); } }
+        else if (kind == 3) {
+            for (u64 t = tg; t; t &= t - 1) { const int to = lsb(t), f = to - delta; *out++ = mk_move(f, to, 4, 0); *out++ = mk_move(f, to, 3, 0); *out++ = mk_move(f, to, 2, 0); *out++ = mk_move(f, to, 1, 0); }
+        } else { *out = mk_move(from, special_to, 0, 1); }
+    }
+    __syncwarp();
+    n_out = total;
+    GenInfo gi;
+    gi.checkers = checkers;
+    gi.has_legal_ep = e1 || e2;
+    return gi;
+}
+
 // shakmaty play_unchecked for a wire move (assumed legal)
 __device__ __forceinline__ DPos make_move(const DPos& p, uint16_t mv) {
     const int from = mv & 63, to = (mv >> 6) & 63, promo = (mv >> 12) & 7, special = mv >> 15;

@@ -154,16 +154,17 @@ struct Ctx {
 // Expands `mv` from `parent` on lane 0: child position, its legal moves (into shared memory), mate / stalemate /
 // insufficient material.  Repetition and move-count draws are decided afterwards by the whole warp.
 __device__ __forceinline__ void lane0_make_child(Ctx& x, const DPos& parent, uint16_t mv) {
+    // every lane builds the child (cheap, uniform), then the warp generates its legal moves cooperatively
+    DPos child = make_move(parent, mv);
+    int n = 0;
+    const GenInfo gi = warp_gen_legal(child, x.sh->moves, x.lane, n);
+    int term = 0;
+    if (n == 0) term = gi.checkers ? 2 : 1;
+    else if (insufficient_material(child)) term = 1;
+    set_key_bits(child, gi.has_legal_ep);
     if (x.lane == 0) {
-        DPos child = make_move(parent, mv);
-        ListSink sink{x.sh->moves, 0};
-        GenInfo gi = gen_legal(child, sink);
-        int term = 0;
-        if (sink.n == 0) term = gi.checkers ? 2 : 1;
-        else if (insufficient_material(child)) term = 1;
-        set_key_bits(child, gi.has_legal_ep);
         x.sh->child = child;
-        x.sh->n_moves = sink.n;
+        x.sh->n_moves = n;
         x.sh->term = term;
     }
     __syncwarp();
