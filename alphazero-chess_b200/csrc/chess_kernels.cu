@@ -43,6 +43,23 @@ void launch_movegen(cudaStream_t s, const az_position* wire, int n, uint16_t* mo
     k_movegen<<<(n + MG_THREADS - 1) / MG_THREADS, MG_THREADS, 0, s>>>(wire, n, moves, index, count);
 }
 
+// one warp per position: the cooperative generator the search kernel uses (same output contract as k_movegen)
+__global__ void __launch_bounds__(128) k_movegen_warp(const az_position* __restrict__ wire, int n, uint16_t* __restrict__ moves_out,
+                                                      int32_t* __restrict__ count_out) {
+    __shared__ uint16_t s_moves[4][AZ_MAX_MOVES];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 4 + w;
+    if (i >= n) return;
+    DPos p = dpos_from_wire(wire[i]);
+    int cnt = 0;
+    warp_gen_legal(p, s_moves[w], lane, cnt);
+    for (int k = lane; k < AZ_MAX_MOVES; k += 32) moves_out[(size_t)i * AZ_MAX_MOVES + k] = k < cnt ? s_moves[w][k] : (uint16_t)AZ_MOVE_NONE;
+    if (lane == 0) count_out[i] = cnt;
+}
+void launch_movegen_warp(cudaStream_t s, const az_position* wire, int n, uint16_t* moves, int32_t* count) {
+    if (n > 0) k_movegen_warp<<<(n + 3) / 4, 128, 0, s>>>(wire, n, moves, count);
+}
+
 // ---------------------------------------------------------------------------------------------------- play_move
 // chess.rs:36-63 driven by a policy index (tree.rs:211-212)
 __global__ void k_play_move(az_position* __restrict__ wire, const az_position* __restrict__ hist, const uint32_t* __restrict__ hist_off,

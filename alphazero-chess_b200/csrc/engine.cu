@@ -216,6 +216,20 @@ int az_movegen(az_engine* e, int n, const az_position* pos, az_move* moves_out, 
     return AZ_OK;
 }
 
+int az_dbg_movegen_warp(az_engine* e, int n, const az_position* pos, az_move* moves_out, int32_t* count_out) {
+    int r = check_batch(e, n);
+    if (r || n == 0) return r;
+    if (!pos || !moves_out || !count_out) return set_err(e, AZ_ERR_INVALID_ARGUMENT, "null buffer");
+    AZ_CUDA(e, cudaMemcpyAsync(e->d_wire, pos, (size_t)n * sizeof(az_position), cudaMemcpyHostToDevice, e->stream));
+    e->n_launches++;
+    launch_movegen_warp(e->stream, e->d_wire, n, e->d_moves, e->d_count);
+    AZ_CUDA(e, cudaGetLastError());
+    AZ_CUDA(e, cudaMemcpyAsync(moves_out, e->d_moves, (size_t)n * AZ_MAX_MOVES * 2, cudaMemcpyDeviceToHost, e->stream));
+    AZ_CUDA(e, cudaMemcpyAsync(count_out, e->d_count, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
+    AZ_CUDA(e, cudaStreamSynchronize(e->stream));
+    return AZ_OK;
+}
+
 int az_play_move(az_engine* e, int n, az_position* pos_inout, const az_position* history, const uint32_t* hist_offsets,
                  const uint16_t* action_index, int32_t* result_out) {
     int r = check_batch(e, n);

@@ -74,6 +74,7 @@ int check_cuda(az_engine* e, cudaError_t r, const char* what);
 
 // chess_kernels.cu
 void launch_movegen(cudaStream_t s, const az_position* wire, int n, uint16_t* moves, uint16_t* index, int32_t* count);
+void launch_movegen_warp(cudaStream_t s, const az_position* wire, int n, uint16_t* moves, int32_t* count);
 void launch_play_move(cudaStream_t s, az_position* wire, const az_position* hist, const uint32_t* hist_off, const uint16_t* action,
                       int32_t* result, int n, RuleParams rp);
 void launch_move_to_index(cudaStream_t s, const az_position* wire, const uint16_t* moves, uint16_t* index, int n);

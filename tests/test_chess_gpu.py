@@ -40,6 +40,34 @@ def test_movegen_lists_identical(eng, corpus):
         assert np.all(moves[i, count[i]:] == az.MOVE_NONE)
 
 
+def test_warp_cooperative_generator_matches(eng, corpus):
+    """The search kernel's warp-cooperative generator must emit exactly the serial generator's list (and the oracle's)."""
+    import ctypes
+
+    positions, _ = corpus
+    extra = ["8/8/8/8/1pPp4/8/8/K6k b - c3 0 1",            # two pawns can capture en passant
+             "4k3/8/8/8/1pPp4/8/8/K3R3 b - c3 0 1",          # ... while in check from the rook: neither resolves it
+             "k7/8/8/8/8/8/1p1p1p2/R1B1N2K b - - 0 1",       # promotions with and without capture, several pawns
+             "r3k2r/8/8/8/8/8/8/R3K2R b KQkq - 0 1", "4k3/8/8/8/8/8/8/R3K2R w KQ - 0 1",
+             "3rkr2/8/8/8/8/8/8/R3K2R w KQ - 0 1",            # both castling paths attacked
+             "4k3/8/8/8/8/5n2/8/R3K2R w KQ - 0 1",            # knight check: no castling
+             "Q2k4/8/8/8/8/8/8/4K3 b - - 0 1", "3k4/3Q4/8/8/8/8/8/3RK3 b - - 0 1"]
+    pos = np.concatenate([positions, np.array([orc.from_fen(f) for f in extra], orc.POSITION_DTYPE)])
+    n = len(pos)
+    moves = np.empty((n, az.MAX_MOVES), np.uint16)
+    count = np.empty(n, np.int32)
+    p = np.ascontiguousarray(pos, az.POSITION_DTYPE)
+    rc = az.lib().az_dbg_movegen_warp(eng._h, n, ctypes.c_void_p(p.ctypes.data), ctypes.c_void_p(moves.ctypes.data),
+                                      ctypes.c_void_p(count.ctypes.data))
+    assert rc == 0
+    ref_moves, _, ref_count = eng.movegen(pos)
+    assert np.array_equal(count, ref_count)
+    assert np.array_equal(moves, ref_moves)
+    for i in range(len(positions), n):
+        mv, _ = orc.legal_moves(pos[i])
+        assert np.array_equal(moves[i, : count[i]], mv), i
+
+
 def test_movegen_empty_and_ragged(eng):
     m, ix, c = eng.movegen(np.zeros(0, az.POSITION_DTYPE))
     assert m.shape == (0, 256) and c.shape == (0,)
