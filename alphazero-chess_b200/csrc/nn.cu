@@ -226,14 +226,13 @@ __global__ void __launch_bounds__(256) k_conv3x3_f32(const float* __restrict__ i
     }
 }
 
-// ---------------------------------------------------------------------------------------------- heads
+// ---------------------------------------------------------------------------------------------- heads (fp32 path)
 // One block (256 threads) per board: policy_conv_1+bn+relu and value_conv+bn+relu (40 x 128 per square),
 // policy_conv_2 (64 x 32 per square), softmax over the 4096 logits, value MLP + tanh (agent.rs:124-141).
-// IN_BF16: tower output NHWC bf16 [b][64][128]; otherwise NCHW f32 [b][128][64].
+// Tower output NCHW f32 [b][128][64].  (The bf16 path uses the tensor-core kernel in nn_heads.cu.)
 constexpr int HEAD_SMEM = (128 * 65 + 128 * 40 + 40 * 64 + 64) * 4;
 
-template <bool IN_BF16, bool PRECISE>
-__global__ void __launch_bounds__(256) k_heads(const void* __restrict__ tower, const float* __restrict__ w40t, const float* __restrict__ b40,
+__global__ void __launch_bounds__(256) k_heads_f32(const float* __restrict__ tower, const float* __restrict__ w40t, const float* __restrict__ b40,
                                                const float* __restrict__ wp2t, const float* __restrict__ bp2, const float* __restrict__ wl1,
                                                const float* __restrict__ bl1, const float* __restrict__ wl2, const float* __restrict__ bl2,
                                                float* __restrict__ policy_out, float* __restrict__ value_out, const int* __restrict__ n_dev,
@@ -247,16 +246,8 @@ __global__ void __launch_bounds__(256) k_heads(const void* __restrict__ tower, c
     const int b = blockIdx.x;
     if (b >= n) return;
     const int t = threadIdx.x;
-    if (IN_BF16) {
-        const __nv_bfloat16* src = reinterpret_cast<const __nv_bfloat16*>(tower) + (size_t)b * 64 * 128;
-        for (int i = t; i < 64 * 64; i += 256) {  // pairs of channels
-            const int sq = i >> 6, c2 = (i & 63) * 2;
-            __nv_bfloat162 v = reinterpret_cast<const __nv_bfloat162*>(src)[i];
-            xs[c2 * 65 + sq] = __low2float(v);
-            xs[(c2 + 1) * 65 + sq] = __high2float(v);
-        }
-    } else {
-        const float* src = reinterpret_cast<const float*>(tower) + (size_t)b * 128 * 64;
+    {
+        const float* src = tower + (size_t)b * 128 * 64;
         for (int i = t; i < 128 * 64; i += 256) xs[(i >> 6) * 65 + (i & 63)] = src[i];
     }
     for (int i = t; i < 128 * 40; i += 256) wts[i] = w40t[i];
@@ -300,7 +291,7 @@ __global__ void __launch_bounds__(256) k_heads(const void* __restrict__ tower, c
     __syncthreads();
     float lsum = 0.0f;
     for (int i = t; i < 4096; i += 256) {
-        float ev = PRECISE ? expf(logits[i] - gmax) : __expf(logits[i] - gmax);
+        float ev = expf(logits[i] - gmax);
         logits[i] = ev;
         lsum += ev;
     }
@@ -327,18 +318,12 @@ __global__ void __launch_bounds__(256) k_heads(const void* __restrict__ tower, c
     if (t == 0) value_out[b] = tanhf(red[16] + red[17] + bl2[0]);
 }
 
-template <bool IN_BF16, bool PRECISE>
-static int launch_heads(az_engine* e, const void* tower, const int* n_dev, int n_static, int grid, float* policy_out, float* value_out) {
+static int launch_heads_f32(az_engine* e, const float* tower, const int* n_dev, int n_static, int grid, float* policy_out, float* value_out) {
     NetWeights* w = e->net;
     static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(k_heads<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HEAD_SMEM);
-        cudaFuncSetAttribute(k_heads<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HEAD_SMEM);
-        cudaFuncSetAttribute(k_heads<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HEAD_SMEM);
-        attr = true;
-    }
+    if (!attr) { cudaFuncSetAttribute(k_heads_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, HEAD_SMEM); attr = true; }
     if (grid <= 0) return 0;
-    k_heads<IN_BF16, PRECISE><<<grid, 256, HEAD_SMEM, e->stream>>>(tower, w->f_w40t, w->f_b40, w->f_wp2t, w->f_bp2, w->f_wl1, w->f_bl1,
+    k_heads_f32<<<grid, 256, HEAD_SMEM, e->stream>>>(tower, w->f_w40t, w->f_b40, w->f_wp2t, w->f_bp2, w->f_wl1, w->f_bl1,
                                                                   w->f_wl2, w->f_bl2, policy_out, value_out, n_dev, n_static);
     return check_cuda(e, cudaGetLastError(), "k_heads");
 }
@@ -385,11 +370,7 @@ int net_forward_bf16(az_engine* e, const int* n_dev, int n_static, float* policy
         x = z;
     }
     if (sample) cudaEventRecord(ps.b, e->stream);
-    static int heads_variant = -1;
-    if (heads_variant < 0) { const char* v = getenv("AZ_HEADS_VARIANT"); heads_variant = v ? atoi(v) : 1; }
-    int hr;
-    if (heads_variant == 1) hr = launch_heads_mma(e, w->a_buf[x], n_dev, n_static, policy_out, value_out, scatter);
-    else hr = launch_heads<true, false>(e, w->a_buf[x], n_dev, n_static, n_dev ? w->max_boards : n_static, policy_out, value_out);
+    const int hr = launch_heads_mma(e, w->a_buf[x], n_dev, n_static, policy_out, value_out, scatter);
     if (sample) { cudaEventCreate(&ps.h1); cudaEventRecord(ps.h1, e->stream); e->prof_pending.push_back(ps); }
     return hr;
 }
@@ -416,7 +397,7 @@ int net_forward_fp32(az_engine* e, const float* planes, const int* n_dev, int n_
         x = z;
     }
     AZ_CUDA(e, cudaGetLastError());
-    return launch_heads<false, true>(e, w->g_buf[x], n_dev, n_static, grid, policy_out, value_out);
+    return launch_heads_f32(e, w->g_buf[x], n_dev, n_static, grid, policy_out, value_out);
 }
 
 }  // namespace azb

@@ -1,8 +1,8 @@
-// 3x3 "same" convolution of the policy/value tower (agent.rs:22-23,36,40,74-76) as an implicit GEMM on the
-// 5th-generation tensor cores: tcgen05.mma with TMEM accumulators, operands staged by TMA.
+// 3x3 "same" convolutions of the policy/value network (agent.rs:22-23,36,40,74-76) as implicit GEMMs on the
+// 5th-generation tensor cores: tcgen05.mma (cta_group::2) with TMEM accumulators, operands staged by TMA.
 //
-//   M = 128 rows  = 2 boards x 64 squares, row r <-> (rank h = r>>4, board b = (r>>3)&1, file w = r&7)
-//   N = 64        = one half of the 128 output channels (CTA parity picks the half; its weights stay resident in SMEM)
+//   M = 256 rows  = 4 boards x 64 squares per CTA pair (128 rows per CTA); within a CTA row r <-> (rank r>>4, board (r>>3)&1, file r&7)
+//   N = 128       = all output channels; each CTA of the pair keeps the weights of 64 of them resident in SMEM
 //   K = 9 taps x Cin, consumed in 64-channel blocks
 //
 // Activations are NHWC bf16 [board][rank][file][C].  One TMA box {64 ch, 8 files, 2 boards, 10 ranks} is fetched per
@@ -10,6 +10,10 @@
 // zero-filled = "same" padding), and because the box is laid out rank-major the three dy taps are just three
 // 1024B-aligned row windows of the same SMEM stage.  So 6 boxes (120 KB) feed the 72 MMAs of a tile instead of 18.
 // BatchNorm is folded into weights/bias on the host; the epilogue applies bias (+ residual) (+ ReLU) and writes bf16.
+//
+//   conv3x3_tc2_kernel<HALVES>  one layer per launch (the 19->128 input convolution, and the tower with AZ_TOWER_FUSED=0)
+//   conv_tower_kernel           the 20 tower layers in one persistent launch
+// The single-CTA first version (N = 64 per CTA, issue-bound) is described in profiles/r1_conv_ablation.md.
 #include "tc_conv.cuh"
 #include "nn_tc.h"
 #include <cuda_bf16.h>
@@ -18,10 +22,8 @@
 
 namespace azb {
 
-constexpr int kThreads = 192;            // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
 constexpr int kStageBytes = 160 * 128;   // {10 ranks x 2 boards x 8 files} rows x 64 channels bf16
 constexpr int kWTileBytes = 64 * 128;    // 64 output channels x 64 input channels bf16
-constexpr int kTmemCols = 128;           // 2 accumulator stages x 64 fp32 columns
 
 template <int HALVES>
 struct ConvSmem {
@@ -32,169 +34,6 @@ struct ConvSmem {
     static constexpr int kMisc = 2048;
     static constexpr int kTotal = kWBytes + kABytes + kMisc + 1024;  // + alignment slack
 };
-
-template <int HALVES>
-__global__ void __launch_bounds__(kThreads, 1)
-conv3x3_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap w_map,
-                  const float* __restrict__ bias, const __nv_bfloat16* __restrict__ residual,
-                  __nv_bfloat16* __restrict__ out, const int* __restrict__ n_boards_ptr, int n_boards_static, int relu, int dbg) {
-    using S = ConvSmem<HALVES>;
-    constexpr int NS = S::kStages;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* w_sm = smem;
-    uint8_t* a_sm = smem + S::kWBytes;
-    uint8_t* misc = a_sm + S::kABytes;
-    float* bias_s = reinterpret_cast<float*>(misc);                     // 64 floats
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(misc + 256);       // NS
-    uint64_t* empty_bar = full_bar + NS;                                // NS
-    uint64_t* wfull_bar = empty_bar + NS;                               // kWTiles
-    uint64_t* tfull_bar = wfull_bar + S::kWTiles;                       // 2
-    uint64_t* tempty_bar = tfull_bar + 2;                               // 2
-    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_boards = n_boards_ptr ? *n_boards_ptr : n_boards_static;
-    const int n_mtiles = (n_boards + 1) >> 1;
-    const int nhalf = blockIdx.x & 1;
-    const int first_tile = blockIdx.x >> 1, tile_step = gridDim.x >> 1;
-
-    if (threadIdx.x == 0) {
-        tma_prefetch_desc(&in_map);
-        tma_prefetch_desc(&w_map);
-        for (int i = 0; i < NS; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < S::kWTiles; i++) mbar_init(&wfull_bar[i], 1);
-        for (int i = 0; i < 2; i++) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 128); }
-        fence_barrier_init();
-    }
-    if (threadIdx.x >= 64 && threadIdx.x < 128) bias_s[threadIdx.x - 64] = bias[nhalf * 64 + threadIdx.x - 64];
-    if (warp == 1) tmem_alloc(tmem_ptr_s, kTmemCols);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr_s;
-
-    if (warp == 0) {
-        if (lane == 0) {
-            // ------------------------------------------------------------ TMA producer
-            int stage = 0; uint32_t phase = 0; bool first = true;
-            for (int mt = first_tile; mt < n_mtiles; mt += tile_step) {
-                for (int half = 0; half < HALVES; half++)
-                    for (int dxi = 0; dxi < 3; dxi++) {
-                        if (first) {  // the weight tiles this stage multiplies with; they stay resident afterwards
-                            for (int dyi = 0; dyi < 3; dyi++) {
-                                int wt = (half * 3 + dxi) * 3 + dyi, tap = dyi * 3 + dxi;
-                                mbar_arrive_expect_tx(&wfull_bar[wt], kWTileBytes);
-                                tma_load_2d(w_sm + wt * kWTileBytes, &w_map, &wfull_bar[wt], half * 64, tap * 128 + nhalf * 64);
-                            }
-                        }
-                        mbar_wait(&empty_bar[stage], phase ^ 1, 1);
-                        if (dbg & 1) { mbar_arrive(&full_bar[stage]); }
-                        else {
-                            mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
-                            tma_load_4d(a_sm + stage * kStageBytes, &in_map, &full_bar[stage], half * 64, dxi - 1, mt * 2, -1);
-                        }
-                        if (++stage == NS) { stage = 0; phase ^= 1; }
-                    }
-                first = false;
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            // ------------------------------------------------------------ MMA issuer (one thread)
-            constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
-            int stage = 0; uint32_t phase = 0; int lt = 0;
-            const uint32_t w_base = smem_u32(w_sm);
-            for (int mt = first_tile; mt < n_mtiles; mt += tile_step, lt++) {
-                const int acc = lt & 1; const uint32_t accphase = (lt >> 1) & 1;
-                mbar_wait(&tempty_bar[acc], accphase ^ 1, 2);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * 64;
-                uint32_t accumulate = 0;
-                for (int half = 0; half < HALVES; half++)
-                    for (int dxi = 0; dxi < 3; dxi++) {
-                        mbar_wait(&full_bar[stage], phase, 3);
-                        tc_fence_after();
-                        const uint32_t a_base = smem_u32(a_sm + stage * kStageBytes);
-#pragma unroll
-                        for (int dyi = 0; dyi < 3; dyi++) {
-                            const int wt = (half * 3 + dxi) * 3 + dyi;
-                            if (lt == 0) { mbar_wait(&wfull_bar[wt], 0, 4); tc_fence_after(); }
-#pragma unroll
-                            for (int k = 0; k < 4; k++) {
-                                uint64_t ad = umma_smem_desc_sw128(a_base + dyi * 2048 + k * 32);
-                                uint64_t bd = umma_smem_desc_sw128(w_base + wt * kWTileBytes + k * 32);
-                                if (!(dbg & 2)) umma_bf16(d_tmem, ad, bd, idesc, accumulate);
-                                accumulate = 1;
-                            }
-                        }
-                        umma_commit(&empty_bar[stage]);
-                        if (++stage == NS) { stage = 0; phase ^= 1; }
-                    }
-                umma_commit(&tfull_bar[acc]);
-            }
-        }
-    } else {
-        // ---------------------------------------------------------------- epilogue (4 warps = 128 TMEM lanes)
-        const int q = warp & 3;
-        const int row = q * 32 + lane;
-        const int h = row >> 4, b = (row >> 3) & 1, w = row & 7;
-        int lt = 0;
-        for (int mt = first_tile; mt < n_mtiles; mt += tile_step, lt++) {
-            const int acc = lt & 1; const uint32_t accphase = (lt >> 1) & 1;
-            const int board = mt * 2 + b;
-            const bool valid = board < n_boards;
-            const size_t off = ((size_t)board * 64 + h * 8 + w) * 128 + nhalf * 64;
-            if (dbg & 4) {
-                mbar_wait(&tfull_bar[acc], accphase, 5);
-                tc_fence_before();
-                mbar_arrive(&tempty_bar[acc]);
-                continue;
-            }
-            uint4 res[8];
-            if (residual != nullptr && valid) {
-                const uint4* rp = reinterpret_cast<const uint4*>(residual + off);
-#pragma unroll
-                for (int i = 0; i < 8; i++) res[i] = __ldg(rp + i);
-            }
-            mbar_wait(&tfull_bar[acc], accphase, 5);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 64;
-#pragma unroll
-            for (int chunk = 0; chunk < 2; chunk++) {
-                uint32_t r[32];
-                tmem_ld32(taddr + chunk * 32, r);
-                tmem_ld_wait();
-                if (chunk == 1) { tc_fence_before(); mbar_arrive(&tempty_bar[acc]); }
-                if (valid) {
-                    uint4* op = reinterpret_cast<uint4*>(out + off + chunk * 32);
-#pragma unroll
-                    for (int v = 0; v < 4; v++) {
-                        uint32_t packed[4];
-#pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            int c = v * 8 + j * 2;
-                            float x0 = __uint_as_float(r[c]) + bias_s[chunk * 32 + c];
-                            float x1 = __uint_as_float(r[c + 1]) + bias_s[chunk * 32 + c + 1];
-                            if (residual != nullptr) {
-                                uint32_t rr = reinterpret_cast<const uint32_t*>(&res[chunk * 4 + v])[j];
-                                x0 += __uint_as_float(rr << 16);
-                                x1 += __uint_as_float(rr & 0xFFFF0000u);
-                            }
-                            if (relu) { x0 = fmaxf(x0, 0.0f); x1 = fmaxf(x1, 0.0f); }
-                            __nv_bfloat162 p = __floats2bfloat162_rn(x0, x1);
-                            packed[j] = *reinterpret_cast<uint32_t*>(&p);
-                        }
-                        op[v] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                    }
-                }
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
-}
 
 // ================================================================================================================
 // CTA-pair version (cta_group::2): the two SMs of a pair compute one 256-row tile (4 boards) against all 128 output
@@ -399,10 +238,8 @@ struct TowerParams {
     const int* n_boards_ptr;
     int n_boards_static;
     int n_layers;              // 20
-    int dbg;                   // timing experiments only (AZ_DBG_TOWER): 1 no weight reload, 2 no epilogue wait, 4 bias of layer 0
 };
 
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 conv_tower_kernel(const TowerParams prm) {
@@ -457,7 +294,7 @@ conv_tower_kernel(const TowerParams prm) {
             const CUtensorMap* w_map = &prm.maps[3 + layer];
             for (int i = 0; i < T; i++) {
                 const int t = first_tile + i * tile_step;
-                if (layer > 0 && !(prm.dbg & 2)) {  // this tile's input was written by this CTA's epilogue one layer ago
+                if (layer > 0) {  // this tile's input was written by this CTA's epilogue one layer ago
                     const uint32_t need = (uint32_t)((layer - 1) * T + i + 1);
                     long long t0 = clock64();
                     for (;;) {
@@ -470,7 +307,7 @@ conv_tower_kernel(const TowerParams prm) {
                 for (int half = 0; half < 2; half++)
                     for (int dxi = 0; dxi < 3; dxi++) {
                         const int grp = half * 3 + dxi;
-                        if (i == 0 && (layer == 0 || !(prm.dbg & 1))) {  // (re)load this group's three weight tiles for the new layer
+                        if (i == 0) {  // (re)load this group's three weight tiles for the new layer
                             if (layer > 0) mbar_wait(&wempty_bar[grp], (uint32_t)((layer - 1) & 1), 21);
                             if (elect_one()) {
                                 if (rank == 0) mbar_arrive_expect_tx(&wfull_bar[grp], 2 * kGroupBytes);
@@ -508,7 +345,7 @@ conv_tower_kernel(const TowerParams prm) {
                         for (int dxi = 0; dxi < 3; dxi++) {
                             const int grp = half * 3 + dxi;
                             mbar_wait(&full_bar[stage], phase, 24);
-                            if (i == 0 && (layer == 0 || !(prm.dbg & 1))) mbar_wait(&wfull_bar[grp], (uint32_t)(layer & 1), 25);
+                            if (i == 0) mbar_wait(&wfull_bar[grp], (uint32_t)(layer & 1), 25);
                             tc_fence_after();
                             if (elect_one()) {
                                 const uint32_t a_lo = (smem_u32(a_sm + stage * kStageBytes) & 0x3FFFF) >> 4;
@@ -567,7 +404,7 @@ conv_tower_kernel(const TowerParams prm) {
                 }
                 mbar_wait(&tfull_bar[acc], accphase, 26);
                 tc_fence_after();
-                if (lazy && done > 0 && (done & 3) == 0 && !(prm.dbg & 8)) {  // earlier tiles' stores have had time to land
+                if (lazy && done > 0 && (done & 3) == 0) {  // earlier tiles' stores have had time to land
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) { __threadfence(); epi_done[warp - 2] = done; }
@@ -610,7 +447,7 @@ conv_tower_kernel(const TowerParams prm) {
                 // fence waits for the stores to land, so with enough tiles in flight it is deferred until the next
                 // accumulator is ready (the producer needs tile i only T tiles later); tiny batches publish eagerly.
                 done++;
-                if (!lazy && !(prm.dbg & 8)) {
+                if (!lazy) {
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) { __threadfence(); epi_done[warp - 2] = done; }
@@ -638,7 +475,6 @@ int tc_tower_launch(cudaStream_t stream, const CUtensorMap* maps_dev, const floa
     p.maps = maps_dev; p.bias = bias;
     for (int i = 0; i < 3; i++) p.act[i] = (__nv_bfloat16*)act[i];
     p.n_boards_ptr = n_boards_dev; p.n_boards_static = n_boards_static; p.n_layers = n_layers;
-    { const char* v = getenv("AZ_DBG_TOWER"); p.dbg = v ? atoi(v) : 0; }
     conv_tower_kernel<<<grid, kThreads2, ConvSmem<2>::kTotal, stream>>>(p);
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
@@ -690,39 +526,19 @@ int tc_conv3x3_launch(cudaStream_t stream, const CUtensorMap* in_map, const CUte
                       const void* residual, void* out, const int* n_boards_dev, int n_boards_static, int relu, int grid, int dbg) {
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e1 = cudaFuncSetAttribute(conv3x3_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<1>::kTotal);
-        cudaError_t e2 = cudaFuncSetAttribute(conv3x3_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<2>::kTotal);
+        cudaError_t e1 = cudaFuncSetAttribute(conv3x3_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<1>::kTotal);
+        cudaError_t e2 = cudaFuncSetAttribute(conv3x3_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<2>::kTotal);
         if (e1 != cudaSuccess || e2 != cudaSuccess) return -2;
         attr_done = true;
     }
     if (grid <= 0) grid = 148;
-    grid &= ~1;
-    static int variant = -1;
-    if (variant < 0) { const char* v = getenv("AZ_CONV_VARIANT"); variant = v ? atoi(v) : 2; }
-    if (variant == 2) {
-        static bool attr2 = false;
-        if (!attr2) {
-            cudaError_t e1 = cudaFuncSetAttribute(conv3x3_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<1>::kTotal);
-            cudaError_t e2 = cudaFuncSetAttribute(conv3x3_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<2>::kTotal);
-            if (e1 != cudaSuccess || e2 != cudaSuccess) return -2;
-            attr2 = true;
-        }
-        if (cin == 64)
-            conv3x3_tc2_kernel<1><<<grid, kThreads2, ConvSmem<1>::kTotal, stream>>>(*in_map, *w_map, bias, (const __nv_bfloat16*)residual,
-                                                                                   (__nv_bfloat16*)out, n_boards_dev, n_boards_static, relu, dbg);
-        else if (cin == 128)
-            conv3x3_tc2_kernel<2><<<grid, kThreads2, ConvSmem<2>::kTotal, stream>>>(*in_map, *w_map, bias, (const __nv_bfloat16*)residual,
-                                                                                   (__nv_bfloat16*)out, n_boards_dev, n_boards_static, relu, dbg);
-        else
-            return -3;
-        return cudaGetLastError() == cudaSuccess ? 0 : -4;
-    }
+    grid &= ~1;  // CTA pairs
     if (cin == 64)
-        conv3x3_tc_kernel<1><<<grid, kThreads, ConvSmem<1>::kTotal, stream>>>(*in_map, *w_map, bias, (const __nv_bfloat16*)residual,
-                                                                              (__nv_bfloat16*)out, n_boards_dev, n_boards_static, relu, dbg);
+        conv3x3_tc2_kernel<1><<<grid, kThreads2, ConvSmem<1>::kTotal, stream>>>(*in_map, *w_map, bias, (const __nv_bfloat16*)residual,
+                                                                               (__nv_bfloat16*)out, n_boards_dev, n_boards_static, relu, dbg);
     else if (cin == 128)
-        conv3x3_tc_kernel<2><<<grid, kThreads, ConvSmem<2>::kTotal, stream>>>(*in_map, *w_map, bias, (const __nv_bfloat16*)residual,
-                                                                              (__nv_bfloat16*)out, n_boards_dev, n_boards_static, relu, dbg);
+        conv3x3_tc2_kernel<2><<<grid, kThreads2, ConvSmem<2>::kTotal, stream>>>(*in_map, *w_map, bias, (const __nv_bfloat16*)residual,
+                                                                               (__nv_bfloat16*)out, n_boards_dev, n_boards_static, relu, dbg);
     else
         return -3;
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
