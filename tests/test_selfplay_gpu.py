@@ -106,3 +106,42 @@ def test_sharded_games_equal_unsharded():
         assert a.tobytes() == b.tobytes(), gid
         compared += 1
     assert compared >= 6
+
+
+def test_selfplay_with_network_matches_oracle_given_identical_outputs():
+    """Whole self-play games through the tcgen05 network: the oracle replays the same games when its tree is fed the
+    outputs the GPU network produces for each position (az_forward is batch-invariant, so they are the same numbers)."""
+    sims, seed = 12, 99
+    w = az.random_weights(seed=11)
+    with az.Engine(max_games=4, num_simulations=sims, seed=seed) as e:
+        e.load_weights(w)
+        e.selfplay_begin(4, first_game_id=500)
+        samples = []
+        for _ in range(600):
+            st = e.selfplay_step(32)
+            if st.pending_samples:
+                samples.append(e.selfplay_drain())
+            if st.games_finished >= 2:
+                break
+        samples = np.concatenate(samples)
+
+        def cb(ctx, pos_ptr, pol_ptr, val_ptr):
+            pos = np.ctypeslib.as_array((np.ctypeslib.ctypes.c_uint8 * 72).from_address(pos_ptr)).view(az.POSITION_DTYPE)
+            p, v = e.forward(pos)
+            np.ctypeslib.as_array(pol_ptr, (4096,))[:] = p[0]
+            val_ptr[0] = float(v[0])
+
+        ev = orc.make_evaluator("callback", callback=orc.EVAL_FN(cb))
+        prm = orc.make_params(num_simulations=sims, seed=seed)
+        checked = 0
+        for gid in sorted(set(int(g) for g in samples["game_id"]))[:2]:
+            rec = samples[samples["game_id"] == gid]
+            rec = rec[np.argsort(rec["ply"])]
+            ep = orc.selfplay_episode(prm, ev, game_id=gid, max_steps=512)
+            assert len(rec) == ep["stats"].n_steps, gid
+            for k in range(len(rec)):
+                assert rec[k]["position"].tobytes() == ep["positions"][k].tobytes(), (gid, k)
+                assert np.array_equal(az.improved_policy(rec[k], sims) * np.float32(sims), ep["visits"][k]), (gid, k)
+                assert rec[k]["action"] == ep["action"][k] and rec[k]["final_value"] == ep["final_value"][k], (gid, k)
+            checked += 1
+        assert checked == 2
