@@ -295,6 +295,64 @@ class Engine:
         return out[: n.value]
 
 
+class ReplayBuffer:
+    """memory.rs ReplayBuffer, device resident (az_replay_*)."""
+
+    def __init__(self, engine, capacity=100_000, max_batch=512):
+        self._e = engine
+        self._L = engine._L
+        self._h = ctypes.c_void_p(0)
+        engine._check(self._L.az_replay_create(engine._h, int(capacity), int(max_batch), ctypes.byref(self._h)), "az_replay_create")
+        self._L.az_replay_destroy.restype = None
+
+    def close(self):
+        if self._h:
+            self._L.az_replay_destroy(self._h)
+            self._h = ctypes.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def add(self, samples):
+        """ReplayBuffer::add for drained az_sample records, in order; returns the number of new unique positions."""
+        s = np.ascontiguousarray(samples, SAMPLE_DTYPE)
+        nu = ctypes.c_int(0)
+        self._e._check(self._L.az_replay_add(self._h, _ptr(s), int(s.shape[0]), ctypes.byref(nu)), "az_replay_add")
+        return nu.value
+
+    def add_pending(self):
+        """Consumes the finished-game samples still in device memory; returns (steps added, new unique positions)."""
+        n, nu = ctypes.c_int(0), ctypes.c_int(0)
+        self._e._check(self._L.az_replay_add_pending(self._h, ctypes.byref(n), ctypes.byref(nu)), "az_replay_add_pending")
+        return n.value, nu.value
+
+    def __len__(self):
+        n = ctypes.c_int(0)
+        self._e._check(self._L.az_replay_len(self._h, ctypes.byref(n)), "az_replay_len")
+        return n.value
+
+    def sample(self, batch_size, seed=0):
+        """ReplayBuffer::sample: (planes [n,19,8,8], policy [n,4096], value [n]) with n = min(batch_size, len)."""
+        planes = np.empty((batch_size, NUM_PLANES, 8, 8), np.float32)
+        policy = np.empty((batch_size, ACTION_SPACE), np.float32)
+        value = np.empty(batch_size, np.float32)
+        n = ctypes.c_int(0)
+        self._e._check(self._L.az_replay_sample(self._h, int(batch_size), ctypes.c_uint64(seed), _ptr(planes), _ptr(policy), _ptr(value),
+                                                ctypes.byref(n)), "az_replay_sample")
+        return planes[: n.value], policy[: n.value], value[: n.value]
+
+    def get(self, pos):
+        p = np.ascontiguousarray(np.atleast_1d(pos), POSITION_DTYPE)
+        policy = np.empty(ACTION_SPACE, np.float32)
+        value = ctypes.c_float(0)
+        visits = ctypes.c_uint32(0)
+        self._e._check(self._L.az_replay_get(self._h, _ptr(p), _ptr(policy), ctypes.byref(value), ctypes.byref(visits)), "az_replay_get")
+        return policy, value.value, visits.value
+
+
 class Profile(ctypes.Structure):
     _fields_ = [("tower_ms", ctypes.c_double), ("tower_samples", ctypes.c_uint64), ("tower_boards", ctypes.c_uint64),
                 ("input_ms", ctypes.c_double), ("heads_ms", ctypes.c_double), ("advance_ms", ctypes.c_double)]

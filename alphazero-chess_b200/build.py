@@ -21,6 +21,7 @@ UNITS = [
     ("nn.cu", []),
     ("nn_tc.cu", []),
     ("nn_heads.cu", []),
+    ("replay.cu", ["-fmad=false"]),
     ("dbg.cu", []),
 ]
 

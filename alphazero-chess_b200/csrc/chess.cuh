@@ -549,6 +549,31 @@ __device__ __forceinline__ int pseudo_legal_ep(const DPos& p) {
     return (pawn_attacks_bb(us ^ 1, bit(ep)) & p.pawn & ours) ? ep : -1;
 }
 
+// ---- the identity of a position as Fen::from_position(.., EnPassantMode::PseudoLegal) sees it (tree.rs:214, memory.rs:42):
+// board, turn, castling rights, pseudo-legal ep square, halfmove clock, fullmove number.  Keys of the evaluation cache and
+// of the replay buffer.
+__device__ __forceinline__ u64 splitmix64(u64 x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+__device__ __forceinline__ DPos fen_key_of(const DPos& p) {
+    DPos k = p;
+    k.meta = (p.meta & 0x1FULL) | ((u64)(pseudo_legal_ep(p) + 1) << 8) | (p.meta & (0xFFFFFFFFULL << 16));
+    return k;
+}
+__device__ __forceinline__ u64 fen_key_hash(const DPos& k) {
+    u64 h = splitmix64(k.pawn);
+    h = splitmix64(h ^ k.knight); h = splitmix64(h ^ k.bishop); h = splitmix64(h ^ k.rook); h = splitmix64(h ^ k.queen);
+    h = splitmix64(h ^ k.king); h = splitmix64(h ^ k.white); h = splitmix64(h ^ k.meta);
+    return h;
+}
+__device__ __forceinline__ bool fen_key_equal(const DPos& a, const DPos& b) {
+    return a.pawn == b.pawn && a.knight == b.knight && a.bishop == b.bishop && a.rook == b.rook && a.queen == b.queen &&
+           a.king == b.king && a.white == b.white && a.meta == b.meta;
+}
+
 // stores the LEGAL ep square in the key bits of meta (chess.rs:52: HashMap<Chess,_> equality uses it)
 __device__ __forceinline__ void set_key_bits(DPos& p, bool has_legal_ep) {
     int lep = has_legal_ep ? meta_ep(p.meta) : -1;

@@ -32,12 +32,6 @@ struct WarpShared {
 
 // ------------------------------------------------------------------------------------------- deterministic RNG
 // Counter-based generator + IEEE-exact log/exp, bit-identical to oracle/mcts.cpp (spec in DESIGN.md).
-__device__ __forceinline__ u64 splitmix64(u64 x) {
-    x += 0x9E3779B97F4A7C15ULL;
-    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
-    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
-    return x ^ (x >> 31);
-}
 __device__ __forceinline__ u64 rng_u64(u64 seed, u64 game, u64 ply, u64 stream, u64 counter) {
     u64 h = splitmix64(seed);
     h = splitmix64(h ^ game);
@@ -358,17 +352,6 @@ __device__ __forceinline__ void select_leaf(Ctx& x, int& leaf_node, int& leaf_ed
 
 
 // ------------------------------------------------------------------------------------------- evaluation cache
-__device__ __forceinline__ DPos cache_key_of(const DPos& p) {
-    DPos k = p;
-    k.meta = (p.meta & 0x1FULL) | ((u64)(pseudo_legal_ep(p) + 1) << 8) | (p.meta & (0xFFFFFFFFULL << 16));
-    return k;
-}
-__device__ __forceinline__ u64 cache_hash(const DPos& k) {
-    u64 h = splitmix64(k.pawn);
-    h = splitmix64(h ^ k.knight); h = splitmix64(h ^ k.bishop); h = splitmix64(h ^ k.rook); h = splitmix64(h ^ k.queen);
-    h = splitmix64(h ^ k.king); h = splitmix64(h ^ k.white); h = splitmix64(h ^ k.meta);
-    return h;
-}
 __device__ __forceinline__ bool cache_key_equal(const CacheEntry* e, const DPos* key, int lane) {
     bool eq = true;
     if (lane < 8) eq = reinterpret_cast<const volatile u64*>(&e->key)[lane] == reinterpret_cast<const u64*>(key)[lane];
@@ -587,9 +570,9 @@ __global__ void __launch_bounds__(WARPS * 32) k_advance(SearchParams prm, Search
         }
         __syncwarp();
         if (prm.cache_mask && prm.mode == 1) {  // cache.insert (training.rs:413)
-            if (x.lane == 0) x.sh->key = cache_key_of(ptr.node_pos[x.nbase + node]);
+            if (x.lane == 0) x.sh->key = fen_key_of(ptr.node_pos[x.nbase + node]);
             __syncwarp();
-            cache_insert(x, cache_hash(x.sh->key), node, ptr.res_value[slot]);
+            cache_insert(x, fen_key_hash(x.sh->key), node, ptr.res_value[slot]);
         }
         if (node == 0) {  // MCTree::init (tree.rs:37-64): root priors, optional noise, no backup
             if (x.c.flags & 1) apply_noise(x, 0, x.c.game_id, x.c.noise_ply);
@@ -629,9 +612,9 @@ __global__ void __launch_bounds__(WARPS * 32) k_advance(SearchParams prm, Search
         if (x.lane == 0) ptr.edge_child[pe] = child;
         x.c.max_depth = max(x.c.max_depth, (uint32_t)(depth + 1));
         if (prm.cache_mask && prm.mode == 1) {  // cache.get (tree.rs:214-218): a hit needs no network evaluation
-            if (x.lane == 0) x.sh->key = cache_key_of(x.sh->child);
+            if (x.lane == 0) x.sh->key = fen_key_of(x.sh->child);
             __syncwarp();
-            const int slot = cache_lookup(x, cache_hash(x.sh->key));
+            const int slot = cache_lookup(x, fen_key_hash(x.sh->key));
             if (slot >= 0) {
                 const CacheEntry* ce = &ptr.cache_entry[slot];
                 const size_t coff = x.ebase + ptr.node_edge_off[x.nbase + child];
@@ -865,6 +848,22 @@ static int evaluate_batch(az_engine* e, SearchState* st) {
     if (e->cfg.precision == 1) return net_forward_fp32(e, q.req_f32, q.batch_count, 0, e->d_policy, e->d_value);
     HeadScatter sc{q.req_edge_off, q.req_nedges, q.edge_mv, q.edge_P};
     return net_forward_bf16(e, q.batch_count, 0, nullptr, e->d_value, &sc);
+}
+
+int search_pending_samples(az_engine* e, const az_sample** d_samples, int* n) {
+    SearchState* st = e->search;
+    if (!st->selfplay_active) return set_err(e, AZ_ERR_STATE, "az_selfplay_begin has not been called");
+    Counters c;
+    AZ_CUDA(e, cudaMemcpyAsync(&c, st->ptr.counters, sizeof c, cudaMemcpyDeviceToHost, e->stream));
+    AZ_CUDA(e, cudaStreamSynchronize(e->stream));
+    *d_samples = st->ptr.out_samples;
+    *n = (int)std::min<unsigned long long>(c.samples_out, st->prm.sample_cap);
+    return 0;
+}
+int search_clear_pending(az_engine* e) {
+    SearchState* st = e->search;
+    AZ_CUDA(e, cudaMemsetAsync(&st->ptr.counters->samples_out, 0, sizeof(unsigned long long), e->stream));
+    return 0;
 }
 
 static int run_wave(az_engine* e, SearchState* st) {

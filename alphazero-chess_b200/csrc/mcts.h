@@ -102,6 +102,9 @@ struct SearchState {
 };
 
 int search_create(az_engine* e);
+// finished-game samples waiting in device memory (what az_selfplay_drain would copy out); clearing resets the queue
+int search_pending_samples(az_engine* e, const az_sample** d_samples, int* n);
+int search_clear_pending(az_engine* e);
 void search_destroy(az_engine* e);
 
 }  // namespace azb

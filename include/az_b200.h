@@ -164,6 +164,23 @@ int az_selfplay_begin(az_engine* eng, int n_games, uint64_t first_game_id);
 int az_selfplay_step(az_engine* eng, int waves, az_selfplay_stats* stats_out);
 int az_selfplay_drain(az_engine* eng, az_sample* out, int max_samples, int* n_out);
 
+/* ---- memory.rs: ReplayBuffer (the consumer of self-play output) ---------------------------
+ * Device resident.  az_replay_add mirrors ReplayBuffer::add (memory.rs:41-76) for a batch of EpisodeSteps applied in
+ * order: positions are de-duplicated by their FEN identity (pseudo-legal ep, counters), policy/value become running
+ * means, the oldest unique position is evicted at capacity; *new_unique_out is the sum of add()'s return values.
+ * az_replay_add_pending consumes the finished-game samples self-play left in device memory (no host round trip).
+ * az_replay_sample mirrors ReplayBuffer::sample (memory.rs:78-97): min(batch, len) distinct entries, uniformly, returned as
+ * to_tensor planes [n][19][8][8], policy [n][4096] and value [n].  Persistence (bincode save/load) is not provided. */
+typedef struct az_replay az_replay;
+int az_replay_create(az_engine* eng, int capacity, int max_batch, az_replay** out);
+void az_replay_destroy(az_replay* rp);
+int az_replay_add(az_replay* rp, const az_sample* samples, int n, int* new_unique_out);
+int az_replay_add_pending(az_replay* rp, int* n_added_out, int* new_unique_out);
+int az_replay_len(az_replay* rp, int* len_out);
+int az_replay_sample(az_replay* rp, int batch_size, uint64_t seed, float* planes_out, float* policy_out, float* value_out, int* n_out);
+/* test hook: the entry stored for one position (visit_count 0 if absent) */
+int az_replay_get(az_replay* rp, const az_position* pos, float* policy_out, float* value_out, uint32_t* visit_count_out);
+
 /* ---- measurement hooks (bench.py) -------------------------------------------------------------------------------
  * az_timer_*: CUDA events on the engine's own stream.  az_profile_enable(k): every k-th network forward brackets the
  * 20 tower convolutions with events and records the batch size; az_profile_read sums what has completed. */

@@ -56,6 +56,7 @@ def lib():
         L.orc_det_exp.argtypes = [ctypes.c_double]
         L.orc_net_create.restype = ctypes.c_void_p
         L.orc_cache_create.restype = ctypes.c_void_p
+        L.orc_replay_create.restype = ctypes.c_void_p
         L.orc_cache_size.restype = ctypes.c_uint64
         L.orc_net_array_size.restype = ctypes.c_uint64
         L.orc_init()
@@ -233,3 +234,29 @@ def cache_create():
 
 def cache_destroy(c):
     lib().orc_cache_destroy(ctypes.c_void_p(c))
+
+
+class Replay:
+    """ReplayBuffer of memory.rs restated (oracle/replay.cpp)."""
+
+    def __init__(self, capacity):
+        self.h = lib().orc_replay_create(int(capacity))
+
+    def add(self, state, improved_policy, final_value):
+        pol = np.ascontiguousarray(improved_policy, np.float32)
+        return lib().orc_replay_add(ctypes.c_void_p(self.h), _p(_one(state)), _p(pol), ctypes.c_float(final_value))
+
+    def get(self, state):
+        pol = np.zeros(ACTION_SPACE, np.float32)
+        val = ctypes.c_float(0)
+        n = lib().orc_replay_get(ctypes.c_void_p(self.h), _p(_one(state)), _p(pol), ctypes.byref(val))
+        return pol, val.value, n
+
+    def __len__(self):
+        return lib().orc_replay_len(ctypes.c_void_p(self.h))
+
+    def __del__(self):
+        try:
+            lib().orc_replay_destroy(ctypes.c_void_p(self.h))
+        except Exception:
+            pass

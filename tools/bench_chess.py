@@ -68,6 +68,33 @@ def main():
         print(json.dumps({"bench": "perft_cpu_oracle", "position": name, "depth": depth, "nodes": total, "seconds": dt,
                           "nodes_per_sec": total / dt, "cores": cores}))
     eng.close()
+    # replay buffer (memory.rs): order-exact add and batch sampling
+    e2 = az.Engine(max_games=512, num_simulations=16, seed=3)
+    e2.set_evaluator_stub(1, 8)
+    e2.selfplay_begin(512)
+    chunks = []
+    for _ in range(400):
+        st = e2.selfplay_step(64)
+        if st.pending_samples:
+            chunks.append(e2.selfplay_drain())
+        if st.games_finished >= 512:
+            break
+    samples = np.concatenate(chunks)
+    rb = az.ReplayBuffer(e2, capacity=100_000, max_batch=512)
+    t0 = time.perf_counter()
+    nu = rb.add(samples)
+    dt = time.perf_counter() - t0
+    print(json.dumps({"bench": "replay_add", "steps": int(len(samples)), "new_unique": int(nu), "seconds": dt, "steps_per_sec": len(samples) / dt,
+                      "note": "az_replay_add: H2D of 1120 B/step + one CTA applying the steps in order (bit-exact running means)"}))
+    rb.sample(512, seed=0)
+    t0 = time.perf_counter()
+    for k in range(50):
+        rb.sample(512, seed=k)
+    dt = (time.perf_counter() - t0) / 50
+    print(json.dumps({"bench": "replay_sample", "batch": 512, "seconds": dt, "batches_per_sec": 1 / dt,
+                      "note": "az_replay_sample incl. D2H of planes + dense policy rows (10.9 MB per batch)"}))
+    rb.close()
+    e2.close()
 
 
 if __name__ == "__main__":
