@@ -1,0 +1,54 @@
+#!/usr/bin/env python
+"""BASELINE config 5 in miniature: the full generation loop of train() (training.rs:70-275) on one GPU -
+self-play on the engine -> device replay buffer -> AdamW steps (PyTorch) -> weights back into the engine -> a short
+evaluation match against the previous weights.  Prints one JSON line per iteration.
+
+    python tools/run_generations.py --games 1024 --sims 64 --iterations 3
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import _pkg  # noqa: E402,F401
+import alphazero_chess_b200 as az  # noqa: E402
+from alphazero_chess_b200 import evaluation as ev  # noqa: E402
+from alphazero_chess_b200 import training as tr  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--games", type=int, default=1024)
+    ap.add_argument("--sims", type=int, default=64)
+    ap.add_argument("--iterations", type=int, default=3)
+    ap.add_argument("--eval-games", type=int, default=32)
+    ap.add_argument("--min-replay", type=int, default=5000)
+    args = ap.parse_args()
+    torch.manual_seed(42)
+    model = tr.import_weights(tr.AlphaZeroNet(), az.random_weights(seed=42)).cuda()
+    opt = tr.make_optimizer(model)
+    eng = az.Engine(max_games=args.games, num_simulations=args.sims, seed=42)
+    old = az.Engine(max_games=args.eval_games, max_batch=args.eval_games, num_simulations=args.sims, seed=42)
+    replay = az.ReplayBuffer(eng, capacity=100_000, max_batch=tr.BATCH_SIZE)
+    for it in range(args.iterations):
+        old.load_weights(tr.export_weights(model))
+        t0 = time.perf_counter()
+        m = tr.run_generation(eng, replay, model, opt, it, args.games, min_replay_size=args.min_replay)
+        m["generation_seconds"] = time.perf_counter() - t0
+        m["positions_per_sec"] = m["positions"] / m["generation_seconds"]
+        if m["trained"] and args.eval_games:
+            t1 = time.perf_counter()
+            r = ev.evaluate(ev.MctsPlayer(eng), ev.MctsPlayer(old), eng, n_games=args.eval_games, seed=it)
+            m["winrate_vs_previous"] = r["winrate"]
+            m["evaluation_seconds"] = time.perf_counter() - t1
+        print(json.dumps(m), flush=True)
+    replay.close(); eng.close(); old.close()
+
+
+if __name__ == "__main__":
+    main()
