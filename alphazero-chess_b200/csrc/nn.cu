@@ -4,6 +4,7 @@
 // BatchNorm (inference form, eps = 1e-5) is folded into the preceding convolution when the weights are imported.
 #include "nn.h"
 #include "nn_tc.h"
+#include "device_once.h"
 #include <cmath>
 #include <cstring>
 #include <cstdlib>
@@ -320,8 +321,8 @@ __global__ void __launch_bounds__(256) k_heads_f32(const float* __restrict__ tow
 
 static int launch_heads_f32(az_engine* e, const float* tower, const int* n_dev, int n_static, int grid, float* policy_out, float* value_out) {
     NetWeights* w = e->net;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(k_heads_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, HEAD_SMEM); attr = true; }
+    static PerDeviceOnce once;
+    if (once.first()) cudaFuncSetAttribute(k_heads_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, HEAD_SMEM);
     if (grid <= 0) return 0;
     k_heads_f32<<<grid, 256, HEAD_SMEM, e->stream>>>(tower, w->f_w40t, w->f_b40, w->f_wp2t, w->f_bp2, w->f_wl1, w->f_bl1,
                                                                   w->f_wl2, w->f_bl2, policy_out, value_out, n_dev, n_static);
@@ -380,8 +381,8 @@ int net_forward_fp32(az_engine* e, const float* planes, const int* n_dev, int n_
     if (!w->loaded) return set_err(e, AZ_ERR_NO_WEIGHTS, "az_load_weights has not been called");
     for (int i = 0; i < 3; i++)
         if (!w->g_buf[i]) AZ_CUDA(e, cudaMalloc(&w->g_buf[i], (size_t)w->max_boards * 128 * 64 * sizeof(float)));
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(k_conv3x3_f32<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 64 * 4); attr = true; }
+    static PerDeviceOnce once;
+    if (once.first()) cudaFuncSetAttribute(k_conv3x3_f32<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 64 * 4);
     const int grid = n_dev ? w->max_boards : n_static;
     if (grid <= 0) return 0;
     e->n_launches += 22;

@@ -6,6 +6,7 @@
 // The heads are 0.3 % of the network's FLOPs; they use mma.sync (one warp per board needs no shared-memory staging of
 // the activations) while the 99 % in the tower runs on tcgen05 (nn_tc.cu).
 #include "nn.h"
+#include "device_once.h"
 #include <algorithm>
 
 namespace azb {
@@ -216,8 +217,8 @@ int launch_heads_mma(az_engine* e, const __nv_bfloat16* tower, const int* n_dev,
     const int n_max = n_dev ? w->max_boards : n_static;
     if (n_max <= 0) return 0;
     const int grid = std::min((n_max + 7) / 8, e->sm_count);
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(k_heads_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, HEADS_DYN_SMEM); attr = true; }
+    static PerDeviceOnce once;
+    if (once.first()) cudaFuncSetAttribute(k_heads_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, HEADS_DYN_SMEM);
     HeadScatter sc{nullptr, nullptr, nullptr, nullptr};
     if (scatter) sc = *scatter;
     k_heads_mma<<<grid, 256, HEADS_DYN_SMEM, e->stream>>>(tower, w->h_w40, w->f_b40, w->h_wp2, w->f_bp2, w->h_wl1t, w->f_bl1, w->f_wl2, w->f_bl2,

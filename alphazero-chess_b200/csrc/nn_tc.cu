@@ -16,6 +16,7 @@
 // The single-CTA first version (N = 64 per CTA, issue-bound) is described in profiles/r1_conv_ablation.md.
 #include "tc_conv.cuh"
 #include "nn_tc.h"
+#include "device_once.h"
 #include <cuda_bf16.h>
 #include <cstdio>
 #include <cstdlib>
@@ -464,11 +465,10 @@ conv_tower_kernel(const TowerParams prm) {
 
 int tc_tower_launch(cudaStream_t stream, const CUtensorMap* maps_dev, const float* bias, void* const* act, const int* n_boards_dev,
                     int n_boards_static, int n_layers, int grid) {
-    static bool attr = false;
-    if (!attr) {
-        if (cudaFuncSetAttribute(conv_tower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<2>::kTotal) != cudaSuccess) return -2;
-        attr = true;
-    }
+    static PerDeviceOnce once;
+    if (once.first() &&
+        cudaFuncSetAttribute(conv_tower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<2>::kTotal) != cudaSuccess)
+        return -2;
     if (grid <= 0) grid = 148;
     grid &= ~1;
     TowerParams p;
@@ -524,12 +524,11 @@ int tc_make_weight_map(CUtensorMap* map, const void* base, int cin) {
 
 int tc_conv3x3_launch(cudaStream_t stream, const CUtensorMap* in_map, const CUtensorMap* w_map, int cin, const float* bias,
                       const void* residual, void* out, const int* n_boards_dev, int n_boards_static, int relu, int grid, int dbg) {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce once;
+    if (once.first()) {
         cudaError_t e1 = cudaFuncSetAttribute(conv3x3_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<1>::kTotal);
         cudaError_t e2 = cudaFuncSetAttribute(conv3x3_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<2>::kTotal);
         if (e1 != cudaSuccess || e2 != cudaSuccess) return -2;
-        attr_done = true;
     }
     if (grid <= 0) grid = 148;
     grid &= ~1;  // CTA pairs
