@@ -793,6 +793,11 @@ int search_create(az_engine* e) {
     p.repetitions = (int)c.repetitions; p.seed = c.seed;
     p.node_cap = c.num_simulations + 2;
     if (p.node_cap > 65535) return set_err(e, AZ_ERR_INVALID_ARGUMENT, "num_simulations must be < 65534");
+    // a game ends by the fullmove limit, so its history and its sample staging hold < 2 * num_fullmoves positions
+    if (2 * (int)c.num_fullmoves > std::min(HIST_CAP, MAX_SAMPLE_PLIES) || c.num_fullmoves == 0 || c.num_halfmoves == 0 || c.repetitions == 0)
+        return set_err(e, AZ_ERR_INVALID_ARGUMENT, "num_fullmoves must be in 1..256, num_halfmoves and repetitions positive");
+    if (!(c.c_puct > 0.0f) || !(c.dirichlet_alpha > 0.0f) || c.dirichlet_epsilon < 0.0f || c.dirichlet_epsilon > 1.0f)
+        return set_err(e, AZ_ERR_INVALID_ARGUMENT, "c_puct and dirichlet_alpha must be positive, dirichlet_epsilon in [0, 1]");
     const int per_node = c.edge_capacity_per_node > 0 ? c.edge_capacity_per_node : 96;
     p.edge_cap = std::max(p.node_cap * std::min(per_node, 218), 256);
     p.mode = 0; p.max_iters = 8; p.fp32_planes = c.precision == 1 ? 1 : 0;
