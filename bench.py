@@ -267,9 +267,10 @@ def run_ours(args, rank, world, local_rank):
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            r = cpu_port_run(az.random_weights(seed=42), S, 42, cores, 1, cores)
+            cpu_plies = 4  # a bounded sample of the same workload: about 10-20 s of host work
+            r = cpu_port_run(az.random_weights(seed=42), S, 42, cores, cpu_plies, cores)
             cpu = {"value": r["simulations"] / r["seconds"], "unit": "sims/s", "cores": cores, "kind": "port",
-                   "sample": f"{cores} games x 1 ply x {S} sims on {cores} host threads, shared evaluation cache ({r['seconds']:.1f} s)",
+                   "sample": f"{cores} games x {cpu_plies} plies x {S} sims on {cores} host threads, shared evaluation cache ({r['seconds']:.1f} s)",
                    "positions_per_sec": r["positions"] / r["seconds"], "evals_per_sec": r["evals"] / r["seconds"]}
         value = sims / (ms_all * 1e-3)
         line = {
