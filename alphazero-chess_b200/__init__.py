@@ -225,6 +225,16 @@ class Engine:
         self._check(self._L.az_perft(self._h, n, _ptr(p), int(depth), _ptr(nodes)), "az_perft")
         return nodes
 
+    def minimax(self, pos, depth):
+        """get_best_move without its random tie-break (chess.rs:295-318): (scores [n][256], count [n]); scores[i, k] is
+        -negamax(child k, depth - 1) for legal move k of position i in movegen order."""
+        p = self._positions(pos)
+        n = p.shape[0]
+        scores = np.zeros((n, MAX_MOVES), np.int32)
+        count = np.zeros(n, np.int32)
+        self._check(self._L.az_minimax(self._h, n, _ptr(p), int(depth), _ptr(scores), _ptr(count)), "az_minimax")
+        return scores, count
+
     def play_move(self, pos, action_index, history=None, hist_offsets=None):
         """play_move (chess.rs:36-63) through a policy index; returns (new positions, GameResult codes)."""
         p = self._positions(pos).copy()
@@ -388,6 +398,7 @@ _engine_measurement_methods()
 # algorithmic FLOPs of one network evaluation (2 x MAC, direct convolution)
 FLOPS_PER_EVAL = 381_272_192
 FLOPS_PER_TOWER_CONV = 2 * 64 * 128 * 1152  # one 3x3 128->128 convolution on one board
+FLOPS_PER_INPUT_CONV = 2 * 64 * 128 * 19 * 9  # the 3x3 19->128 input convolution on one board
 
 
 def improved_policy(sample, num_simulations):

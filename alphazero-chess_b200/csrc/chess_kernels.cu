@@ -2,6 +2,7 @@
 // One thread per position for the rule kernels (branch-minimised bitboard code, move lists staged in shared memory and
 // written back coalesced); one warp per position for the plane encoder.
 #include "engine.h"
+#include <climits>
 
 namespace azb {
 
@@ -212,6 +213,99 @@ __global__ void __launch_bounds__(256) k_perft_count(const DPos* __restrict__ in
 }
 void launch_perft_count(cudaStream_t s, const DPos* in, const uint32_t* in_root, int n_in, unsigned long long* nodes) {
     if (n_in > 0) k_perft_count<<<(n_in + 255) / 256, 256, 0, s>>>(in, in_root, n_in, nodes);
+}
+
+// ------------------------------------------------------------------------------------------------- minimax player
+// chess.rs:247-318 (evaluate_material / negamax / get_best_move), full width and unpruned as in the reference, as a
+// breadth-first sweep over level buffers: expand, score the horizon, then fold the children back with one integer
+// atomicMax per child (order-independent, so the result is deterministic).
+__device__ __forceinline__ int material_for_mover(const DPos& p) {  // chess.rs:254-264
+    const u64 occ = occupied(p);
+    const u64 ours = meta_turn(p.meta) == 0 ? p.white : occ ^ p.white;
+    const u64 theirs = occ ^ ours;
+    return 100 * (popc(p.pawn & ours) - popc(p.pawn & theirs)) + 320 * (popc(p.knight & ours) - popc(p.knight & theirs)) +
+           330 * (popc(p.bishop & ours) - popc(p.bishop & theirs)) + 500 * (popc(p.rook & ours) - popc(p.rook & theirs)) +
+           900 * (popc(p.queen & ours) - popc(p.queen & theirs));
+}
+
+// interior node with `depth` plies left (depth >= 1): a finished game scores itself (chess.rs:267-277), anything else is
+// expanded and starts at INT_MIN.  The root (is_root) is never treated as finished: get_best_move walks its legal moves
+// without asking (chess.rs:295-303).
+__global__ void __launch_bounds__(128) k_mm_expand(const DPos* __restrict__ in, int n_in, int depth, int is_root, DPos* __restrict__ out,
+                                                   uint32_t* __restrict__ out_parent, unsigned long long* __restrict__ out_count,
+                                                   int* __restrict__ score, unsigned int* __restrict__ first_child,
+                                                   int* __restrict__ n_child) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    uint16_t legal[AZ_MAX_MOVES];
+    int cnt = 0;
+    DPos p;
+    if (i < n_in) {
+        p = in[i];
+        ListSink sink{legal, 0};
+        const GenInfo gi = gen_legal(p, sink);
+        cnt = sink.n;
+        if (!is_root) {
+            if (cnt == 0) score[i] = gi.checkers ? -20000 - depth : 0;
+            else if (insufficient_material(p)) { score[i] = 0; cnt = 0; }
+            else score[i] = INT_MIN;
+        }
+    }
+    int incl = cnt;
+    for (int d = 1; d < 32; d <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned long long base = 0;
+    if (lane == 31 && total > 0) base = atomicAdd(out_count, (unsigned long long)total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    const unsigned long long o = base + (unsigned long long)(incl - cnt);
+    if (i < n_in && first_child) { first_child[i] = (unsigned int)o; n_child[i] = cnt; }
+    for (int k = 0; k < cnt; k++) { out[o + k] = make_move(p, legal[k]); out_parent[o + k] = (uint32_t)i; }
+}
+
+// horizon (depth 0): mate / stalemate / insufficient material, else material (chess.rs:267-280)
+__global__ void __launch_bounds__(256) k_mm_leaf(const DPos* __restrict__ in, int n_in, int* __restrict__ score) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_in) return;
+    const DPos p = in[i];
+    CountSink cs{0};
+    const GenInfo gi = gen_legal(p, cs);
+    int sc;
+    if (cs.n == 0) sc = gi.checkers ? -20000 : 0;
+    else if (insufficient_material(p)) sc = 0;
+    else sc = material_for_mover(p);
+    score[i] = sc;
+}
+
+__global__ void __launch_bounds__(256) k_mm_backup(const int* __restrict__ child_score, const uint32_t* __restrict__ child_parent,
+                                                   int n_children, int* __restrict__ parent_score) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n_children) atomicMax(&parent_score[child_parent[j]], -child_score[j]);
+}
+
+// scores of the root's legal moves, in legal-move order (the random choice among the best stays with the caller)
+__global__ void __launch_bounds__(256) k_mm_root(const unsigned int* __restrict__ first_child, const int* __restrict__ n_child,
+                                                 const int* __restrict__ child_score, int n_roots, int* __restrict__ scores_out,
+                                                 int* __restrict__ count_out) {
+    const int r = blockIdx.x, k = threadIdx.x;
+    if (r >= n_roots) return;
+    const int c = n_child[r];
+    scores_out[(size_t)r * AZ_MAX_MOVES + k] = k < c ? -child_score[first_child[r] + k] : 0;
+    if (k == 0) count_out[r] = c;
+}
+
+void launch_mm_expand(cudaStream_t s, const DPos* in, int n_in, int depth, int is_root, DPos* out, uint32_t* out_parent,
+                      unsigned long long* out_count, int* score, unsigned int* first_child, int* n_child) {
+    if (n_in > 0) k_mm_expand<<<(n_in + 127) / 128, 128, 0, s>>>(in, n_in, depth, is_root, out, out_parent, out_count, score, first_child, n_child);
+}
+void launch_mm_leaf(cudaStream_t s, const DPos* in, int n_in, int* score) {
+    if (n_in > 0) k_mm_leaf<<<(n_in + 255) / 256, 256, 0, s>>>(in, n_in, score);
+}
+void launch_mm_backup(cudaStream_t s, const int* child_score, const uint32_t* child_parent, int n_children, int* parent_score) {
+    if (n_children > 0) k_mm_backup<<<(n_children + 255) / 256, 256, 0, s>>>(child_score, child_parent, n_children, parent_score);
+}
+void launch_mm_root(cudaStream_t s, const unsigned int* first_child, const int* n_child, const int* child_score, int n_roots,
+                    int* scores_out, int* count_out) {
+    if (n_roots > 0) k_mm_root<<<n_roots, AZ_MAX_MOVES, 0, s>>>(first_child, n_child, child_score, n_roots, scores_out, count_out);
 }
 
 }  // namespace azb

@@ -140,6 +140,8 @@ void az_engine_destroy(az_engine* e) {
     cudaFree(e->d_value); cudaFree(e->d_scores); cudaFree(e->d_perft_count); cudaFree(e->d_perft_nodes);
     for (auto p : e->perft_pos) cudaFree(p);
     for (auto p : e->perft_root) cudaFree(p);
+    for (auto p : e->mm_score) cudaFree(p);
+    cudaFree(e->d_mm_first); cudaFree(e->d_mm_nchild); cudaFree(e->d_mm_out); cudaFree(e->d_mm_count);
     for (auto& ps : e->prof_pending) { if (ps.adv) cudaEventDestroy(ps.adv); cudaEventDestroy(ps.in0); cudaEventDestroy(ps.a); cudaEventDestroy(ps.b); cudaEventDestroy(ps.h1); }
     if (e->prof_counts_host) cudaFreeHost(e->prof_counts_host);
     if (e->timer0) { cudaEventDestroy(e->timer0); cudaEventDestroy(e->timer1); }
@@ -303,6 +305,21 @@ int az_encode(az_engine* e, int n, const az_position* pos, float* planes_out) {
 // ------------------------------------------------------------------------------------------------- perft
 // Breadth-first over device-resident level buffers.  A chunk of parents is sized so that even 218 children each fit the
 // next level's buffer; the last ply is bulk-counted without materialising positions.
+static int perft_buffers(az_engine* e, int level) {  // level buffers shared by az_perft and az_minimax
+    if (e->perft_cap == 0) {
+        e->perft_cap = std::max<size_t>((size_t)1 << 24, (size_t)e->max_batch);
+        AZ_CUDA(e, cudaMalloc(&e->d_perft_nodes, (size_t)e->max_batch * sizeof(unsigned long long)));
+    }
+    while ((int)e->perft_pos.size() <= level) {
+        DPos* p = nullptr; uint32_t* q = nullptr;
+        AZ_CUDA(e, cudaMalloc(&p, e->perft_cap * sizeof(DPos)));
+        e->perft_pos.push_back(p);
+        AZ_CUDA(e, cudaMalloc(&q, e->perft_cap * sizeof(uint32_t)));
+        e->perft_root.push_back(q);
+    }
+    return 0;
+}
+
 static int perft_level(az_engine* e, int level, size_t n, int depth_remaining) {
     if (depth_remaining == 1) {
         const size_t step = 1u << 24;
@@ -311,13 +328,7 @@ static int perft_level(az_engine* e, int level, size_t n, int depth_remaining) {
         AZ_CUDA(e, cudaGetLastError());
         return 0;
     }
-    if ((int)e->perft_pos.size() <= level + 1) {
-        DPos* p = nullptr; uint32_t* q = nullptr;
-        AZ_CUDA(e, cudaMalloc(&p, e->perft_cap * sizeof(DPos)));
-        e->perft_pos.push_back(p);
-        AZ_CUDA(e, cudaMalloc(&q, e->perft_cap * sizeof(uint32_t)));
-        e->perft_root.push_back(q);
-    }
+    if (int rb = perft_buffers(e, level + 1)) return rb;
     const size_t chunk = e->perft_cap / 218;
     for (size_t s = 0; s < n; s += chunk) {
         size_t m = std::min(chunk, n - s);
@@ -336,20 +347,77 @@ static int perft_level(az_engine* e, int level, size_t n, int depth_remaining) {
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------- minimax
+// negamax(node, d) for the n nodes of `level` into mm_score[level]; chunks are sized like perft's.
+static int mm_level(az_engine* e, int level, size_t n, int d, int* scores_out_dev, int* count_out_dev) {
+    while ((int)e->mm_score.size() <= level + 1) {
+        int* p = nullptr;
+        AZ_CUDA(e, cudaMalloc(&p, e->perft_cap * sizeof(int)));
+        e->mm_score.push_back(p);
+    }
+    if (d == 0) {
+        e->n_launches++;
+        launch_mm_leaf(e->stream, e->perft_pos[level], (int)n, e->mm_score[level]);
+        AZ_CUDA(e, cudaGetLastError());
+        return 0;
+    }
+    int r = perft_buffers(e, level + 1);
+    if (r) return r;
+    const bool root = level == 0;
+    const size_t chunk = e->perft_cap / 218;
+    for (size_t s = 0; s < n; s += chunk) {
+        const size_t m = std::min(chunk, n - s);
+        AZ_CUDA(e, cudaMemsetAsync(e->d_perft_count, 0, sizeof(unsigned long long), e->stream));
+        e->n_launches++;
+        launch_mm_expand(e->stream, e->perft_pos[level] + s, (int)m, d, root ? 1 : 0, e->perft_pos[level + 1], e->perft_root[level + 1],
+                         e->d_perft_count, e->mm_score[level] + s, root ? e->d_mm_first + s : nullptr, root ? e->d_mm_nchild + s : nullptr);
+        AZ_CUDA(e, cudaGetLastError());
+        unsigned long long produced = 0;
+        AZ_CUDA(e, cudaMemcpyAsync(&produced, e->d_perft_count, sizeof produced, cudaMemcpyDeviceToHost, e->stream));
+        AZ_CUDA(e, cudaStreamSynchronize(e->stream));
+        if (produced > e->perft_cap) return set_err(e, AZ_ERR_CAPACITY, "minimax level buffer overflow");
+        r = mm_level(e, level + 1, (size_t)produced, d - 1, nullptr, nullptr);
+        if (r) return r;
+        e->n_launches++;
+        if (root)
+            launch_mm_root(e->stream, e->d_mm_first + s, e->d_mm_nchild + s, e->mm_score[level + 1], (int)m,
+                           scores_out_dev + s * AZ_MAX_MOVES, count_out_dev + s);
+        else
+            launch_mm_backup(e->stream, e->mm_score[level + 1], e->perft_root[level + 1], (int)produced, e->mm_score[level] + s);
+        AZ_CUDA(e, cudaGetLastError());
+    }
+    return 0;
+}
+
+int az_minimax(az_engine* e, int n, const az_position* pos, int depth, int32_t* scores_out, int32_t* count_out) {
+    int r = check_batch(e, n);
+    if (r || n == 0) return r;
+    if (!pos || !scores_out || !count_out || depth < 1 || depth > 8) return set_err(e, AZ_ERR_INVALID_ARGUMENT, "bad minimax arguments");
+    r = perft_buffers(e, 0);
+    if (r) return r;
+    if (!e->d_mm_out) {
+        AZ_CUDA(e, cudaMalloc(&e->d_mm_first, (size_t)e->max_batch * sizeof(unsigned int)));
+        AZ_CUDA(e, cudaMalloc(&e->d_mm_nchild, (size_t)e->max_batch * sizeof(int)));
+        AZ_CUDA(e, cudaMalloc(&e->d_mm_count, (size_t)e->max_batch * sizeof(int)));
+        AZ_CUDA(e, cudaMalloc(&e->d_mm_out, (size_t)e->max_batch * AZ_MAX_MOVES * sizeof(int)));
+    }
+    AZ_CUDA(e, cudaMemcpyAsync(e->d_wire, pos, (size_t)n * sizeof(az_position), cudaMemcpyHostToDevice, e->stream));
+    launch_wire_to_dpos(e->stream, e->d_wire, e->perft_pos[0], e->perft_root[0], n);
+    r = mm_level(e, 0, (size_t)n, depth, e->d_mm_out, e->d_mm_count);
+    if (r) return r;
+    AZ_CUDA(e, cudaMemcpyAsync(scores_out, e->d_mm_out, (size_t)n * AZ_MAX_MOVES * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    AZ_CUDA(e, cudaMemcpyAsync(count_out, e->d_mm_count, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    AZ_CUDA(e, cudaStreamSynchronize(e->stream));
+    return AZ_OK;
+}
+
 int az_perft(az_engine* e, int n, const az_position* pos, int depth, uint64_t* nodes_out) {
     int r = check_batch(e, n);
     if (r || n == 0) return r;
     if (!pos || !nodes_out || depth < 0 || depth > 12) return set_err(e, AZ_ERR_INVALID_ARGUMENT, "bad perft arguments");
     if (depth == 0) { for (int i = 0; i < n; i++) nodes_out[i] = 1; return AZ_OK; }
-    if (e->perft_cap == 0) {
-        e->perft_cap = std::max<size_t>((size_t)1 << 24, (size_t)e->max_batch);
-        AZ_CUDA(e, cudaMalloc(&e->d_perft_nodes, (size_t)e->max_batch * sizeof(unsigned long long)));
-        DPos* p = nullptr; uint32_t* q = nullptr;
-        AZ_CUDA(e, cudaMalloc(&p, e->perft_cap * sizeof(DPos)));
-        e->perft_pos.push_back(p);
-        AZ_CUDA(e, cudaMalloc(&q, e->perft_cap * sizeof(uint32_t)));
-        e->perft_root.push_back(q);
-    }
+    r = perft_buffers(e, 0);
+    if (r) return r;
     AZ_CUDA(e, cudaMemcpyAsync(e->d_wire, pos, (size_t)n * sizeof(az_position), cudaMemcpyHostToDevice, e->stream));
     AZ_CUDA(e, cudaMemsetAsync(e->d_perft_nodes, 0, (size_t)n * sizeof(unsigned long long), e->stream));
     launch_wire_to_dpos(e->stream, e->d_wire, e->perft_pos[0], e->perft_root[0], n);

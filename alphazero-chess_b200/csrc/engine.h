@@ -46,6 +46,12 @@ struct az_engine {
     unsigned long long* d_perft_count = nullptr;
     unsigned long long* d_perft_nodes = nullptr;
     size_t perft_cap = 0;
+    // minimax (az_minimax): per-level score arrays beside the perft level buffers, root bookkeeping
+    std::vector<int*> mm_score;
+    unsigned int* d_mm_first = nullptr;  // [max_batch]
+    int* d_mm_nchild = nullptr;          // [max_batch]
+    int* d_mm_out = nullptr;             // [max_batch][256]
+    int* d_mm_count = nullptr;           // [max_batch]
 
     // measurement
     uint64_t n_launches = 0;
@@ -84,5 +90,11 @@ void launch_wire_to_dpos(cudaStream_t s, const az_position* wire, DPos* out, uin
 void launch_perft_expand(cudaStream_t s, const DPos* in, const uint32_t* in_root, int n_in, DPos* out, uint32_t* out_root,
                          unsigned long long* out_count);
 void launch_perft_count(cudaStream_t s, const DPos* in, const uint32_t* in_root, int n_in, unsigned long long* nodes);
+void launch_mm_expand(cudaStream_t s, const DPos* in, int n_in, int depth, int is_root, DPos* out, uint32_t* out_parent,
+                      unsigned long long* out_count, int* score, unsigned int* first_child, int* n_child);
+void launch_mm_leaf(cudaStream_t s, const DPos* in, int n_in, int* score);
+void launch_mm_backup(cudaStream_t s, const int* child_score, const uint32_t* child_parent, int n_children, int* parent_score);
+void launch_mm_root(cudaStream_t s, const unsigned int* first_child, const int* n_child, const int* child_score, int n_roots,
+                    int* scores_out, int* count_out);
 
 }  // namespace azb

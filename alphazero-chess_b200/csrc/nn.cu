@@ -59,7 +59,7 @@ int net_create(az_engine* e) {
     const size_t nb = (size_t)e->max_batch;
     int r = 0;
     r |= dmalloc(e, &w->f_w_in, 128 * 19 * 9); r |= dmalloc(e, &w->f_b_in, 128);
-    r |= dmalloc(e, &w->f_w_tower, (size_t)20 * 128 * 128 * 9); r |= dmalloc(e, &w->f_b_tower, 20 * 128);
+    r |= dmalloc(e, &w->f_w_tower, (size_t)20 * 128 * 128 * 9); r |= dmalloc(e, &w->f_b_tower, 21 * 128);  // row 20: copy of f_b_in for the fused launch
     r |= dmalloc(e, &w->f_w40t, 128 * 40); r |= dmalloc(e, &w->f_b40, 40);
     r |= dmalloc(e, &w->f_wp2t, 32 * 64); r |= dmalloc(e, &w->f_bp2, 64);
     r |= dmalloc(e, &w->f_wl1, 512 * 64); r |= dmalloc(e, &w->f_bl1, 64);
@@ -77,10 +77,12 @@ int net_create(az_engine* e) {
     for (int l = 0; l < 20; l++)
         if (tc_make_weight_map(&w->map_w_tower[l], w->h_w_tower + (size_t)l * 9 * 128 * 128, 128))
             return set_err(e, AZ_ERR_CUDA, "cuTensorMapEncodeTiled(w_tower)");
-    CUtensorMap host_maps[23];
+    CUtensorMap host_maps[25];
     for (int i = 0; i < 3; i++) host_maps[i] = w->map_a[i];
     for (int l = 0; l < 20; l++) host_maps[3 + l] = w->map_w_tower[l];
-    if (dmalloc(e, &w->d_maps, 23)) return AZ_ERR_OUT_OF_MEMORY;
+    host_maps[23] = w->map_a_in;
+    host_maps[24] = w->map_w_in;
+    if (dmalloc(e, &w->d_maps, 25)) return AZ_ERR_OUT_OF_MEMORY;
     AZ_CUDA(e, cudaMemcpy(w->d_maps, host_maps, sizeof host_maps, cudaMemcpyHostToDevice));
     return 0;
 }
@@ -120,6 +122,7 @@ static int load_from_host(az_engine* e, const float* const* a) {
     fold(a[0], a[1], a[2], a[3], a[4], a[5], 128, 19 * 9, fw.data(), fb.data());
     r |= upload(e, w->f_w_in, fw.data(), 128 * 19 * 9 * 4);
     r |= upload(e, w->f_b_in, fb.data(), 128 * 4);
+    r |= upload(e, w->f_b_tower + 20 * 128, fb.data(), 128 * 4);
     for (int tap = 0; tap < 9; tap++)
         for (int co = 0; co < 128; co++)
             for (int ci = 0; ci < 64; ci++)
@@ -333,15 +336,24 @@ int net_forward_bf16(az_engine* e, const int* n_dev, int n_static, float* policy
     NetWeights* w = e->net;
     if (!w->loaded) return set_err(e, AZ_ERR_NO_WEIGHTS, "az_load_weights has not been called");
     const int grid = e->sm_count & ~1;
-    e->n_launches += 2;  // input convolution + heads; the tower adds 1 (fused) or 20 below
+    e->n_launches += 1;  // heads; the input convolution and the tower add 1 (one fused launch), 2 or 21 below
     const bool sample = e->prof_every > 0 && (e->prof_counter++ % (uint64_t)e->prof_every) == 0 && e->prof_pending.size() < 4000;
     az_engine::ProfSample ps{nullptr, nullptr, nullptr, nullptr, nullptr, 0};
     if (sample) {
         ps.adv = e->prof_adv_event; e->prof_adv_event = nullptr;
         cudaEventCreate(&ps.in0); cudaEventRecord(ps.in0, e->stream);
     }
-    int r = tc_conv3x3_launch(e->stream, &w->map_a_in, &w->map_w_in, 64, w->f_b_in, nullptr, w->a_buf[0], n_dev, n_static, 1, grid);
-    if (r) return set_err(e, AZ_ERR_CUDA, "tc conv (input) launch failed");
+    // AZ_TOWER_FUSED: 1 (default) = input convolution + one launch for the 20 tower layers, 2 = the input convolution runs as
+    // an extra first layer of that launch (measured: 48 us inside vs 60 us alone per 4096 boards, epilogue-bound either
+    // way, so the wave gains 0.2 % -- kept as an option), 0 = 21 launches
+    static int fused = -1;
+    if (fused < 0) { const char* v = getenv("AZ_TOWER_FUSED"); fused = v ? atoi(v) : 1; }
+    int r = 0;
+    if (fused < 2) {
+        e->n_launches += 1;
+        r = tc_conv3x3_launch(e->stream, &w->map_a_in, &w->map_w_in, 64, w->f_b_in, nullptr, w->a_buf[0], n_dev, n_static, 1, grid);
+        if (r) return set_err(e, AZ_ERR_CUDA, "tc conv (input) launch failed");
+    }
     if (sample) {
         cudaEventCreate(&ps.a); cudaEventCreate(&ps.b);
         ps.slot = e->prof_slot; e->prof_slot = (e->prof_slot + 1) % 4096;
@@ -350,12 +362,10 @@ int net_forward_bf16(az_engine* e, const int* n_dev, int n_static, float* policy
         cudaEventRecord(ps.a, e->stream);
     }
     int x = 0;  // buffer holding the block input
-    static int fused = -1;
-    if (fused < 0) { const char* v = getenv("AZ_TOWER_FUSED"); fused = v ? atoi(v) : 1; }
     if (fused) {
         void* act[3] = {w->a_buf[0], w->a_buf[1], w->a_buf[2]};
         e->n_launches += 1;
-        r = tc_tower_launch(e->stream, w->d_maps, w->f_b_tower, act, n_dev, n_static, 20, grid);
+        r = tc_tower_launch(e->stream, w->d_maps, w->f_b_tower, act, n_dev, n_static, 20, fused >= 2, grid);
         if (r) return set_err(e, AZ_ERR_CUDA, "tower launch failed");
         x = 2;  // ten blocks rotate the three buffers: (0 + 10 * 2) % 3
     }

@@ -233,12 +233,14 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
 // tile t of layer l: the epilogue warps publish per-warp completion counters after a generic->async proxy fence and the
 // TMA producer checks them (they are normally many tiles ahead).
 struct TowerParams {
-    const CUtensorMap* maps;   // device memory: [0..2] activation buffers, [3..22] weights of the 20 layers
-    const float* bias;         // [20][128]
+    const CUtensorMap* maps;   // device memory: [0..2] activation buffers, [3..22] weights of the 20 layers,
+                               // [23] the 64-channel plane buffer, [24] the input convolution's weights
+    const float* bias;         // [21][128]: 20 tower layers, then the input convolution
     __nv_bfloat16* act[3];
     const int* n_boards_ptr;
     int n_boards_static;
     int n_layers;              // 20
+    int stem;                  // 1: run the input convolution (agent.rs:117; 64 padded channels -> act[0]) as a first layer
 };
 
 
@@ -267,7 +269,8 @@ conv_tower_kernel(const TowerParams prm) {
     const int n_tiles = (n_boards + 3) >> 2;
     const int first_tile = blockIdx.x >> 1, tile_step = gridDim.x >> 1;
     const int T = first_tile < n_tiles ? (n_tiles - first_tile + tile_step - 1) / tile_step : 0;  // tiles of this pair
-    const int NL = prm.n_layers;
+    const int stem = prm.stem;
+    const int NL = prm.n_layers + stem;  // loop index L; tower layer = L - stem (-1 is the input convolution: one channel half)
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NS; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
@@ -288,15 +291,17 @@ conv_tower_kernel(const TowerParams prm) {
         // ---------------------------------------------------------------- TMA producer (both CTAs)
         int stage = 0; uint32_t phase = 0;
         int x = 0;
-        for (int layer = 0; layer < NL; layer++) {
-            const int blk_second = layer & 1;
+        for (int L = 0; L < NL; L++) {
+            const int layer = L - stem;
+            const int blk_second = layer >= 0 ? (layer & 1) : 0;
             const int in_buf = blk_second ? (x + 1) % 3 : x;
-            const CUtensorMap* in_map = &prm.maps[in_buf];
-            const CUtensorMap* w_map = &prm.maps[3 + layer];
+            const CUtensorMap* in_map = layer >= 0 ? &prm.maps[in_buf] : &prm.maps[23];
+            const CUtensorMap* w_map = layer >= 0 ? &prm.maps[3 + layer] : &prm.maps[24];
+            const int halves = layer >= 0 ? 2 : 1;
             for (int i = 0; i < T; i++) {
                 const int t = first_tile + i * tile_step;
-                if (layer > 0) {  // this tile's input was written by this CTA's epilogue one layer ago
-                    const uint32_t need = (uint32_t)((layer - 1) * T + i + 1);
+                if (L > 0) {  // this tile's input was written by this CTA's epilogue one layer ago
+                    const uint32_t need = (uint32_t)((L - 1) * T + i + 1);
                     long long t0 = clock64();
                     for (;;) {
                         bool ok = lane >= 8 || epi_done[lane & 7] >= need;
@@ -305,11 +310,12 @@ conv_tower_kernel(const TowerParams prm) {
                     }
                     fence_proxy_async();
                 }
-                for (int half = 0; half < 2; half++)
+                for (int half = 0; half < halves; half++)
                     for (int dxi = 0; dxi < 3; dxi++) {
                         const int grp = half * 3 + dxi;
                         if (i == 0) {  // (re)load this group's three weight tiles for the new layer
-                            if (layer > 0) mbar_wait(&wempty_bar[grp], (uint32_t)((layer - 1) & 1), 21);
+                            const int used = half == 0 ? L : layer;  // earlier layers that went through this group
+                            if (used > 0) mbar_wait(&wempty_bar[grp], (uint32_t)((used - 1) & 1), 21);
                             if (elect_one()) {
                                 if (rank == 0) mbar_arrive_expect_tx(&wfull_bar[grp], 2 * kGroupBytes);
                                 for (int dyi = 0; dyi < 3; dyi++)
@@ -336,17 +342,19 @@ conv_tower_kernel(const TowerParams prm) {
             const uint64_t dbase = umma_desc_base_sw128();
             const uint32_t w_lo = (smem_u32(w_sm) & 0x3FFFF) >> 4;
             int stage = 0; uint32_t phase = 0; int lt = 0;
-            for (int layer = 0; layer < NL; layer++) {
+            for (int L = 0; L < NL; L++) {
+                const int layer = L - stem;
+                const int halves = layer >= 0 ? 2 : 1;
                 for (int i = 0; i < T; i++, lt++) {
                     const int acc = lt & 1; const uint32_t accphase = (lt >> 1) & 1;
                     mbar_wait(&tempty_bar[acc], accphase ^ 1, 23);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + acc * 128;
-                    for (int half = 0; half < 2; half++)
+                    for (int half = 0; half < halves; half++)
                         for (int dxi = 0; dxi < 3; dxi++) {
                             const int grp = half * 3 + dxi;
                             mbar_wait(&full_bar[stage], phase, 24);
-                            if (i == 0) mbar_wait(&wfull_bar[grp], (uint32_t)(layer & 1), 25);
+                            if (i == 0) mbar_wait(&wfull_bar[grp], (uint32_t)((half == 0 ? L : layer) & 1), 25);
                             tc_fence_after();
                             if (elect_one()) {
                                 const uint32_t a_lo = (smem_u32(a_sm + stage * kStageBytes) & 0x3FFFF) >> 4;
@@ -382,15 +390,17 @@ conv_tower_kernel(const TowerParams prm) {
         // completion is published lazily (after the next accumulator wait) and only every 4th tile when the pair has
         // enough tiles in flight; the producer needs tile i of this layer only T tiles later (T >= 8 leaves slack >= 4)
         const bool lazy = T >= 8;
-        for (int layer = 0; layer < NL; layer++) {
-            const int blk_second = layer & 1;
-            const int out_buf = blk_second ? (x + 2) % 3 : (x + 1) % 3;
+        for (int L = 0; L < NL; L++) {
+            const int layer = L - stem;
+            const int blk_second = layer >= 0 ? (layer & 1) : 0;
+            const int out_buf = layer < 0 ? 0 : blk_second ? (x + 2) % 3 : (x + 1) % 3;
             __nv_bfloat16* out = prm.act[out_buf];
             const __nv_bfloat16* residual = blk_second ? prm.act[x] : nullptr;
             // the 8 epilogue warps switch layers together: whoever arrives refills the buffer last used two layers ago
-            if (threadIdx.x - 64 < 128) bias_s[(layer & 1) * 128 + threadIdx.x - 64] = prm.bias[layer * 128 + threadIdx.x - 64];
+            if (threadIdx.x - 64 < 128)
+                bias_s[(L & 1) * 128 + threadIdx.x - 64] = prm.bias[(layer >= 0 ? layer : prm.n_layers) * 128 + threadIdx.x - 64];
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            const float* bias = bias_s + (layer & 1) * 128 + ch * 64;
+            const float* bias = bias_s + (L & 1) * 128 + ch * 64;
             for (int i = 0; i < T; i++, lt++) {
                 const int t = first_tile + i * tile_step;
                 const int acc = lt & 1; const uint32_t accphase = (lt >> 1) & 1;
@@ -464,7 +474,7 @@ conv_tower_kernel(const TowerParams prm) {
 }
 
 int tc_tower_launch(cudaStream_t stream, const CUtensorMap* maps_dev, const float* bias, void* const* act, const int* n_boards_dev,
-                    int n_boards_static, int n_layers, int grid) {
+                    int n_boards_static, int n_layers, int stem, int grid) {
     static PerDeviceOnce once;
     if (once.first() &&
         cudaFuncSetAttribute(conv_tower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<2>::kTotal) != cudaSuccess)
@@ -474,7 +484,7 @@ int tc_tower_launch(cudaStream_t stream, const CUtensorMap* maps_dev, const floa
     TowerParams p;
     p.maps = maps_dev; p.bias = bias;
     for (int i = 0; i < 3; i++) p.act[i] = (__nv_bfloat16*)act[i];
-    p.n_boards_ptr = n_boards_dev; p.n_boards_static = n_boards_static; p.n_layers = n_layers;
+    p.n_boards_ptr = n_boards_dev; p.n_boards_static = n_boards_static; p.n_layers = n_layers; p.stem = stem ? 1 : 0;
     conv_tower_kernel<<<grid, kThreads2, ConvSmem<2>::kTotal, stream>>>(p);
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }

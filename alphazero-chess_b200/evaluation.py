@@ -3,7 +3,7 @@
 A match advances all its games in lockstep: per ply the positions whose side to move belongs to a player are handed to
 that player as ONE batch (az_search / az_forward / az_movegen), then az_play_move applies all chosen moves.  The
 reference runs 256 async games against two inference servers; batching by player is the same schedule without the
-channel hops.  MiniMax and Human players of the reference are out of scope.
+channel hops.  The Human player (terminal input) is out of scope.
 Randomness (move sampling in the opening, the random player) uses the engine's counter-based generator convention,
 keyed by (seed, game, ply); the reference draws from an unseeded thread_rng.
 """
@@ -86,6 +86,25 @@ class RandomPlayer:
     def choose(self, positions, histories, fullmoves, stochastic, seed, game_ids, plies):
         _, index, count = self.engine.movegen(positions)
         return [int(index[k, int(_uniform(seed ^ 0x5151, game_ids[k], plies[k]) * count[k])]) for k in range(len(positions))]
+
+
+class MiniMaxPlayer:
+    """Player::MiniMax(depth) (validation.rs:113-120, 352-358; chess.rs:247-318): full-width negamax over material, a
+    random choice among the best-scoring moves.  The whole batch of positions is searched by az_minimax in one call; the
+    reference default is depth 4 (main.rs:103, training.rs:254)."""
+
+    def __init__(self, engine, depth=4):
+        self.engine, self.depth = engine, depth
+
+    def choose(self, positions, histories, fullmoves, stochastic, seed, game_ids, plies):
+        scores, count = self.engine.minimax(positions, self.depth)
+        _, index, _ = self.engine.movegen(positions)
+        out = []
+        for k in range(len(positions)):
+            sc = scores[k, : count[k]]
+            best = np.flatnonzero(sc == sc.max())
+            out.append(int(index[k, best[int(_uniform(seed ^ 0x3A3A, game_ids[k], plies[k]) * len(best))]]))
+        return out
 
 
 def evaluate(player_1, player_2, rules_engine, n_games=EVALUATION_GAMES, num_stochastic_moves=TEMPERATURE_ANNEALING, seed=0,

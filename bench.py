@@ -247,18 +247,23 @@ def run_ours(args, rank, world, local_rank):
         peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
         roof = None
         if prof.tower_samples:
-            fused = os.environ.get("AZ_TOWER_FUSED", "1") != "0"
+            mode = int(os.environ.get("AZ_TOWER_FUSED", "1"))
+            fused = mode != 0
             n_launch = 1 if fused else 20  # the 20 tower convolutions run as one persistent launch or as 20 launches
             launch_ms = prof.tower_ms / (prof.tower_samples * n_launch)
             boards = prof.tower_boards / prof.tower_samples
-            flops_per_launch = az.FLOPS_PER_TOWER_CONV * (20 // n_launch) * boards
+            # algorithmic flops: 20 x (3x3, 128->128) per board, plus the input convolution's 19 real channels when it is
+            # fused into the same launch (mode 2; the 45 zero-padded channels the MMA also multiplies are not counted)
+            flops_per_launch = (az.FLOPS_PER_TOWER_CONV * (20 // n_launch) + (az.FLOPS_PER_INPUT_CONV if mode >= 2 else 0)) * boards
             achieved = flops_per_launch / (launch_ms * 1e-3) / 1e12
             traffic = None
             tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
             if os.path.exists(tp):
                 with open(tp) as f:
                     traffic = json.load(f).get("conv_tower_kernel_dram_bytes_per_launch" if fused else "conv3x3_tc2_dram_bytes_per_launch")
-            kname = ("conv_tower_kernel (the 20 3x3 128->128 convolutions of the tower in one persistent tcgen05 cta_group::2 launch)"
+            kname = ("conv_tower_kernel (input convolution + the 20 3x3 128->128 convolutions of the tower in one persistent tcgen05 "
+                     "cta_group::2 launch)" if mode >= 2 else
+                     "conv_tower_kernel (the 20 3x3 128->128 convolutions of the tower in one persistent tcgen05 cta_group::2 launch)"
                      if fused else "conv3x3_tc2_kernel<2> (tcgen05 cta_group::2 3x3 128->128 convolution, 20 of 23 launches per wave)")
             roof = {"bound": "tensor", "kernel": kname,
                     "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,

@@ -107,6 +107,11 @@ int az_forward(az_engine* eng, int n, const az_position* pos, float* policy_out,
 int az_movegen(az_engine* eng, int n, const az_position* pos, az_move* moves_out, uint16_t* index_out, int32_t* count_out);
 /* perft(depth) per root, breadth-first on the GPU (BASELINE config 2) */
 int az_perft(az_engine* eng, int n, const az_position* pos, int depth, uint64_t* nodes_out);
+/* get_best_move up to its random tie-break (chess.rs:295-318; Player::MiniMax(depth), validation.rs:113,352): the full-width
+ * negamax score -negamax(child, depth-1) of every legal move of each root, in az_movegen order.  scores_out [n][256],
+ * count_out [n] (0 = no legal move: the reference returns None).  Mate is +-(20000 + remaining depth), draws 0, the
+ * horizon is material (100/320/330/500/900) from the mover's side (chess.rs:247-292).  1 <= depth <= 8. */
+int az_minimax(az_engine* eng, int n, const az_position* pos, int depth, int32_t* scores_out, int32_t* count_out);
 /* play_move (chess.rs:36-63) driven by a policy index as in tree.rs:211-212.  history is the concatenation of every
  * position already counted in GameState::pos_count (including the current one), hist_offsets[n+1] delimits games. */
 int az_play_move(az_engine* eng, int n, az_position* pos_inout, const az_position* history, const uint32_t* hist_offsets,

@@ -116,6 +116,7 @@ int orc_legal_moves(const Pos* p, uint16_t* moves_out, uint16_t* index_out) {
 }
 
 uint64_t orc_perft(const Pos* p, int depth) { return perft(*p, depth); }
+int orc_minimax_scores(const Pos* p, int depth, int32_t* scores) { return minimax_scores(*p, depth, scores); }
 int orc_outcome(const Pos* p) { return outcome(*p); }
 int orc_legal_ep_square(const Pos* p) { return legal_ep_square(*p); }
 int orc_pseudo_legal_ep_square(const Pos* p) { return pseudo_legal_ep_square(*p); }

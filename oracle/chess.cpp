@@ -1,3 +1,4 @@
+#include <cstdint>
 // ORACLE — TEST INFRASTRUCTURE ONLY (see oracle.hpp).
 //
 // Chess rules: restates shakmaty 0.29.0 (pinned in /root/reference/Cargo.lock:4573-4576,
@@ -393,6 +394,47 @@ int outcome(const Pos& p) {
     }
     if (is_insufficient_material(p)) return DRAW;
     return 0;
+}
+
+// chess.rs:247-264 evaluate_material: pawn 100, knight 320, bishop 330, rook 500, queen 900, from the mover's side
+int evaluate_material(const Pos& p) {
+    static const int value[5] = {100, 320, 330, 500, 900};
+    const int us = p.turn, them = us ^ 1;
+    int score = 0;
+    for (int r = 0; r < 5; r++) {
+        score += __builtin_popcountll(p.role[r] & p.color[us]) * value[r];
+        score -= __builtin_popcountll(p.role[r] & p.color[them]) * value[r];
+    }
+    return score;
+}
+
+// chess.rs:266-292 negamax: full width, no pruning; a decided game scores -(20000 + remaining depth) for the side to move
+// that is mated, a drawn one (stalemate, insufficient material) 0; the horizon scores material.
+int negamax(const Pos& p, int depth) {
+    MoveList ml; legal_moves(p, ml);
+    const bool over = ml.n == 0 || is_insufficient_material(p);
+    if (depth == 0 || over) {
+        if (ml.n == 0) return checkers(p) ? -20000 - depth : 0;
+        if (over) return 0;
+        return evaluate_material(p);
+    }
+    int best = INT32_MIN;
+    for (int i = 0; i < ml.n; i++) {
+        Pos c = p; play_unchecked(c, ml.m[i]);
+        const int sc = -negamax(c, depth - 1);
+        if (sc > best) best = sc;
+    }
+    return best;
+}
+
+// chess.rs:295-318 get_best_move, up to the random choice among the best: the score of every legal move, in move order
+int minimax_scores(const Pos& p, int depth, int32_t* scores) {
+    MoveList ml; legal_moves(p, ml);
+    for (int i = 0; i < ml.n; i++) {
+        Pos c = p; play_unchecked(c, ml.m[i]);
+        scores[i] = -negamax(c, depth - 1);
+    }
+    return ml.n;
 }
 
 u64 perft(const Pos& p, int depth) {

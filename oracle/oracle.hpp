@@ -78,6 +78,9 @@ bool is_insufficient_material(const Pos& p);
 // 0 unknown, 1 draw, 2 white wins, 3 black wins   (shakmaty Position::outcome)
 int outcome(const Pos& p);
 u64 perft(const Pos& p, int depth);
+int evaluate_material(const Pos& p);                         // chess.rs:247-264
+int negamax(const Pos& p, int depth);                        // chess.rs:266-292
+int minimax_scores(const Pos& p, int depth, int32_t* scores); // chess.rs:295-318 (scores of the legal moves, in order)
 
 // ---- chess.rs restatement -------------------------------------------------
 constexpr int ACTION_SPACE = 4096;

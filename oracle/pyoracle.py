@@ -96,6 +96,13 @@ def perft(pos, depth):
     return int(lib().orc_perft(_p(_one(pos)), int(depth)))
 
 
+def minimax_scores(pos, depth):
+    """chess.rs:295-318: -negamax(child, depth - 1) for every legal move, in legal-move order."""
+    out = np.zeros(256, np.int32)
+    n = lib().orc_minimax_scores(_p(_one(pos)), int(depth), _p(out))
+    return out[:n].copy()
+
+
 def perft_batch(positions, depth, threads):
     p = np.ascontiguousarray(positions, POSITION_DTYPE)
     out = np.zeros(p.shape[0], np.uint64)

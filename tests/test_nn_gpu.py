@@ -85,3 +85,33 @@ def test_search_with_network_matches_oracle_given_identical_outputs(weights):
             assert np.array_equal(visits[k], v), k
             assert np.array_equal(scores[k], s), k
             assert depth[k] == d
+
+
+_MODE_SCRIPT = """
+import sys, hashlib
+sys.path.insert(0, {tests!r})
+import _pkg  # noqa: F401
+import alphazero_chess_b200 as az
+from helpers import random_playouts
+p, _ = random_playouts(150, seed=8, max_plies=100)
+with az.Engine(max_games=256, precision=0) as e:
+    e.load_weights(az.random_weights(seed=3, randomize_bn=True))
+    pol, val = e.forward(p)
+print("DIGEST", hashlib.sha256(pol.tobytes() + val.tobytes()).hexdigest())
+"""
+
+
+def test_launch_modes_give_identical_bits():
+    """AZ_TOWER_FUSED = 0 (21 launches), 1 (input convolution + fused tower), 2 (everything in one launch) run the same
+    MMAs in the same order, so the network's outputs must not differ by a single bit."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    digests = []
+    for mode in ("0", "1", "2"):
+        env = dict(os.environ, AZ_TOWER_FUSED=mode)
+        out = subprocess.run([sys.executable, "-c", _MODE_SCRIPT.format(tests=here)], env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        digests.append([l for l in out.stdout.splitlines() if l.startswith("DIGEST")][0])
+    assert digests[0] == digests[1] == digests[2], digests

@@ -152,3 +152,24 @@ def test_selfplay_episode_terminates_and_backfills():
     orc.cache_destroy(c)
     assert np.array_equal(ep["action"], ep2["action"]) and np.array_equal(ep["visits"], ep2["visits"])
     assert ep2["stats"].cache_hits > 0
+
+
+def test_minimax_hand_derived_scores():
+    """chess.rs:247-318 restated: values worked out by hand (material 100/320/330/500/900, mate 20000 + remaining depth)."""
+    start = orc.from_fen("rnbqkbnr/pppppppp/8/8/8/8/PPPPPPPP/RNBQKBNR w KQkq - 0 1")
+    for d in (1, 2, 3):
+        assert not orc.minimax_scores(start, d).any() and len(orc.minimax_scores(start, d)) == 20
+    mate = orc.from_fen("6k1/5ppp/8/8/8/8/8/R6K w - - 0 1")           # Ra8 mates; otherwise rook against three pawns
+    mv, _ = orc.legal_moves(mate)
+    s1, s2 = orc.minimax_scores(mate, 1), orc.minimax_scores(mate, 2)
+    ra8 = [k for k, m in enumerate(mv) if (m & 63) == 0 and ((m >> 6) & 63) == 56][0]
+    assert s1[ra8] == 20000 and s2[ra8] == 20001
+    assert all(s1[k] == 200 for k in range(len(mv)) if k != ra8)
+    kk = orc.from_fen("8/8/4k3/8/8/4K3/8/8 w - - 0 1")                 # dead position after any move: 0, never material
+    assert not orc.minimax_scores(kk, 3).any()
+    q = orc.from_fen("4k3/8/8/3q4/4P3/8/8/4K3 w - - 0 1")              # exd5 wins the queen; anything else loses the pawn
+    mv, _ = orc.legal_moves(q)
+    cap = [k for k, m in enumerate(mv) if (m & 63) == 28 and ((m >> 6) & 63) == 35][0]
+    s1, s2 = orc.minimax_scores(q, 1), orc.minimax_scores(q, 2)
+    assert s1[cap] == 100 and s2[cap] == 100
+    assert all(s1[k] == -800 and s2[k] == -900 for k in range(len(mv)) if k != cap)
