@@ -67,6 +67,22 @@ def main():
         assert total == KAT[(name, depth)]
         print(json.dumps({"bench": "perft_cpu_oracle", "position": name, "depth": depth, "nodes": total, "seconds": dt,
                           "nodes_per_sec": total / dt, "cores": cores}))
+    # Player::MiniMax(4) (chess.rs:247-318): one move decision for each of 256 positions, full width, four plies
+    mm_pos = positions[:256]
+    eng.minimax(mm_pos[:8], 2)
+    for depth in (3, 4):
+        t0 = time.perf_counter()
+        scores, cnt = eng.minimax(mm_pos, depth)
+        dt = time.perf_counter() - t0
+        leaves = int(eng.perft(mm_pos, depth).sum())  # upper bound: finished games are not expanded by negamax
+        print(json.dumps({"bench": "minimax", "roots": int(len(mm_pos)), "depth": depth, "seconds": dt, "decisions_per_sec": len(mm_pos) / dt,
+                          "perft_leaves": leaves, "leaves_per_sec": leaves / dt}))
+    t0 = time.perf_counter()
+    n_mm_cpu = 4
+    for p in mm_pos[:n_mm_cpu]:
+        orc.minimax_scores(p, 4)
+    dt = time.perf_counter() - t0
+    print(json.dumps({"bench": "minimax_cpu_oracle", "roots": n_mm_cpu, "depth": 4, "seconds": dt, "decisions_per_sec": n_mm_cpu / dt, "cores": 1}))
     eng.close()
     # replay buffer (memory.rs): order-exact add and batch sampling
     e2 = az.Engine(max_games=512, num_simulations=16, seed=3)
