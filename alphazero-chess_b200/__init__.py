@@ -312,6 +312,7 @@ class ReplayBuffer:
         self._e = engine
         self._L = engine._L
         self._h = ctypes.c_void_p(0)
+        self._max_batch = int(max_batch)
         engine._check(self._L.az_replay_create(engine._h, int(capacity), int(max_batch), ctypes.byref(self._h)), "az_replay_create")
         self._L.az_replay_destroy.restype = None
 
@@ -353,6 +354,42 @@ class ReplayBuffer:
         self._e._check(self._L.az_replay_sample(self._h, int(batch_size), ctypes.c_uint64(seed), _ptr(planes), _ptr(policy), _ptr(value),
                                                 ctypes.byref(n)), "az_replay_sample")
         return planes[: n.value], policy[: n.value], value[: n.value]
+
+    def export(self, first, n):
+        """Entries [first, first + n) in FIFO order (oldest first): (positions, policy [k,4096], value [k], visit_count [k])."""
+        pos = np.zeros(n, POSITION_DTYPE)
+        policy = np.empty((n, ACTION_SPACE), np.float32)
+        value = np.empty(n, np.float32)
+        visits = np.empty(n, np.uint32)
+        k = ctypes.c_int(0)
+        self._e._check(self._L.az_replay_export(self._h, int(first), int(n), _ptr(pos), _ptr(policy), _ptr(value), _ptr(visits),
+                                                ctypes.byref(k)), "az_replay_export")
+        return pos[: k.value], policy[: k.value], value[: k.value], visits[: k.value]
+
+    def import_entries(self, pos, policy, value, visits):
+        """Appends stored entries (running means and visit counts as given) as the newest ones, in order."""
+        pos = np.ascontiguousarray(pos, POSITION_DTYPE)
+        policy = np.ascontiguousarray(policy, np.float32)
+        value = np.ascontiguousarray(value, np.float32)
+        visits = np.ascontiguousarray(visits, np.uint32)
+        self._e._check(self._L.az_replay_import(self._h, int(pos.shape[0]), _ptr(pos), _ptr(policy), _ptr(value), _ptr(visits)),
+                       "az_replay_import")
+
+    def save(self, path, page=512):
+        """ReplayBuffer::save (memory.rs:100-104): the reference's bincode file (see replay_io.py)."""
+        from . import replay_io
+        n, page = len(self), min(page, self._max_batch)
+        replay_io.write_file(path, (self.export(first, page) for first in range(0, n, page)), n)
+
+    def load(self, path, page=512):
+        """ReplayBuffer::load (memory.rs:107-114) into this (normally empty) buffer."""
+        from . import replay_io
+        pos, policy, value, visits = replay_io.read_file(path)
+        page = min(page, self._max_batch)
+        for first in range(0, len(pos), page):
+            sl = slice(first, first + page)
+            self.import_entries(pos[sl], policy[sl], value[sl], visits[sl])
+        return len(pos)
 
     def get(self, pos):
         p = np.ascontiguousarray(np.atleast_1d(pos), POSITION_DTYPE)

@@ -37,6 +37,7 @@ struct az_replay {
     float* d_planes = nullptr;        // [max_batch][19][64]
     float* d_pol = nullptr;           // [max_batch][4096]
     float* d_val = nullptr;           // [max_batch]
+    az_position* d_pos = nullptr;     // [max_batch] export/import page (lazy)
     int max_batch = 0;
 };
 
@@ -124,7 +125,9 @@ __global__ void __launch_bounds__(256) k_replay_gather(ReplayPtrs r, const int32
                                                        float* __restrict__ policy, float* __restrict__ value) {
     const int b = blockIdx.x;
     if (b >= n) return;
-    const int slot = idx[b];
+    // idx holds FIFO ranks (0 = oldest), so a buffer reloaded from a file samples like the one that was saved
+    const int len = r.state[1];
+    const int slot = ((len >= r.cap ? r.state[0] : 0) + idx[b]) % r.cap;
     const DPos p = r.keys[slot];   // the key IS the position as the reference rebuilds it from the FEN (memory.rs:90)
     const u64 occ = occupied(p);
     const u64 ours = meta_turn(p.meta) == 0 ? p.white : occ ^ p.white;
@@ -150,6 +153,51 @@ __global__ void k_replay_get(ReplayPtrs r, const az_position* __restrict__ wire,
     __syncthreads();
     for (int k = threadIdx.x; k < AZ_ACTION_SPACE; k += blockDim.x)
         policy[k] = s_slot >= 0 ? r.policy[(size_t)s_slot * AZ_ACTION_SPACE + k] : 0.0f;
+}
+
+// persistence (memory.rs:100-115): entries [first, first + n) in FIFO order (oldest first) out of / into the ring
+__global__ void __launch_bounds__(256) k_replay_export(ReplayPtrs r, int first, int n, az_position* __restrict__ pos, float* __restrict__ policy,
+                                                       float* __restrict__ value, uint32_t* __restrict__ visits) {
+    const int b = blockIdx.x;
+    if (b >= n) return;
+    const int len = r.state[1];
+    const int oldest = len >= r.cap ? r.state[0] : 0;
+    const int slot = (oldest + first + b) % r.cap;
+    const float4* src = reinterpret_cast<const float4*>(r.policy + (size_t)slot * AZ_ACTION_SPACE);
+    float4* dst = reinterpret_cast<float4*>(policy + (size_t)b * AZ_ACTION_SPACE);
+    for (int k = threadIdx.x; k < AZ_ACTION_SPACE / 4; k += 256) dst[k] = src[k];
+    if (threadIdx.x == 0) { pos[b] = dpos_to_wire(r.keys[slot]); value[b] = r.value[slot]; visits[b] = r.visits[slot]; }
+}
+
+// entries appended in order as the newest ones (an entry whose position is already present replaces it in place)
+__global__ void __launch_bounds__(1024) k_replay_import(ReplayPtrs r, int n, const az_position* __restrict__ pos, const float* __restrict__ policy,
+                                                        const float* __restrict__ value, const uint32_t* __restrict__ visits) {
+    __shared__ int s_slot;
+    const int t = threadIdx.x;
+    int head = r.state[0], len = r.state[1];
+    for (int i = 0; i < n; i++) {
+        if (t == 0) {
+            const DPos key = fen_key_of(dpos_from_wire(pos[i]));
+            const u64 h = fen_key_hash(key);
+            int slot = replay_find(r, key, h);
+            if (slot < 0) {
+                slot = head;
+                if (len >= r.cap) replay_table_erase(r, slot);
+                else len++;
+                r.keys[slot] = key;
+                replay_table_insert(r, h, slot);
+                head = head + 1 == r.cap ? 0 : head + 1;
+            }
+            r.value[slot] = value[i];
+            r.visits[slot] = visits[i];
+            s_slot = slot;
+        }
+        __syncthreads();
+        float* pol = r.policy + (size_t)s_slot * AZ_ACTION_SPACE;
+        for (int k = t; k < AZ_ACTION_SPACE; k += 1024) pol[k] = policy[(size_t)i * AZ_ACTION_SPACE + k];
+        __syncthreads();
+    }
+    if (t == 0) { r.state[0] = head; r.state[1] = len; }
 }
 
 static inline uint64_t host_splitmix64(uint64_t x) {
@@ -197,7 +245,7 @@ void az_replay_destroy(az_replay* rp) {
     cudaSetDevice(rp->eng->cfg.device);
     cudaStreamSynchronize(rp->eng->stream);
     cudaFree(rp->p.keys); cudaFree(rp->p.policy); cudaFree(rp->p.value); cudaFree(rp->p.visits); cudaFree(rp->p.table);
-    cudaFree(rp->p.state); cudaFree(rp->d_staging); cudaFree(rp->d_idx); cudaFree(rp->d_planes); cudaFree(rp->d_pol); cudaFree(rp->d_val);
+    cudaFree(rp->p.state); cudaFree(rp->d_staging); cudaFree(rp->d_idx); cudaFree(rp->d_planes); cudaFree(rp->d_pol); cudaFree(rp->d_val); cudaFree(rp->d_pos);
     delete rp;
 }
 
@@ -264,7 +312,7 @@ int az_replay_sample(az_replay* rp, int batch_size, uint64_t seed, float* planes
     const int n = std::min(batch_size, len);   // effective_batch_size (memory.rs:79)
     *n_out = n;
     if (n == 0) return AZ_OK;
-    // choose_multiple: n distinct live slots, uniformly (partial Fisher-Yates over the dense slot range [0, len))
+    // choose_multiple: n distinct live entries, uniformly (partial Fisher-Yates over the FIFO ranks [0, len))
     std::vector<int32_t> pool(len);
     for (int i = 0; i < len; i++) pool[i] = i;
     uint64_t s = host_splitmix64(seed);
@@ -280,6 +328,50 @@ int az_replay_sample(az_replay* rp, int batch_size, uint64_t seed, float* planes
     if (planes_out) AZ_CUDA(e, cudaMemcpyAsync(planes_out, rp->d_planes, (size_t)n * AZ_NUM_PLANES * 64 * 4, cudaMemcpyDeviceToHost, e->stream));
     if (policy_out) AZ_CUDA(e, cudaMemcpyAsync(policy_out, rp->d_pol, (size_t)n * AZ_ACTION_SPACE * 4, cudaMemcpyDeviceToHost, e->stream));
     if (value_out) AZ_CUDA(e, cudaMemcpyAsync(value_out, rp->d_val, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
+    AZ_CUDA(e, cudaStreamSynchronize(e->stream));
+    return AZ_OK;
+}
+
+int az_replay_export(az_replay* rp, int first, int n, az_position* pos_out, float* policy_out, float* value_out, uint32_t* visits_out,
+                     int* n_out) {
+    if (!rp || !n_out || first < 0 || n < 0 || !pos_out || !policy_out || !value_out || !visits_out) return AZ_ERR_INVALID_ARGUMENT;
+    az_engine* e = rp->eng;
+    cudaSetDevice(e->cfg.device);
+    if (n > rp->max_batch) return set_err(e, AZ_ERR_CAPACITY, "page larger than the replay buffer's max_batch");
+    int len = 0;
+    int r = az_replay_len(rp, &len);
+    if (r) return r;
+    const int m = std::max(0, std::min(n, len - first));
+    *n_out = m;
+    if (m == 0) return AZ_OK;
+    if (!rp->d_pos) AZ_CUDA(e, cudaMalloc(&rp->d_pos, (size_t)rp->max_batch * sizeof(az_position)));
+    e->n_launches++;
+    k_replay_export<<<m, 256, 0, e->stream>>>(rp->p, first, m, rp->d_pos, rp->d_pol, rp->d_val, reinterpret_cast<uint32_t*>(rp->d_idx));
+    AZ_CUDA(e, cudaGetLastError());
+    AZ_CUDA(e, cudaMemcpyAsync(pos_out, rp->d_pos, (size_t)m * sizeof(az_position), cudaMemcpyDeviceToHost, e->stream));
+    AZ_CUDA(e, cudaMemcpyAsync(policy_out, rp->d_pol, (size_t)m * AZ_ACTION_SPACE * 4, cudaMemcpyDeviceToHost, e->stream));
+    AZ_CUDA(e, cudaMemcpyAsync(value_out, rp->d_val, (size_t)m * 4, cudaMemcpyDeviceToHost, e->stream));
+    AZ_CUDA(e, cudaMemcpyAsync(visits_out, rp->d_idx, (size_t)m * 4, cudaMemcpyDeviceToHost, e->stream));
+    AZ_CUDA(e, cudaStreamSynchronize(e->stream));
+    return AZ_OK;
+}
+
+int az_replay_import(az_replay* rp, int n, const az_position* pos, const float* policy, const float* value, const uint32_t* visits) {
+    if (!rp || n < 0 || (n > 0 && (!pos || !policy || !value || !visits))) return AZ_ERR_INVALID_ARGUMENT;
+    az_engine* e = rp->eng;
+    cudaSetDevice(e->cfg.device);
+    if (n > rp->max_batch) return set_err(e, AZ_ERR_CAPACITY, "page larger than the replay buffer's max_batch");
+    if (n == 0) return AZ_OK;
+    for (int i = 0; i < n; i++)
+        if (visits[i] == 0) return set_err(e, AZ_ERR_INVALID_ARGUMENT, "a stored entry has visit_count >= 1");
+    if (!rp->d_pos) AZ_CUDA(e, cudaMalloc(&rp->d_pos, (size_t)rp->max_batch * sizeof(az_position)));
+    AZ_CUDA(e, cudaMemcpyAsync(rp->d_pos, pos, (size_t)n * sizeof(az_position), cudaMemcpyHostToDevice, e->stream));
+    AZ_CUDA(e, cudaMemcpyAsync(rp->d_pol, policy, (size_t)n * AZ_ACTION_SPACE * 4, cudaMemcpyHostToDevice, e->stream));
+    AZ_CUDA(e, cudaMemcpyAsync(rp->d_val, value, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
+    AZ_CUDA(e, cudaMemcpyAsync(rp->d_idx, visits, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
+    e->n_launches++;
+    k_replay_import<<<1, 1024, 0, e->stream>>>(rp->p, n, rp->d_pos, rp->d_pol, rp->d_val, reinterpret_cast<const uint32_t*>(rp->d_idx));
+    AZ_CUDA(e, cudaGetLastError());
     AZ_CUDA(e, cudaStreamSynchronize(e->stream));
     return AZ_OK;
 }

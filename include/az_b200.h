@@ -175,7 +175,10 @@ int az_selfplay_drain(az_engine* eng, az_sample* out, int max_samples, int* n_ou
  * means, the oldest unique position is evicted at capacity; *new_unique_out is the sum of add()'s return values.
  * az_replay_add_pending consumes the finished-game samples self-play left in device memory (no host round trip).
  * az_replay_sample mirrors ReplayBuffer::sample (memory.rs:78-97): min(batch, len) distinct entries, uniformly, returned as
- * to_tensor planes [n][19][8][8], policy [n][4096] and value [n].  Persistence (bincode save/load) is not provided. */
+ * to_tensor planes [n][19][8][8], policy [n][4096] and value [n].
+ * az_replay_export / az_replay_import move pages (<= max_batch entries) of {position, policy[4096], value, visit_count} in
+ * FIFO order (oldest first) for ReplayBuffer::save / load (memory.rs:100-115); the bincode framing of the reference's file
+ * is host-side (alphazero-chess_b200/replay_io.py).  Imported entries are appended as the newest ones. */
 typedef struct az_replay az_replay;
 int az_replay_create(az_engine* eng, int capacity, int max_batch, az_replay** out);
 void az_replay_destroy(az_replay* rp);
@@ -183,6 +186,9 @@ int az_replay_add(az_replay* rp, const az_sample* samples, int n, int* new_uniqu
 int az_replay_add_pending(az_replay* rp, int* n_added_out, int* new_unique_out);
 int az_replay_len(az_replay* rp, int* len_out);
 int az_replay_sample(az_replay* rp, int batch_size, uint64_t seed, float* planes_out, float* policy_out, float* value_out, int* n_out);
+int az_replay_export(az_replay* rp, int first, int n, az_position* pos_out, float* policy_out, float* value_out, uint32_t* visits_out,
+                     int* n_out);
+int az_replay_import(az_replay* rp, int n, const az_position* pos, const float* policy, const float* value, const uint32_t* visits);
 /* test hook: the entry stored for one position (visit_count 0 if absent) */
 int az_replay_get(az_replay* rp, const az_position* pos, float* policy_out, float* value_out, uint32_t* visit_count_out);
 

@@ -117,3 +117,35 @@ def test_sample_contract(played):
     p2, _, _ = gpu.sample(512, seed=3)
     assert p2.tobytes() != planes.tobytes()
     gpu.close()
+
+
+@pytest.mark.parametrize("capacity", [100_000, 300])
+def test_save_load_round_trip(played, capacity, tmp_path):
+    """ReplayBuffer::save / load (memory.rs:100-115): a reloaded buffer holds the same entries in the same FIFO order, so it
+    samples identically and evicts identically when more steps arrive."""
+    e, samples = played
+    a = az.ReplayBuffer(e, capacity=capacity, max_batch=64)
+    first, rest = samples[: len(samples) * 2 // 3], samples[len(samples) * 2 // 3:]
+    a.add(first)
+    path = tmp_path / "replay_buffer"
+    a.save(path)
+    b = az.ReplayBuffer(e, capacity=capacity, max_batch=64)
+    assert b.load(path) == len(a) == len(b)
+    pa, pb = a.export(0, 64), b.export(0, 64)
+    for x, y in zip(pa, pb):
+        assert x.tobytes() == y.tobytes()
+    for seed in (0, 9):
+        for x, y in zip(a.sample(48, seed=seed), b.sample(48, seed=seed)):
+            assert np.array_equal(x, y)
+    assert a.add(rest) == b.add(rest)          # same de-duplication and the same evictions afterwards
+    assert len(a) == len(b)
+    n = len(a)
+    for start in (0, max(0, n - 64)):
+        for x, y in zip(a.export(start, 64), b.export(start, 64)):
+            assert x.tobytes() == y.tobytes()
+    # the file itself: stored FENs carry the pseudo-legal en-passant square only, visit counts >= 1
+    from alphazero_chess_b200 import replay_io
+    pos, policy, value, visits = replay_io.read_file(path)
+    assert visits.min() >= 1 and np.allclose(policy.sum(1), 1.0, atol=1e-3)
+    a.close()
+    b.close()
