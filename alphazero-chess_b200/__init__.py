@@ -186,6 +186,11 @@ class Engine:
         ptrs = (ctypes.c_void_p * NUM_WEIGHT_ARRAYS)(*[a.ctypes.data for a in arrs])
         self._check(self._L.az_load_weights(self._h, ptrs, NUM_WEIGHT_ARRAYS), "az_load_weights")
 
+    def load_mpk(self, path):
+        """load_model (main.rs:109-116) from a burn `.mpk` checkpoint (see mpk.py)."""
+        from . import mpk
+        self.load_weights(mpk.load_mpk(path))
+
     def load_weights_dev(self, device_ptrs):
         ptrs = (ctypes.c_void_p * NUM_WEIGHT_ARRAYS)(*device_ptrs)
         self._check(self._L.az_load_weights_dev(self._h, ptrs, NUM_WEIGHT_ARRAYS), "az_load_weights_dev")
