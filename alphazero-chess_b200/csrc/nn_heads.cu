@@ -1,9 +1,9 @@
 // Policy and value heads of agent.rs:124-141 for the bf16 path, fused into one kernel on warp-level tensor-core MMAs:
 //   stage 1  [64 squares x 128 ch] x [128 x 40]   policy_conv_1 (32) and value_conv (8), BatchNorm folded, ReLU
 //   stage 2  [64 co x 32] x [32 x 64 squares]     policy_conv_2, kept transposed so that logits land as [co][square]
-//   softmax over the 4096 logits in registers (one warp owns one board), probabilities written as 32-byte sectors
+//   softmax over the 4096 logits in registers (two warps share a board, 32 squares each), probabilities written as 32-byte sectors
 //   value    [8 boards x 512] x [512 x 64] -> ReLU -> 64 -> 1 -> tanh, one board group per block
-// The heads are 0.3 % of the network's FLOPs; they use mma.sync (one warp per board needs no shared-memory staging of
+// The heads are 0.3 % of the network's FLOPs; they use mma.sync (a warp reads its rows straight from global memory, no shared-memory staging of
 // the activations) while the 99 % in the tower runs on tcgen05 (nn_tc.cu).
 #include "nn.h"
 #include "device_once.h"
@@ -18,7 +18,7 @@ constexpr int HEXP_PITCH = 68;   // floats per output-channel row of the per-war
 constexpr int HEADS_DYN_SMEM = 8 * 64 * HEXP_PITCH * 4;
 
 __device__ __forceinline__ void mma_bf16_16816(float* d, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
@@ -27,35 +27,41 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&p);
 }
 
-__global__ void __launch_bounds__(256, 1)
+// Two warps share a board (32 squares each) so that 16 warps are resident per SM: the kernel is latency-bound (a
+// handful of dependent MMA / shared-memory / global steps per board), and halving the per-warp accumulators (D2 is
+// [64 co][32 squares] = 64 registers) is what buys the second set of warps.
+__device__ __forceinline__ void pair_sync(int board_slot) { asm volatile("bar.sync %0, 64;" ::"r"(board_slot + 1) : "memory"); }
+
+__global__ void __launch_bounds__(512, 1)
 k_heads_mma(const __nv_bfloat16* __restrict__ tower, const __nv_bfloat16* __restrict__ w40, const float* __restrict__ b40,
             const __nv_bfloat16* __restrict__ wp2, const float* __restrict__ bp2, const __nv_bfloat16* __restrict__ wl1t,
             const float* __restrict__ bl1, const float* __restrict__ wl2, const float* __restrict__ bl2, float* __restrict__ policy_out,
             float* __restrict__ value_out, const int* __restrict__ n_dev, int n_static, HeadScatter sc) {
-    extern __shared__ float s_exp_all[];  // [8 warps][64 co][HEXP_PITCH]: exp(logit - max) of one board per warp
+    extern __shared__ float s_exp_all[];  // [8 boards][64 co][HEXP_PITCH]: exp(logit - max) of the board in flight
     __shared__ __align__(16) __nv_bfloat16 s_w40[40 * HW40_PITCH];
     __shared__ __align__(16) __nv_bfloat16 s_w2[64 * HW2_PITCH];
     __shared__ __align__(16) __nv_bfloat16 s_v1[8 * HV1_PITCH];
-    __shared__ float s_b40[40], s_b2[64], s_vsum[8][8];
+    __shared__ float s_b40[40], s_b2[64], s_red[2][8][2], s_hid[2][8][64], s_vsum[16];
     const int n = n_dev ? *n_dev : n_static;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31, g = lane >> 2, tig = lane & 3;
+    const int bs = warp >> 1, h = warp & 1;  // board slot in the block, square half
     // weights to shared memory with 16-byte copies (8 bf16): 40 rows x 16 chunks and 64 rows x 4 chunks
-    for (int i = t; i < 40 * 16; i += 256)
+    for (int i = t; i < 40 * 16; i += 512)
         *reinterpret_cast<uint4*>(s_w40 + (i >> 4) * HW40_PITCH + (i & 15) * 8) = __ldg(reinterpret_cast<const uint4*>(w40) + i);
-    for (int i = t; i < 64 * 4; i += 256)
-        *reinterpret_cast<uint4*>(s_w2 + (i >> 2) * HW2_PITCH + (i & 3) * 8) = __ldg(reinterpret_cast<const uint4*>(wp2) + i);
+    if (t < 64 * 4)
+        *reinterpret_cast<uint4*>(s_w2 + (t >> 2) * HW2_PITCH + (t & 3) * 8) = __ldg(reinterpret_cast<const uint4*>(wp2) + t);
     if (t < 40) s_b40[t] = b40[t];
     if (t < 64) s_b2[t] = bp2[t];
     __syncthreads();
 
     for (int base = blockIdx.x * 8; base < n; base += gridDim.x * 8) {
-        const int b = base + warp;
+        const int b = base + bs;
         const bool active = b < n;
         if (active) {
-            // ---------------- stage 1: D1[square][40]
-            float d1[4][5][4];
+            // ---------------- stage 1: D1[square][40] for this warp's 32 squares
+            float d1[2][5][4];
 #pragma unroll
-            for (int mt = 0; mt < 4; mt++)
+            for (int mt = 0; mt < 2; mt++)
 #pragma unroll
                 for (int nt = 0; nt < 5; nt++)
 #pragma unroll
@@ -64,8 +70,16 @@ k_heads_mma(const __nv_bfloat16* __restrict__ tower, const __nv_bfloat16* __rest
             // uses them for TWO k-steps.  The K order inside a 32-channel block is therefore permuted (k-step A takes
             // sub-channels 0-3 of every thread's group, k-step B 4-7); the weight fragments below use the same
             // permutation, which leaves the dot products unchanged.
-            const uint4* X = reinterpret_cast<const uint4*>(tower + (size_t)b * 64 * 128);  // [square][16 x 16 B]
-#pragma unroll 2
+            const uint4* X = reinterpret_cast<const uint4*>(tower + (size_t)b * 64 * 128) + h * 32 * 16;  // [square][16 x 16 B]
+            uint4 lo[4][2], hi[4][2];
+#pragma unroll
+            for (int blk = 0; blk < 4; blk++)
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++) {
+                    lo[blk][mt] = __ldg(X + (mt * 16 + g) * 16 + blk * 4 + tig);
+                    hi[blk][mt] = __ldg(X + (mt * 16 + g + 8) * 16 + blk * 4 + tig);
+                }
+#pragma unroll
             for (int blk = 0; blk < 4; blk++) {
                 uint2 bfA[5], bfB[5];
 #pragma unroll
@@ -75,19 +89,18 @@ k_heads_mma(const __nv_bfloat16* __restrict__ tower, const __nv_bfloat16* __rest
                     bfB[nt] = make_uint2(wv.z, wv.w);
                 }
 #pragma unroll
-                for (int mt = 0; mt < 4; mt++) {
-                    const uint4 lo = __ldg(X + (mt * 16 + g) * 16 + blk * 4 + tig);
-                    const uint4 hi = __ldg(X + (mt * 16 + g + 8) * 16 + blk * 4 + tig);
+                for (int mt = 0; mt < 2; mt++) {
 #pragma unroll
-                    for (int nt = 0; nt < 5; nt++) {
-                        mma_bf16_16816(d1[mt][nt], lo.x, hi.x, lo.y, hi.y, bfA[nt].x, bfA[nt].y);
-                        mma_bf16_16816(d1[mt][nt], lo.z, hi.z, lo.w, hi.w, bfB[nt].x, bfB[nt].y);
-                    }
+                    for (int nt = 0; nt < 5; nt++)
+                        mma_bf16_16816(d1[mt][nt], lo[blk][mt].x, hi[blk][mt].x, lo[blk][mt].y, hi[blk][mt].y, bfA[nt].x, bfA[nt].y);
+#pragma unroll
+                    for (int nt = 0; nt < 5; nt++)
+                        mma_bf16_16816(d1[mt][nt], lo[blk][mt].z, hi[blk][mt].z, lo[blk][mt].w, hi[blk][mt].w, bfB[nt].x, bfB[nt].y);
                 }
             }
             // bias + ReLU; value hidden (columns 32..39) to shared memory as the flattened [c*64 + square] row
 #pragma unroll
-            for (int mt = 0; mt < 4; mt++) {
+            for (int mt = 0; mt < 2; mt++) {
 #pragma unroll
                 for (int nt = 0; nt < 5; nt++) {
                     const float bb0 = s_b40[nt * 8 + tig * 2], bb1 = s_b40[nt * 8 + tig * 2 + 1];
@@ -96,26 +109,26 @@ k_heads_mma(const __nv_bfloat16* __restrict__ tower, const __nv_bfloat16* __rest
                     d1[mt][nt][2] = fmaxf(d1[mt][nt][2] + bb0, 0.0f);
                     d1[mt][nt][3] = fmaxf(d1[mt][nt][3] + bb1, 0.0f);
                 }
-                __nv_bfloat16* vr = s_v1 + warp * HV1_PITCH;
-                const int sq = mt * 16 + g, c = tig * 2;
+                __nv_bfloat16* vr = s_v1 + bs * HV1_PITCH;
+                const int sq = h * 32 + mt * 16 + g, c = tig * 2;
                 vr[c * 64 + sq] = __float2bfloat16_rn(d1[mt][4][0]);
                 vr[(c + 1) * 64 + sq] = __float2bfloat16_rn(d1[mt][4][1]);
                 vr[c * 64 + sq + 8] = __float2bfloat16_rn(d1[mt][4][2]);
                 vr[(c + 1) * 64 + sq + 8] = __float2bfloat16_rn(d1[mt][4][3]);
             }
             // ---------------- stage 2 (transposed): D2[co][square] = W2[co][k] * P1[square][k]
-            float d2[4][8][4];
+            float d2[4][4][4];
 #pragma unroll
             for (int mt = 0; mt < 4; mt++)
 #pragma unroll
-                for (int nt = 0; nt < 8; nt++)
+                for (int nt = 0; nt < 4; nt++)
 #pragma unroll
                     for (int i = 0; i < 4; i++) d2[mt][nt][i] = 0.0f;
 #pragma unroll
             for (int ks = 0; ks < 2; ks++) {
-                uint32_t bfr[8][2];
+                uint32_t bfr[4][2];
 #pragma unroll
-                for (int nt = 0; nt < 8; nt++) {  // squares 8nt..8nt+7 come from D1 m-tile nt>>1, row half nt&1
+                for (int nt = 0; nt < 4; nt++) {  // squares 8nt..8nt+7 of this half come from D1 m-tile nt>>1, row half nt&1
                     const int h2 = (nt & 1) * 2;
                     bfr[nt][0] = pack_bf16(d1[nt >> 1][2 * ks][h2], d1[nt >> 1][2 * ks][h2 + 1]);
                     bfr[nt][1] = pack_bf16(d1[nt >> 1][2 * ks + 1][h2], d1[nt >> 1][2 * ks + 1][h2 + 1]);
@@ -125,89 +138,99 @@ k_heads_mma(const __nv_bfloat16* __restrict__ tower, const __nv_bfloat16* __rest
                     const uint32_t* wp = reinterpret_cast<const uint32_t*>(s_w2 + (mt * 16 + g) * HW2_PITCH + ks * 16 + tig * 2);
                     const uint32_t a0 = wp[0], a1 = wp[8 * HW2_PITCH / 2], a2 = wp[4], a3 = wp[8 * HW2_PITCH / 2 + 4];
 #pragma unroll
-                    for (int nt = 0; nt < 8; nt++) mma_bf16_16816(d2[mt][nt], a0, a1, a2, a3, bfr[nt][0], bfr[nt][1]);
+                    for (int nt = 0; nt < 4; nt++) mma_bf16_16816(d2[mt][nt], a0, a1, a2, a3, bfr[nt][0], bfr[nt][1]);
                 }
             }
-            // ---------------- softmax over the board's 4096 logits (agent.rs:130)
+            // ---------------- softmax over the board's 4096 logits (agent.rs:130), two warps per board
             float mx = -INFINITY;
 #pragma unroll
             for (int mt = 0; mt < 4; mt++) {
                 const float c0 = s_b2[mt * 16 + g], c1 = s_b2[mt * 16 + g + 8];
 #pragma unroll
-                for (int nt = 0; nt < 8; nt++) {
+                for (int nt = 0; nt < 4; nt++) {
                     d2[mt][nt][0] += c0; d2[mt][nt][1] += c0; d2[mt][nt][2] += c1; d2[mt][nt][3] += c1;
                     mx = fmaxf(mx, fmaxf(fmaxf(d2[mt][nt][0], d2[mt][nt][1]), fmaxf(d2[mt][nt][2], d2[mt][nt][3])));
                 }
             }
             for (int d = 16; d; d >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+            if (lane == 0) s_red[0][bs][h] = mx;
+            pair_sync(bs);
+            mx = fmaxf(s_red[0][bs][0], s_red[0][bs][1]);
             float sum = 0.0f;
 #pragma unroll
             for (int mt = 0; mt < 4; mt++)
 #pragma unroll
-                for (int nt = 0; nt < 8; nt++)
+                for (int nt = 0; nt < 4; nt++)
 #pragma unroll
                     for (int i = 0; i < 4; i++) { d2[mt][nt][i] = __expf(d2[mt][nt][i] - mx); sum += d2[mt][nt][i]; }
             for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
-            const float inv = __fdividef(1.0f, sum);
-            if (sc.edge_P) {  // priors of the legal moves only, written into the tree (tree.rs:84-104 reads nothing else)
-                float* se = s_exp_all + warp * 64 * HEXP_PITCH;
+            if (lane == 0) s_red[1][bs][h] = sum;
+            if (sc.edge_P) {  // this half of the exp tile; the scatter below reads both halves
+                float* se = s_exp_all + bs * 64 * HEXP_PITCH;
 #pragma unroll
                 for (int mt = 0; mt < 4; mt++)
 #pragma unroll
-                    for (int nt = 0; nt < 8; nt++) {
-                        const int co = mt * 16 + g, sq = nt * 8 + tig * 2;
+                    for (int nt = 0; nt < 4; nt++) {
+                        const int co = mt * 16 + g, sq = h * 32 + nt * 8 + tig * 2;
                         *reinterpret_cast<float2*>(se + co * HEXP_PITCH + sq) = make_float2(d2[mt][nt][0], d2[mt][nt][1]);
                         *reinterpret_cast<float2*>(se + (co + 8) * HEXP_PITCH + sq) = make_float2(d2[mt][nt][2], d2[mt][nt][3]);
                     }
-                __syncwarp();
+            }
+            pair_sync(bs);
+            const float inv = __fdividef(1.0f, s_red[1][bs][0] + s_red[1][bs][1]);
+            if (sc.edge_P) {  // priors of the legal moves only, written into the tree (tree.rs:84-104 reads nothing else)
+                const float* se = s_exp_all + bs * 64 * HEXP_PITCH;
                 const unsigned long long eo = sc.edge_off[b];
                 const int L = sc.n_edges[b];
-                for (int e2 = lane; e2 < L; e2 += 32) {
+                for (int e2 = h * 32 + lane; e2 < L; e2 += 64) {
                     const uint32_t idx = sc.edge_mv[eo + e2] >> 16;
                     sc.edge_P[eo + e2] = se[(idx >> 6) * HEXP_PITCH + (idx & 63)] * inv;
                 }
-                __syncwarp();
             }
             if (policy_out) {
                 float* po = policy_out + (size_t)b * 4096;
 #pragma unroll
                 for (int mt = 0; mt < 4; mt++)
 #pragma unroll
-                    for (int nt = 0; nt < 8; nt++) {
-                        const int co = mt * 16 + g, sq = nt * 8 + tig * 2;
+                    for (int nt = 0; nt < 4; nt++) {
+                        const int co = mt * 16 + g, sq = h * 32 + nt * 8 + tig * 2;
                         *reinterpret_cast<float2*>(po + co * 64 + sq) = make_float2(d2[mt][nt][0] * inv, d2[mt][nt][1] * inv);
                         *reinterpret_cast<float2*>(po + (co + 8) * 64 + sq) = make_float2(d2[mt][nt][2] * inv, d2[mt][nt][3] * inv);
                     }
             }
         } else {
-            for (int i = lane; i < 512; i += 32) s_v1[warp * HV1_PITCH + i] = __float2bfloat16_rn(0.0f);
+            for (int i = h * 32 + lane; i < 512; i += 64) s_v1[bs * HV1_PITCH + i] = __float2bfloat16_rn(0.0f);
         }
-        __syncthreads();
-        // ---------------- value head: hidden[board][8w..8w+7] on warp w (rows 8..15 of the M=16 tile are unused)
+        // ---------------- value head: warp w sums K half (w >> 3) of hidden[board][8(w&7) .. +7] (rows 8..15 of the M=16 tile unused)
         {
             float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-            const uint32_t* W = reinterpret_cast<const uint32_t*>(wl1t + (size_t)(warp * 8 + g) * 512);
-            const uint32_t* V = reinterpret_cast<const uint32_t*>(s_v1 + g * HV1_PITCH);
-#pragma unroll 4
-            for (int ks = 0; ks < 32; ks++) {
-                const uint32_t a0 = V[ks * 8 + tig], a2 = V[ks * 8 + tig + 4];
-                const uint32_t b0 = __ldg(W + ks * 8 + tig), b1 = __ldg(W + ks * 8 + tig + 4);
-                mma_bf16_16816(acc, a0, 0u, a2, 0u, b0, b1);
-            }
-            const int hn = warp * 8 + tig * 2;
-            float part = fmaxf(acc[0] + bl1[hn], 0.0f) * wl2[hn] + fmaxf(acc[1] + bl1[hn + 1], 0.0f) * wl2[hn + 1];
-            part += __shfl_xor_sync(0xffffffffu, part, 1);
-            part += __shfl_xor_sync(0xffffffffu, part, 2);
-            if (tig == 0) s_vsum[warp][g] = part;
-        }
-        __syncthreads();
-        if (t < 8 && base + t < n) {
-            float v = bl2[0];
+            const int hw = warp & 7, kh = warp >> 3;
+            const uint32_t* W = reinterpret_cast<const uint32_t*>(wl1t + (size_t)(hw * 8 + g) * 512) + kh * 128;
+            const uint32_t* V = reinterpret_cast<const uint32_t*>(s_v1 + g * HV1_PITCH) + kh * 128;
+            // the weight fragments do not depend on the boards: requested before the barrier (the policy accumulators are
+            // dead by now), so their L2 latency hides behind the wait for the slowest warp
+            uint32_t wf[16][2];
 #pragma unroll
-            for (int w = 0; w < 8; w++) v += s_vsum[w][t];
-            value_out[base + t] = tanhf(v);
+            for (int ks = 0; ks < 16; ks++) { wf[ks][0] = __ldg(W + ks * 8 + tig); wf[ks][1] = __ldg(W + ks * 8 + tig + 4); }
+            __syncthreads();
+#pragma unroll
+            for (int ks = 0; ks < 16; ks++) {
+                const uint32_t a0 = V[ks * 8 + tig], a2 = V[ks * 8 + tig + 4];
+                mma_bf16_16816(acc, a0, 0u, a2, 0u, wf[ks][0], wf[ks][1]);
+            }
+            const int hn = hw * 8 + tig * 2;   // acc[0], acc[1]: board g, hidden units hn, hn + 1
+            s_hid[kh][g][hn] = acc[0];
+            s_hid[kh][g][hn + 1] = acc[1];
         }
         __syncthreads();
+        {   // 8 boards x 64 hidden units on 512 threads: ReLU(sum of the two K halves + bias) * w2, reduced per board
+            const int vb = t >> 6, hn = t & 63;
+            float part = fmaxf(s_hid[0][vb][hn] + s_hid[1][vb][hn] + bl1[hn], 0.0f) * wl2[hn];
+            for (int d = 16; d; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+            if (lane == 0) s_vsum[warp] = part;
+        }
+        __syncthreads();
+        if (t < 8 && base + t < n) value_out[base + t] = tanhf(bl2[0] + s_vsum[2 * t] + s_vsum[2 * t + 1]);
     }
 }
 
@@ -221,7 +244,7 @@ int launch_heads_mma(az_engine* e, const __nv_bfloat16* tower, const int* n_dev,
     if (once.first()) cudaFuncSetAttribute(k_heads_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, HEADS_DYN_SMEM);
     HeadScatter sc{nullptr, nullptr, nullptr, nullptr};
     if (scatter) sc = *scatter;
-    k_heads_mma<<<grid, 256, HEADS_DYN_SMEM, e->stream>>>(tower, w->h_w40, w->f_b40, w->h_wp2, w->f_bp2, w->h_wl1t, w->f_bl1, w->f_wl2, w->f_bl2,
+    k_heads_mma<<<grid, 512, HEADS_DYN_SMEM, e->stream>>>(tower, w->h_w40, w->f_b40, w->h_wp2, w->f_bp2, w->h_wl1t, w->f_bl1, w->f_wl2, w->f_bl2,
                                              policy_out, value_out, n_dev, n_static, sc);
     return check_cuda(e, cudaGetLastError(), "k_heads_mma");
 }
