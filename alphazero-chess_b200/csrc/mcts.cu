@@ -551,7 +551,10 @@ __device__ void move_step(Ctx& x) {
 }
 
 // ------------------------------------------------------------------------------------------- the wave kernel
-__global__ void __launch_bounds__(WARPS * 32) k_advance(SearchParams prm, SearchPtrs ptr) {
+// MINB = resident blocks per SM the register allocation is bounded for: the kernel is a chain of dependent global loads
+// per game, so resident warps (latency hiding) are worth more than registers (AZ_ADV_MINB selects, see launch below)
+template <int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) k_advance(SearchParams prm, SearchPtrs ptr) {
     __shared__ WarpShared shared[WARPS];
     const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (g >= prm.n_games) return;
@@ -881,7 +884,14 @@ static int run_wave(az_engine* e, SearchState* st) {
         cudaEventRecord(e->prof_adv_event, e->stream);
     }
     e->n_launches++;
-    k_advance<<<blocks, WARPS * 32, 0, e->stream>>>(st->prm, st->ptr);
+    static int minb = -1;
+    if (minb < 0) { const char* v = getenv("AZ_ADV_MINB"); minb = v ? atoi(v) : 4; }  // measured per wave of 4096 games: 3 -> 95 us, 4 -> 81 us (128 registers, no spills), 5 -> 81 us, 6 -> 84 us
+    switch (minb) {
+        case 4: k_advance<4><<<blocks, WARPS * 32, 0, e->stream>>>(st->prm, st->ptr); break;
+        case 5: k_advance<5><<<blocks, WARPS * 32, 0, e->stream>>>(st->prm, st->ptr); break;
+        case 6: k_advance<6><<<blocks, WARPS * 32, 0, e->stream>>>(st->prm, st->ptr); break;
+        default: k_advance<3><<<blocks, WARPS * 32, 0, e->stream>>>(st->prm, st->ptr); break;
+    }
     AZ_CUDA(e, cudaGetLastError());
     return evaluate_batch(e, st);
 }
