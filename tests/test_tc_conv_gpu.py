@@ -51,6 +51,12 @@ def test_conv3x3_no_residual_no_relu():
     assert (err <= 0.02 + 0.01 * ref.abs()).all(), err.max().item()
 
 
+def test_conv3x3_input_layer_speed_report():
+    out, ref, ms = _run(4096, 64, residual=False, relu=True, iters=20)
+    print(f"\nconv3x3 tc (64 padded input channels): {ms * 1e3:.1f} us @4096 boards")
+    assert ms > 0
+
+
 def test_conv3x3_speed_report():
     out, ref, ms = _run(4096, 128, residual=True, relu=True, iters=20)
     flops = 2.0 * 4096 * 64 * 128 * 1152
