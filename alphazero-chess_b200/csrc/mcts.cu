@@ -180,7 +180,7 @@ __device__ __forceinline__ bool draw_by_rules(Ctx& x, const DPos& child, int dep
         const int j = v - 2 * k;
         if (k <= n_cand && j >= 0) {
             const DPos* q;
-            if (j > root_v) q = &x.ptr.node_pos[x.nbase + (x.ptr.path[(size_t)x.g * x.prm.node_cap + (j - root_v)] & 0xFFFF)];
+            if (j > root_v) q = &x.ptr.node_pos[x.nbase + (x.ptr.path[(size_t)x.g * x.prm.node_cap + (j - root_v)].x & 0xFFFF)];
             else q = &x.ptr.hist[(size_t)x.g * HIST_CAP + j];
             eq = same_position_key(*q, child);
         }
@@ -299,9 +299,9 @@ __device__ __forceinline__ void backup(Ctx& x, float leaf_value, int path_len) {
     for (int i0 = 0; i0 < path_len; i0 += 32) {
         const int i = i0 + x.lane;
         if (i < path_len) {
-            const uint32_t pe = x.ptr.path[(size_t)x.g * x.prm.node_cap + i];
-            const int node = pe & 0xFFFF, edge = pe >> 16;
-            const size_t e = x.ebase + x.ptr.node_edge_off[x.nbase + node] + edge;
+            const uint2 pe = x.ptr.path[(size_t)x.g * x.prm.node_cap + i];
+            const int node = pe.x & 0xFFFF;
+            const size_t e = x.ebase + pe.y;
             // levels above the leaf's parent: the sign flips once per level
             const int up = path_len - 1 - i;
             const float v = (up & 1) ? leaf_value : -leaf_value;
@@ -325,25 +325,33 @@ __device__ __forceinline__ void select_leaf(Ctx& x, int& leaf_node, int& leaf_ed
         const float sq = __fsqrt_rn(total);
         float best = -INFINITY;
         int best_e = 0x7FFFFFFF;
+        // the child link travels with the score, so the walk does not wait for one more dependent load per level
+        int best_child = x.lane == 0 && L > 0 ? x.ptr.edge_child[off] : -1;
         for (int e = x.lane; e < L; e += 32) {
             const float P = x.ptr.edge_P[off + e], N = x.ptr.edge_N[off + e], W = x.ptr.edge_W[off + e];
+            const int ch = x.ptr.edge_child[off + e];
             const float u = __fdiv_rn(__fmul_rn(__fmul_rn(x.prm.c_puct, P), sq), __fadd_rn(1.0f, N));
             const float q = N > 0.0f ? __fdiv_rn(W, N) : 0.0f;
             const float v = __fadd_rn(q, u);
-            if (v > best) { best = v; best_e = e; }
+            if (v > best) { best = v; best_e = e; best_child = ch; }
         }
         // warp argmax: larger value wins, ties go to the earlier move (strict '>' in list order)
         for (int d = 16; d; d >>= 1) {
             const float ov = __shfl_xor_sync(0xffffffffu, best, d);
             const int oe = __shfl_xor_sync(0xffffffffu, best_e, d);
-            if (ov > best || (ov == best && oe < best_e)) { best = ov; best_e = oe; }
+            const int oc = __shfl_xor_sync(0xffffffffu, best_child, d);
+            if (ov > best || (ov == best && oe < best_e)) { best = ov; best_e = oe; best_child = oc; }
         }
-        if (best_e == 0x7FFFFFFF) best_e = 0;  // every score was NaN / -inf: the reference keeps max_index = 0 (first move)
+        if (best_e == 0x7FFFFFFF) {  // every score was NaN / -inf: the reference keeps max_index = 0 (first move)
+            best_e = 0;
+            best_child = __shfl_sync(0xffffffffu, best_child, 0);
+        }
         if (x.lane == 0) {
-            x.ptr.path[(size_t)x.g * x.prm.node_cap + depth] = (uint32_t)node | ((uint32_t)best_e << 16);
+            x.ptr.path[(size_t)x.g * x.prm.node_cap + depth] =
+                make_uint2((uint32_t)node | ((uint32_t)best_e << 16), (uint32_t)(off - x.ebase) + (uint32_t)best_e);
             x.st_edges += L;
         }
-        const int child = x.ptr.edge_child[off + best_e];
+        const int child = best_child;
         if (child < 0) { leaf_node = node; leaf_edge = best_e; __syncwarp(); return; }
         node = child;
         depth++;
@@ -638,15 +646,16 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_advance(SearchParams prm, 
 
     if (x.lane == 0) {
         ptr.ctl[g] = x.c;
-        Counters* ct = ptr.counters;
-        if (x.st_sims) atomicAdd(&ct->simulations, (unsigned long long)x.st_sims);
-        if (x.st_pos) atomicAdd(&ct->positions, (unsigned long long)x.st_pos);
-        if (x.st_evals) atomicAdd(&ct->evaluations, (unsigned long long)x.st_evals);
-        if (x.st_term) atomicAdd(&ct->terminal_leaves, (unsigned long long)x.st_term);
-        if (x.st_games) atomicAdd(&ct->games_finished, (unsigned long long)x.st_games);
-        if (x.st_depth) atomicAdd(&ct->sum_leaf_depth, (unsigned long long)x.st_depth);
-        if (x.st_edges) atomicAdd(&ct->sum_edges, (unsigned long long)x.st_edges);
-        if (x.st_hits) atomicAdd(&ct->cache_hits, (unsigned long long)x.st_hits);
+        // statistics: same field order as Counters; 64 stripes keep 4096 warps from queueing on eight addresses
+        unsigned long long* ct = ptr.stats + (size_t)(blockIdx.x & (STAT_STRIPES - 1)) * 8;
+        if (x.st_sims) atomicAdd(&ct[0], (unsigned long long)x.st_sims);
+        if (x.st_pos) atomicAdd(&ct[1], (unsigned long long)x.st_pos);
+        if (x.st_evals) atomicAdd(&ct[2], (unsigned long long)x.st_evals);
+        if (x.st_hits) atomicAdd(&ct[3], (unsigned long long)x.st_hits);
+        if (x.st_term) atomicAdd(&ct[4], (unsigned long long)x.st_term);
+        if (x.st_games) atomicAdd(&ct[5], (unsigned long long)x.st_games);
+        if (x.st_depth) atomicAdd(&ct[6], (unsigned long long)x.st_depth);
+        if (x.st_edges) atomicAdd(&ct[7], (unsigned long long)x.st_edges);
     }
 }
 
@@ -817,6 +826,7 @@ int search_create(az_engine* e) {
     r |= salloc(e, st, &q.req_f32, (size_t)e->max_batch * AZ_NUM_PLANES * 64);
     r |= salloc(e, st, &q.req_edge_off, (size_t)e->max_batch); r |= salloc(e, st, &q.req_nedges, (size_t)e->max_batch);
     r |= salloc(e, st, &q.start_prior, 32); r |= salloc(e, st, &q.counters, 1);
+    r |= salloc(e, st, &q.stats, (size_t)STAT_STRIPES * 8);
     if (r) return AZ_ERR_OUT_OF_MEMORY;
     p.cache_mask = 0; q.cache_state = nullptr; q.cache_entry = nullptr;
     if (c.cache_log2 > 0) {
@@ -832,6 +842,7 @@ int search_create(az_engine* e) {
     q.game_samples = nullptr;
     q.out_samples = nullptr;
     cudaMemset(q.counters, 0, sizeof(Counters));
+    cudaMemset(q.stats, 0, (size_t)STAT_STRIPES * 8 * sizeof(unsigned long long));
     cudaMemset(q.batch_count, 0, 16);
     return 0;
 }
@@ -1010,6 +1021,7 @@ int az_selfplay_begin(az_engine* e, int n_games, uint64_t first_game_id) {
     std::memset(&zero, 0, sizeof zero);
     zero.next_game_id = first_game_id + n_games;
     AZ_CUDA(e, cudaMemcpyAsync(q.counters, &zero, sizeof zero, cudaMemcpyHostToDevice, e->stream));
+    AZ_CUDA(e, cudaMemsetAsync(q.stats, 0, (size_t)STAT_STRIPES * 8 * sizeof(unsigned long long), e->stream));
     // the one shared forward of the start position (training.rs:344-350)
     az_position sp;
     az_position_start(&sp);
@@ -1048,8 +1060,16 @@ int az_selfplay_step(az_engine* e, int waves, az_selfplay_stats* out) {
         if (r) return r;
     }
     Counters c;
+    unsigned long long stripes[STAT_STRIPES * 8];
     AZ_CUDA(e, cudaMemcpyAsync(&c, st->ptr.counters, sizeof c, cudaMemcpyDeviceToHost, e->stream));
+    AZ_CUDA(e, cudaMemcpyAsync(stripes, st->ptr.stats, sizeof stripes, cudaMemcpyDeviceToHost, e->stream));
     AZ_CUDA(e, cudaStreamSynchronize(e->stream));
+    {
+        unsigned long long sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int i = 0; i < STAT_STRIPES * 8; i++) sum[i & 7] += stripes[i];
+        c.simulations = sum[0]; c.positions = sum[1]; c.evaluations = sum[2]; c.cache_hits = sum[3];
+        c.terminal_leaves = sum[4]; c.games_finished = sum[5]; c.sum_leaf_depth = sum[6]; c.sum_edges = sum[7];
+    }
     if (out) {
         out->simulations = c.simulations; out->positions = c.positions; out->evaluations = c.evaluations; out->cache_hits = c.cache_hits;
         out->terminal_leaves = c.terminal_leaves; out->games_finished = c.games_finished; out->sum_leaf_depth = c.sum_leaf_depth;

@@ -57,6 +57,8 @@ struct Counters {
         next_game_id, samples_out, errors;
 };
 
+constexpr int STAT_STRIPES = 64;
+
 struct SearchPtrs {
     // nodes [G * node_cap]
     DPos* node_pos;
@@ -73,7 +75,7 @@ struct SearchPtrs {
     uint32_t* edge_mv;   // wire move | policy index << 16
     // per game
     GameCtl* ctl;
-    uint32_t* path;      // [G][node_cap]: node | edge << 16
+    uint2* path;         // [G][node_cap]: x = node | edge << 16, y = the edge's index in the game's edge pool (saves backup a lookup)
     DPos* hist;          // [G][HIST_CAP]
     // evaluation requests / results
     int* batch_count;
@@ -91,6 +93,7 @@ struct SearchPtrs {
     uint32_t* cache_state;     // [slots] 0 empty, 1 being written, (tag << 2) | 2 published
     CacheEntry* cache_entry;   // [slots]
     Counters* counters;
+    unsigned long long* stats;         // [STAT_STRIPES][8]: the statistics fields of Counters, striped by block to spread the atomics
 };
 
 struct SearchState {
