@@ -10,6 +10,7 @@
 // one batch (the reference's recv_many batch, training.rs:369).
 #include "mcts.h"
 #include "nn.h"
+#include <cstdio>
 #include <cstring>
 #include <algorithm>
 
@@ -559,10 +560,17 @@ __device__ void move_step(Ctx& x) {
 }
 
 // ------------------------------------------------------------------------------------------- the wave kernel
-// MINB = resident blocks per SM the register allocation is bounded for: the kernel is a chain of dependent global loads
+#ifdef AZ_ADV_TIMING
+#define ADV_T0() long long t_prev = clock64(), t_start = t_prev; unsigned long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define ADV_T(k) do { const long long t_now = clock64(); t_acc[k] += (unsigned long long)(t_now - t_prev); t_prev = t_now; } while (0)
+#else
+#define ADV_T0() do { } while (0)
+#define ADV_T(k) do { } while (0)
+#endif
+// MINB = resident groups of four warps per SM the register allocation is bounded for: the kernel is a chain of dependent global loads
 // per game, so resident warps (latency hiding) are worth more than registers (AZ_ADV_MINB selects, see launch below)
 template <int MINB>
-__global__ void __launch_bounds__(WARPS * 32, MINB) k_advance(SearchParams prm, SearchPtrs ptr) {
+__global__ void __launch_bounds__(WARPS * 32, MINB * 4 / WARPS) k_advance(SearchParams prm, SearchPtrs ptr) {
     __shared__ WarpShared shared[WARPS];
     const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (g >= prm.n_games) return;
@@ -570,6 +578,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_advance(SearchParams prm, 
           ptr.ctl[g], 0, 0, 0, 0, 0, 0, 0, 0};
     if (x.c.status != 0) return;
 
+    ADV_T0();
     // ---- 1. the evaluation requested in the previous wave has arrived
     if (x.c.pending_node >= 0) {
         const int node = x.c.pending_node, slot = x.c.pending_slot;
@@ -595,21 +604,26 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_advance(SearchParams prm, 
         x.c.pending_node = -1;
     }
 
+    ADV_T(0);
     // ---- 2. run until the network is needed again
     for (int iter = 0; iter < prm.max_iters; iter++) {
         if ((int)x.c.sims_done >= prm.S) {
             if (prm.mode == 0) { x.c.status = 1; break; }
             move_step(x);
+            ADV_T(6);
             if (x.c.status != 0) break;
             continue;
         }
         int node, edge, depth;
         select_leaf(x, node, edge, depth);
+        ADV_T(1);
         const size_t pe = x.ebase + ptr.node_edge_off[x.nbase + node] + edge;
         const DPos parent = ptr.node_pos[x.nbase + node];
         lane0_make_child(x, parent, (uint16_t)(ptr.edge_mv[pe] & 0xFFFF));
         int term = x.sh->term;
+        ADV_T(2);
         if (term == 0 && draw_by_rules(x, x.sh->child, depth + 1)) term = 1;
+        ADV_T(3);
         if (x.lane == 0) x.st_depth += depth + 1;
         if (term != 0) {
             // Draw -> 0.0, decisive -> -1.0 from the child's side (tree.rs:233-234); nothing is stored
@@ -619,6 +633,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_advance(SearchParams prm, 
             continue;
         }
         const int child = create_node(x, depth + 1);
+        ADV_T(4);
         if (child < 0) { x.c.status = 2; if (x.lane == 0) atomicAdd(&ptr.counters->errors, 1ULL); break; }
         if (x.lane == 0) ptr.edge_child[pe] = child;
         x.c.max_depth = max(x.c.max_depth, (uint32_t)(depth + 1));
@@ -641,13 +656,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_advance(SearchParams prm, 
         x.c.pending_node = child;
         x.c.pending_slot = submit_request(x, child);
         x.c.path_len = depth + 1;
+        ADV_T(5);
         break;
     }
 
     if (x.lane == 0) {
         ptr.ctl[g] = x.c;
         // statistics: same field order as Counters; 64 stripes keep 4096 warps from queueing on eight addresses
-        unsigned long long* ct = ptr.stats + (size_t)(blockIdx.x & (STAT_STRIPES - 1)) * 8;
+        unsigned long long* ct = ptr.stats + (size_t)(blockIdx.x & (STAT_STRIPES - 1)) * 16;
         if (x.st_sims) atomicAdd(&ct[0], (unsigned long long)x.st_sims);
         if (x.st_pos) atomicAdd(&ct[1], (unsigned long long)x.st_pos);
         if (x.st_evals) atomicAdd(&ct[2], (unsigned long long)x.st_evals);
@@ -656,6 +672,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) k_advance(SearchParams prm, 
         if (x.st_games) atomicAdd(&ct[5], (unsigned long long)x.st_games);
         if (x.st_depth) atomicAdd(&ct[6], (unsigned long long)x.st_depth);
         if (x.st_edges) atomicAdd(&ct[7], (unsigned long long)x.st_edges);
+#ifdef AZ_ADV_TIMING
+        t_acc[7] = (unsigned long long)(clock64() - t_start);
+        for (int k = 0; k < 8; k++) atomicAdd(&ct[8 + k], t_acc[k]);
+#endif
     }
 }
 
@@ -826,7 +846,7 @@ int search_create(az_engine* e) {
     r |= salloc(e, st, &q.req_f32, (size_t)e->max_batch * AZ_NUM_PLANES * 64);
     r |= salloc(e, st, &q.req_edge_off, (size_t)e->max_batch); r |= salloc(e, st, &q.req_nedges, (size_t)e->max_batch);
     r |= salloc(e, st, &q.start_prior, 32); r |= salloc(e, st, &q.counters, 1);
-    r |= salloc(e, st, &q.stats, (size_t)STAT_STRIPES * 8);
+    r |= salloc(e, st, &q.stats, (size_t)STAT_STRIPES * 16);
     if (r) return AZ_ERR_OUT_OF_MEMORY;
     p.cache_mask = 0; q.cache_state = nullptr; q.cache_entry = nullptr;
     if (c.cache_log2 > 0) {
@@ -842,7 +862,7 @@ int search_create(az_engine* e) {
     q.game_samples = nullptr;
     q.out_samples = nullptr;
     cudaMemset(q.counters, 0, sizeof(Counters));
-    cudaMemset(q.stats, 0, (size_t)STAT_STRIPES * 8 * sizeof(unsigned long long));
+    cudaMemset(q.stats, 0, (size_t)STAT_STRIPES * 16 * sizeof(unsigned long long));
     cudaMemset(q.batch_count, 0, 16);
     return 0;
 }
@@ -1021,7 +1041,7 @@ int az_selfplay_begin(az_engine* e, int n_games, uint64_t first_game_id) {
     std::memset(&zero, 0, sizeof zero);
     zero.next_game_id = first_game_id + n_games;
     AZ_CUDA(e, cudaMemcpyAsync(q.counters, &zero, sizeof zero, cudaMemcpyHostToDevice, e->stream));
-    AZ_CUDA(e, cudaMemsetAsync(q.stats, 0, (size_t)STAT_STRIPES * 8 * sizeof(unsigned long long), e->stream));
+    AZ_CUDA(e, cudaMemsetAsync(q.stats, 0, (size_t)STAT_STRIPES * 16 * sizeof(unsigned long long), e->stream));
     // the one shared forward of the start position (training.rs:344-350)
     az_position sp;
     az_position_start(&sp);
@@ -1060,13 +1080,21 @@ int az_selfplay_step(az_engine* e, int waves, az_selfplay_stats* out) {
         if (r) return r;
     }
     Counters c;
-    unsigned long long stripes[STAT_STRIPES * 8];
+    unsigned long long stripes[STAT_STRIPES * 16];
     AZ_CUDA(e, cudaMemcpyAsync(&c, st->ptr.counters, sizeof c, cudaMemcpyDeviceToHost, e->stream));
     AZ_CUDA(e, cudaMemcpyAsync(stripes, st->ptr.stats, sizeof stripes, cudaMemcpyDeviceToHost, e->stream));
     AZ_CUDA(e, cudaStreamSynchronize(e->stream));
     {
         unsigned long long sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (int i = 0; i < STAT_STRIPES * 8; i++) sum[i & 7] += stripes[i];
+        for (int i = 0; i < STAT_STRIPES * 16; i++) if ((i & 15) < 8) sum[i & 7] += stripes[i];
+#ifdef AZ_ADV_TIMING
+        unsigned long long tc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int i = 0; i < STAT_STRIPES * 16; i++) if ((i & 15) >= 8) tc[i & 7] += stripes[i];
+        fprintf(stderr, "azb: k_advance phase clocks per warp-wave: consume %.0f select %.0f child %.0f rules %.0f create %.0f submit %.0f move %.0f total %.0f\n",
+                (double)tc[0] / ((double)st->prm.n_games * waves), (double)tc[1] / ((double)st->prm.n_games * waves), (double)tc[2] / ((double)st->prm.n_games * waves),
+                (double)tc[3] / ((double)st->prm.n_games * waves), (double)tc[4] / ((double)st->prm.n_games * waves), (double)tc[5] / ((double)st->prm.n_games * waves),
+                (double)tc[6] / ((double)st->prm.n_games * waves), (double)tc[7] / ((double)st->prm.n_games * waves));
+#endif
         c.simulations = sum[0]; c.positions = sum[1]; c.evaluations = sum[2]; c.cache_hits = sum[3];
         c.terminal_leaves = sum[4]; c.games_finished = sum[5]; c.sum_leaf_depth = sum[6]; c.sum_edges = sum[7];
     }

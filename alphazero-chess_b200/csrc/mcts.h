@@ -93,7 +93,7 @@ struct SearchPtrs {
     uint32_t* cache_state;     // [slots] 0 empty, 1 being written, (tag << 2) | 2 published
     CacheEntry* cache_entry;   // [slots]
     Counters* counters;
-    unsigned long long* stats;         // [STAT_STRIPES][8]: the statistics fields of Counters, striped by block to spread the atomics
+    unsigned long long* stats;         // [STAT_STRIPES][16] (8..15: AZ_ADV_TIMING phase clocks): the statistics fields of Counters, striped by block to spread the atomics
 };
 
 struct SearchState {
