@@ -46,3 +46,43 @@ def reduce_metrics(sums, maxes, dist=None):
         dist.all_reduce(m, op=dist.ReduceOp.MAX)
         s, m = s.cpu(), m.cpu()
     return s.numpy(), m.numpy()
+
+
+def gather_samples(samples, dist=None, device=None, dst=0):
+    """Replay-buffer gather: every rank hands in the az_sample records of its finished games; rank `dst`
+    receives them concatenated in rank order (the order ReplayBuffer::add then sees), the others get an empty array.
+    One size exchange plus one padded gather per call; `device` is the CUDA device for the NCCL backend (None = CPU/gloo)."""
+    import torch
+
+    samples = np.ascontiguousarray(samples)
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return samples
+    world, rank = dist.get_world_size(), dist.get_rank()
+    item = samples.dtype.itemsize
+    n = torch.tensor([samples.shape[0]], dtype=torch.int64, device=device)
+    sizes = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(sizes, n)
+    counts = [int(t.item()) for t in sizes]
+    width = max(counts)
+    if width == 0:
+        return samples[:0]
+    buf = torch.zeros(width * item, dtype=torch.uint8, device=device)
+    if samples.shape[0]:
+        buf[: samples.shape[0] * item] = torch.from_numpy(samples.view(np.uint8).reshape(-1)).to(buf.device)
+    parts = [torch.empty_like(buf) for _ in range(world)] if rank == dst else None
+    dist.gather(buf, parts, dst=dst)
+    if rank != dst:
+        return samples[:0]
+    out = [parts[r][: counts[r] * item].cpu().numpy().view(samples.dtype) for r in range(world) if counts[r]]
+    return np.concatenate(out)
+
+
+def all_done(done, dist=None, device=None):
+    """True once every rank reports done (one small all-reduce)."""
+    import torch
+
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return bool(done)
+    t = torch.tensor([1 if done else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(t.item())

@@ -175,3 +175,63 @@ def run_generation(engine, replay, model, optimizer, iteration, n_games, min_rep
         out.update(trained=True, avg_policy_loss=pl, avg_value_loss=vl, learning_rate=get_cyclical_lr(iteration))
         engine.load_weights(export_weights(model))
     return out
+
+
+def run_generation_sharded(engine, replay, model, optimizer, iteration, games_per_rank, dist, device, min_replay_size=MIN_REPLAY_SIZE,
+                           waves_per_call=64, num_steps=NUM_TRAIN_STEPS, batch_size=BATCH_SIZE):
+    """run_generation over several GPUs (BASELINE config 5): every rank plays its own games (disjoint game ids,
+    no data-path collective), the finished games' steps are gathered to rank 0 in rank order and added to ITS replay
+    buffer (the single FEN-keyed buffer of memory.rs), rank 0 runs the training steps, and the new weights go back to all
+    ranks with one broadcast and an on-device import.  `replay`, `model` and `optimizer` are only used on rank 0."""
+    from . import SAMPLE_DTYPE, sharding, weight_sizes
+
+    rank = dist.get_rank() if dist is not None and dist.is_initialized() else 0
+    world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+    sizes = weight_sizes()
+    offs = sharding.weight_offsets(sizes)
+    flat = torch.zeros(int(offs[-1]), dtype=torch.float32, device=device)
+
+    def sync_weights():
+        if rank == 0:
+            flat.copy_(torch.from_numpy(sharding.flatten_weights(export_weights(model))))
+        sharding.broadcast_weights(flat, dist, src=0)
+        if flat.is_cuda:
+            torch.cuda.synchronize(flat.device)
+            engine.load_weights_dev([flat.data_ptr() + 4 * int(o) for o in offs[:-1]])
+        else:
+            engine.load_weights(sharding.split_weights(flat.numpy(), sizes))
+
+    sync_weights()
+    engine.selfplay_begin(games_per_rank, first_game_id=sharding.first_game_id(rank) + iteration * (1 << 24))
+    steps = new_unique = 0
+    done = False
+    st = None
+    while True:
+        mine = np.zeros(0, SAMPLE_DTYPE)
+        if not done:
+            st = engine.selfplay_step(waves_per_call)
+            if st.pending_samples:
+                mine = engine.selfplay_drain()
+            done = st.games_finished >= games_per_rank
+        got = sharding.gather_samples(mine, dist, device if flat.is_cuda else None)
+        if rank == 0 and len(got):
+            steps += len(got)
+            new_unique += replay.add(got)
+        if sharding.all_done(done, dist, device if flat.is_cuda else None):
+            break
+    sums, _ = sharding.reduce_metrics([float(st.simulations), float(st.evaluations)], [0.0], dist)
+    out = {"iteration": iteration, "n_ranks": world, "positions": steps, "new_unique_states": new_unique,
+           "replay_buffer_size": len(replay) if rank == 0 else 0, "simulations": int(sums[0]), "evaluations": int(sums[1]), "trained": False}
+    train = all_flag = False
+    if rank == 0:
+        train = len(replay) >= min_replay_size
+    t = torch.tensor([1 if train else 0], dtype=torch.int32, device=device if flat.is_cuda else None)
+    if world > 1:
+        dist.broadcast(t, src=0)
+    all_flag = bool(t.item())
+    if all_flag:
+        if rank == 0:
+            pl, vl = train_iteration(model, optimizer, replay, iteration, num_steps, batch_size)
+            out.update(trained=True, avg_policy_loss=pl, avg_value_loss=vl, learning_rate=get_cyclical_lr(iteration))
+        sync_weights()
+    return out

@@ -24,3 +24,22 @@ def test_two_devices_one_process():
         b, _, _ = e1.search(roots, num_simulations=16)
         assert np.array_equal(a, b)
         assert int(e1.perft(orc.startpos(), 4)[0]) == 197281
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_sharded_generation_loop_two_ranks():
+    """BASELINE config 5 over NCCL: games sharded over two ranks, samples gathered into rank 0's replay buffer, training on
+    rank 0, weights broadcast back (tools/run_generations.py under torch.distributed.run)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(29700 + os.getpid() % 200), os.path.join(root, "tools", "run_generations.py"),
+           "--games", "128", "--sims", "32", "--iterations", "2", "--min-replay", "1000", "--eval-games", "0"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]
+    lines = [json.loads(l) for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 2 and all(m["n_ranks"] == 2 and m["trained"] for m in lines)
+    assert lines[0]["positions"] > 2 * 128 * 20 and lines[0]["replay_buffer_size"] == lines[0]["new_unique_states"]

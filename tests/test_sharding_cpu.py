@@ -47,3 +47,36 @@ def test_split_weights_round_trip():
     assert all(np.array_equal(a, b) for a, b in zip(arrays, parts))
     ids = [sharding.first_game_id(r) for r in range(8)]
     assert len(set(ids)) == 8 and all(b - a == sharding.GAME_ID_STRIDE for a, b in zip(ids, ids[1:]))
+
+
+def _gather_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rounds = []
+    # round 0: both ranks contribute (3 and 5 records), round 1: only rank 1, round 2: nobody
+    for rnd, counts in enumerate(([3, 5], [0, 4], [0, 0])):
+        mine = np.zeros(counts[rank], az.SAMPLE_DTYPE)
+        mine["game_id"] = sharding.first_game_id(rank) + np.arange(counts[rank])
+        mine["ply"] = rnd
+        mine["final_value"] = rank + 0.5
+        got = sharding.gather_samples(mine, dist)
+        rounds.append(got)
+        done = sharding.all_done(rank == 1 or rnd >= 1, dist)
+        assert done == (rnd >= 1)
+    np.save(os.path.join(out_dir, f"g{rank}.npy"), np.concatenate(rounds).view(np.uint8))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sample_gather_two_rank_gloo(tmp_path):
+    """Replay samples reach rank 0 in rank order with every byte intact; other ranks receive nothing."""
+    world, port = 2, 31500 + (os.getpid() % 2000)
+    mp.spawn(_gather_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    g0 = np.load(tmp_path / "g0.npy").view(az.SAMPLE_DTYPE)
+    g1 = np.load(tmp_path / "g1.npy").view(az.SAMPLE_DTYPE)
+    assert len(g1) == 0 and len(g0) == 12
+    stride = sharding.GAME_ID_STRIDE
+    assert list(g0["game_id"]) == [0, 1, 2, stride, stride + 1, stride + 2, stride + 3, stride + 4, stride, stride + 1, stride + 2, stride + 3]
+    assert list(g0["ply"]) == [0] * 8 + [1] * 4
+    assert list(g0["final_value"][:3]) == [0.5] * 3 and list(g0["final_value"][3:]) == [1.5] * 9

@@ -4,6 +4,8 @@ self-play on the engine -> device replay buffer -> AdamW steps (PyTorch) -> weig
 evaluation match against the previous weights.  Prints one JSON line per iteration.
 
     python tools/run_generations.py --games 1024 --sims 64 --iterations 3
+    torchrun --nproc-per-node 8 tools/run_generations.py --games 1024 --sims 64 --iterations 3     # games sharded, samples
+                                                           # gathered to rank 0's buffer, weights broadcast (NCCL)
 """
 import argparse
 import json
@@ -23,31 +25,53 @@ from alphazero_chess_b200 import training as tr  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--games", type=int, default=1024)
+    ap.add_argument("--games", type=int, default=1024, help="games per GPU and iteration")
     ap.add_argument("--sims", type=int, default=64)
     ap.add_argument("--iterations", type=int, default=3)
     ap.add_argument("--eval-games", type=int, default=32)
     ap.add_argument("--min-replay", type=int, default=5000)
     args = ap.parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(42)
-    model = tr.import_weights(tr.AlphaZeroNet(), az.random_weights(seed=42)).cuda()
-    opt = tr.make_optimizer(model)
-    eng = az.Engine(max_games=args.games, num_simulations=args.sims, seed=42)
-    old = az.Engine(max_games=args.eval_games, max_batch=args.eval_games, num_simulations=args.sims, seed=42)
-    replay = az.ReplayBuffer(eng, capacity=100_000, max_batch=tr.BATCH_SIZE)
+    eng = az.Engine(device=local, max_games=args.games, num_simulations=args.sims, seed=42)
+    model = opt = replay = old = None
+    if rank == 0:
+        model = tr.import_weights(tr.AlphaZeroNet(), az.random_weights(seed=42)).to(dev)
+        opt = tr.make_optimizer(model)
+        replay = az.ReplayBuffer(eng, capacity=100_000, max_batch=tr.BATCH_SIZE)
+        old = az.Engine(device=local, max_games=args.eval_games, max_batch=args.eval_games, num_simulations=args.sims, seed=42)
     for it in range(args.iterations):
-        old.load_weights(tr.export_weights(model))
+        if rank == 0:
+            old.load_weights(tr.export_weights(model))
         t0 = time.perf_counter()
-        m = tr.run_generation(eng, replay, model, opt, it, args.games, min_replay_size=args.min_replay)
+        if world == 1:
+            m = tr.run_generation(eng, replay, model, opt, it, args.games, min_replay_size=args.min_replay)
+        else:
+            m = tr.run_generation_sharded(eng, replay, model, opt, it, args.games, dist, dev, min_replay_size=args.min_replay)
         m["generation_seconds"] = time.perf_counter() - t0
         m["positions_per_sec"] = m["positions"] / m["generation_seconds"]
-        if m["trained"] and args.eval_games:
+        if rank == 0 and m["trained"] and args.eval_games:
             t1 = time.perf_counter()
             r = ev.evaluate(ev.MctsPlayer(eng), ev.MctsPlayer(old), eng, n_games=args.eval_games, seed=it)
             m["winrate_vs_previous"] = r["winrate"]
             m["evaluation_seconds"] = time.perf_counter() - t1
-        print(json.dumps(m), flush=True)
-    replay.close(); eng.close(); old.close()
+        if world > 1:
+            dist.barrier()
+        if rank == 0:
+            print(json.dumps(m), flush=True)
+    if rank == 0:
+        replay.close(); old.close()
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
