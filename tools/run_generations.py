@@ -47,9 +47,10 @@ def main():
         model = tr.import_weights(tr.AlphaZeroNet(), az.random_weights(seed=42)).to(dev)
         opt = tr.make_optimizer(model)
         replay = az.ReplayBuffer(eng, capacity=100_000, max_batch=tr.BATCH_SIZE)
-        old = az.Engine(device=local, max_games=args.eval_games, max_batch=args.eval_games, num_simulations=args.sims, seed=42)
+        if args.eval_games:
+            old = az.Engine(device=local, max_games=args.eval_games, max_batch=args.eval_games, num_simulations=args.sims, seed=42)
     for it in range(args.iterations):
-        if rank == 0:
+        if rank == 0 and old is not None:
             old.load_weights(tr.export_weights(model))
         t0 = time.perf_counter()
         if world == 1:
@@ -68,7 +69,9 @@ def main():
         if rank == 0:
             print(json.dumps(m), flush=True)
     if rank == 0:
-        replay.close(); old.close()
+        replay.close()
+        if old is not None:
+            old.close()
     eng.close()
     if world > 1:
         dist.destroy_process_group()
