@@ -9,6 +9,7 @@
 // Error behaviour: where the reference returns Err("Illegal move") the mirror returns GameResult::Illegal / nullopt;
 // where it panics, az::Error is thrown with the engine's message.  One Engine per GPU; calls are not thread safe.
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cstdint>
 #include <memory>
@@ -229,6 +230,74 @@ inline std::pair<float, std::vector<EpisodeStep>> run_all_episodes(AlphaZero& mo
         if (n_finished >= n_games) break;  // a finished game's steps arrive together, so every episode is complete
     }
     return {(float)(evals / batches), std::move(steps)};
+}
+
+// ---- memory.rs ----------------------------------------------------------------------------------------------------
+struct TrainingBatch {          // what ReplayBuffer::sample hands to train() (training.rs:150-172), already stacked
+    std::size_t n = 0;
+    std::vector<float> planes;  // [n][19][8][8]
+    std::vector<float> policy;  // [n][4096]
+    std::vector<float> value;   // [n]
+};
+
+class ReplayBuffer {            // memory.rs:26-118, device resident
+public:
+    ReplayBuffer(Engine& e, int capacity = 100000, int max_batch = 512) : eng_(&e), max_batch_(max_batch) {
+        az_replay* h = nullptr;
+        e.check(az_replay_create(e.handle(), capacity, max_batch, &h), "az_replay_create");
+        h_.reset(h);
+    }
+    // add(step) for a batch of self-play records, in order; returns the number of new unique positions (memory.rs:41-76)
+    std::size_t add(const std::vector<az_sample>& steps) {
+        int nu = 0;
+        eng_->check(az_replay_add(h_.get(), steps.data(), (int)steps.size(), &nu), "az_replay_add");
+        return (std::size_t)nu;
+    }
+    // the finished games still in device memory (no host round trip); returns (steps, new unique positions)
+    std::pair<std::size_t, std::size_t> add_pending() {
+        int n = 0, nu = 0;
+        eng_->check(az_replay_add_pending(h_.get(), &n, &nu), "az_replay_add_pending");
+        return {(std::size_t)n, (std::size_t)nu};
+    }
+    std::size_t len() const {
+        int n = 0;
+        eng_->check(az_replay_len(h_.get(), &n), "az_replay_len");
+        return (std::size_t)n;
+    }
+    TrainingBatch sample(std::size_t batch_size, uint64_t seed) const {   // memory.rs:78-97
+        TrainingBatch b;
+        b.planes.resize(batch_size * AZ_NUM_PLANES * 64);
+        b.policy.resize(batch_size * ACTION_SPACE);
+        b.value.resize(batch_size);
+        int n = 0;
+        eng_->check(az_replay_sample(h_.get(), (int)batch_size, seed, b.planes.data(), b.policy.data(), b.value.data(), &n), "az_replay_sample");
+        b.n = (std::size_t)n;
+        b.planes.resize(b.n * AZ_NUM_PLANES * 64); b.policy.resize(b.n * ACTION_SPACE); b.value.resize(b.n);
+        return b;
+    }
+    az_replay* handle() const { return h_.get(); }
+
+private:
+    struct Deleter { void operator()(az_replay* r) const { az_replay_destroy(r); } };
+    Engine* eng_;
+    int max_batch_;
+    std::unique_ptr<az_replay, Deleter> h_;
+};
+
+// ---- chess.rs:295-318 -----------------------------------------------------------------------------------------------
+// get_best_move(pos, depth): the reference picks uniformly among the best-scoring moves with thread_rng; here the caller
+// supplies the random number (u in [0,1)) so that a match is reproducible.  None when there is no legal move.
+inline std::optional<Move> get_best_move(Engine& e, const Position& pos, uint32_t depth, double u = 0.0) {
+    std::vector<int32_t> scores(AZ_MAX_MOVES);
+    int32_t count = 0;
+    e.check(az_minimax(e.handle(), 1, &pos, (int)depth, scores.data(), &count), "az_minimax");
+    if (count == 0) return std::nullopt;
+    std::vector<Move> moves = legal_moves(e, pos);
+    int32_t best = scores[0];
+    for (int i = 1; i < count; i++) best = std::max(best, scores[i]);
+    std::vector<Move> best_moves;
+    for (int i = 0; i < count; i++) if (scores[i] == best) best_moves.push_back(moves[(std::size_t)i]);
+    return best_moves[std::min(best_moves.size() - 1, (std::size_t)(u * (double)best_moves.size()))];
 }
 
 }  // namespace az

@@ -65,5 +65,35 @@ int main(int argc, char** argv) {
     for (auto& s : steps) { vsum += s.final_value; dsum += s.search_depth; }
     std::printf("{\"test\": \"episodes\", \"steps\": %zu, \"value_sum\": %.6f, \"depth_sum\": %zu, \"avg_batch\": %.3f}\n", steps.size(), vsum,
                 dsum, avg_batch);
+
+    // memory.rs: the finished games' steps go from device memory into the replay buffer; sample a batch
+    {
+        az_config c2 = Engine::default_config();
+        c2.max_games = 8; c2.num_simulations = 24; c2.seed = 7;
+        Engine e2(c2);
+        if (az_set_evaluator_stub(e2.handle(), 1, stub_seed) != AZ_OK) return 3;
+        ReplayBuffer rb(e2, 1000, 64);
+        if (az_selfplay_begin(e2.handle(), 8, 0) != AZ_OK) return 4;
+        az_selfplay_stats st2{};
+        std::size_t added = 0, unique = 0;
+        while (st2.games_finished < 8) {
+            e2.check(az_selfplay_step(e2.handle(), 32, &st2), "az_selfplay_step");
+            if (st2.pending_samples) { auto [n, nu] = rb.add_pending(); added += n; unique += nu; }
+        }
+        TrainingBatch b = rb.sample(64, 3);
+        double psum = 0; for (float v : b.policy) psum += v;
+        std::printf("{\"test\": \"replay\", \"added\": %zu, \"unique\": %zu, \"len\": %zu, \"batch\": %zu, \"policy_sum\": %.4f}\n", added, unique,
+                    rb.len(), b.n, psum);
+    }
+
+    // chess.rs:295-318: the minimax bot finds the mate in one and reports None without legal moves
+    {
+        Position mate{}, mated{};
+        az_position_from_fen("6k1/5ppp/8/8/8/8/8/R6K w - - 0 1", &mate);
+        az_position_from_fen("R5k1/5ppp/8/8/8/8/8/7K b - - 1 1", &mated);
+        auto mv = get_best_move(eng, mate, 2);
+        std::printf("{\"test\": \"minimax\", \"from\": %d, \"to\": %d, \"none\": %d}\n", mv ? (int)(*mv & 63) : -1, mv ? (int)((*mv >> 6) & 63) : -1,
+                    (int)!get_best_move(eng, mated, 2).has_value());
+    }
     return 0;
 }

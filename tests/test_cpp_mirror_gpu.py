@@ -50,3 +50,9 @@ def test_cpp_mirror(tmp_path):
         dsum += int(ep["depth"].sum())
     assert res["episodes"]["steps"] == steps and res["episodes"]["depth_sum"] == dsum
     assert abs(res["episodes"]["value_sum"] - vsum) < 1e-4
+    # memory.rs through the mirror: every step was added, duplicates merged, a full batch of probability rows sampled
+    rp = res["replay"]
+    assert rp["added"] > 8 * 20 and 0 < rp["unique"] <= rp["added"] and rp["len"] == min(rp["unique"], 1000)
+    assert rp["batch"] == min(64, rp["len"]) and abs(rp["policy_sum"] - rp["batch"]) < 1e-2
+    # chess.rs get_best_move: Ra1-a8 mates; a mated side has no move
+    assert res["minimax"] == {"test": "minimax", "from": 0, "to": 56, "none": 1}
