@@ -4,13 +4,23 @@
 // device memory, so a generation's positions never travel to the host.
 //
 // `add` is order dependent in the reference: the running mean (old*n + new)/(n+1) is evaluated in f32 in the order the
-// steps arrive, and which position is evicted depends on the insertion order of the unique ones.  To stay bit-exact one
-// CTA applies a batch strictly in order (a step costs about a microsecond: a hash probe by one thread, then a 16 KB
-// read-modify-write of the dense policy row by 1024 threads); it runs once per generation, off the self-play hot path.
+// steps arrive, and which position is evicted depends on the insertion order of the unique ones.  To stay bit-exact AND
+// parallel the batch is applied in two phases per chunk:
+//   A  k_replay_resolve (one warp): decides for every step, in order, which slot it lands in, whether it is a new unique
+//      position (evicting the oldest when full) and the visit count it meets.  Only 64-byte keys and counters move; the
+//      warp probes the hash table for 32 steps at once and then replays their decisions in order from shared memory
+//      (a speculative hit is void if an earlier step of the window evicted that slot, a miss if an earlier step of the
+//      window brought the same position), so the DRAM/L2 latency of a probe is paid once per 32 steps.
+//   B  k_replay_apply (one CTA per touched slot): the steps that hit the same slot form a chain (prev/next links written
+//      by A); the CTA of the chain's last step walks it in order with the 16 KB policy row in registers.  Chains are
+//      independent, and a chain whose slot was evicted again later in the chunk is never touched.
+// Evicted positions leave stale entries in the open-addressing table (their slot now holds another key, so a probe just
+// walks past them); k_replay_rebuild re-inserts the live slots when too many have accumulated.
 // Sampling and batch assembly (planes, policy rows, values) are parallel over the batch.
 #include "engine.h"
 #include "mcts.h"
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -21,9 +31,17 @@ struct ReplayPtrs {
     float* policy;         // [cap][4096] running mean of improved_policy
     float* value;          // [cap]
     uint32_t* visits;      // [cap] visit_count
-    int32_t* table;        // [tsize] open addressing, linear probing with backward-shift deletion: slot or -1
-    int32_t* state;        // [4]: head (next slot, = oldest when full), len, new_unique (of the last add), reserved
+    int32_t* table;        // [tsize] open addressing, linear probing: slot or -1 (entries of evicted positions go stale)
+    int32_t* state;        // [4]: head (next slot, = oldest when full), len, new_unique (of the last add), stale entries
+    int32_t* last_touch;   // [cap] index (within the current chunk) of the last step that touched the slot, -1 = none
     int cap, tmask;
+};
+
+struct StepPtrs {          // per step of the current chunk, written by phase A, read by phase B
+    int32_t* slot;
+    uint32_t* old;         // visit count the step meets (0 = new unique position)
+    int32_t* prev;         // previous / next step of the chunk on the same slot (-1 = none)
+    int32_t* next;
 };
 
 }  // namespace azb
@@ -39,6 +57,10 @@ struct az_replay {
     float* d_val = nullptr;           // [max_batch]
     az_position* d_pos = nullptr;     // [max_batch] export/import page (lazy)
     int max_batch = 0;
+    azb::StepPtrs sp{};
+    int chunk = 0;                    // steps per phase A/B round
+    int window = 0;                   // steps probed together by phase A
+    int force_slow = 0;               // AZ_REPLAY_FORCE_SLOW=1: phase A always takes its in-order path (tests)
 };
 
 namespace azb {
@@ -55,69 +77,186 @@ __device__ __forceinline__ void replay_table_insert(const ReplayPtrs& r, u64 h, 
     while (r.table[i] >= 0) i = (i + 1) & r.tmask;
     r.table[i] = slot;
 }
-// remove the table entry pointing at `slot` (backward-shift deletion keeps probe sequences intact without tombstones)
-__device__ __forceinline__ void replay_table_erase(const ReplayPtrs& r, int slot) {
-    uint32_t i = (uint32_t)fen_key_hash(r.keys[slot]) & r.tmask;
-    while (r.table[i] != slot) i = (i + 1) & r.tmask;
-    uint32_t hole = i;
-    for (uint32_t j = (hole + 1) & r.tmask;; j = (j + 1) & r.tmask) {
-        const int s = r.table[j];
-        if (s < 0) break;
-        const uint32_t home = (uint32_t)fen_key_hash(r.keys[s]) & r.tmask;
-        // the entry at j may move into the hole if its home position does not lie cyclically in (hole, j]
-        const bool between = hole <= j ? (home > hole && home <= j) : (home > hole || home <= j);
-        if (!between) { r.table[hole] = s; hole = j; }
+
+// Phase A.  One warp; lanes < W each take one step of the window.
+__global__ void __launch_bounds__(32) k_replay_resolve(ReplayPtrs r, StepPtrs sp, const az_sample* __restrict__ samples, int n, int W,
+                                                       int force_slow) {
+    __shared__ DPos s_key[32];
+    __shared__ int s_slot[32], s_tpos[32];
+    __shared__ uint32_t s_cnt[32];
+    const int lane = threadIdx.x;
+    int head = r.state[0], len = r.state[1], new_unique = 0, stale = r.state[3];
+    for (int i0 = 0; i0 < n; i0 += W) {
+        const int m = min(W, n - i0);
+        const bool active = lane < m;
+        const int gi = i0 + lane;
+        DPos key{};
+        int s = -1, lt = -1;
+        uint32_t pos = 0, v_old = 0;
+        if (active) {   // speculative probe against the table as it stands before this window
+            key = fen_key_of(dpos_from_wire(samples[gi].position));
+            pos = (uint32_t)fen_key_hash(key) & r.tmask;
+            for (;; pos = (pos + 1) & r.tmask) {
+                s = r.table[pos];
+                if (s < 0 || fen_key_equal(r.keys[s], key)) break;
+            }
+            if (s >= 0) { v_old = r.visits[s]; lt = r.last_touch[s]; }
+            s_key[lane] = key;
+        }
+        __syncwarp();
+        // pairwise relations inside the window, by shuffling the 64-bit hashes (full keys are compared only on a hash match)
+        const u64 h = active ? fen_key_hash(key) : 0ULL;
+        const bool spec_hit = s >= 0;
+        int dup = -1, root = -1, rank = 0;   // latest / first earlier step with the same position, how many there are
+        bool last = true, tconf = false;
+        for (int l2 = 0; l2 < m; l2++) {
+            const u64 h2 = __shfl_sync(0xffffffffu, h, l2);
+            const uint32_t pos2 = __shfl_sync(0xffffffffu, pos, l2);
+            const bool hit2 = __shfl_sync(0xffffffffu, (int)spec_hit, l2) != 0;
+            if (!active || l2 == lane) continue;
+            const bool same = h2 == h && fen_key_equal(s_key[l2], key);
+            if (l2 < lane) {
+                if (same) { if (root < 0) root = l2; dup = l2; rank++; }
+                else if (!spec_hit && !hit2 && pos2 == pos) tconf = true;   // two new positions want the same empty table entry
+            } else if (same) {
+                last = false;
+            }
+        }
+        int my_slot = -1, my_prev = -1, my_tpos = -1;
+        uint32_t my_old = 0;
+        bool my_ins = false;
+        const int head0 = head;
+        // fast path: assume no speculative hit was evicted inside this window; then everything is a prefix sum
+        const bool opt_ins = active && dup < 0 && !spec_hit;
+        const unsigned ins_mask = __ballot_sync(0xffffffffu, opt_ins);
+        const int ins_before = __popc(ins_mask & ((1u << lane) - 1u));
+        int d = s - head0;
+        if (d < 0) d += r.cap;
+        const bool violated = force_slow || (active && ((dup < 0 && spec_hit && d < ins_before) || tconf));
+        if (!__any_sync(0xffffffffu, violated)) {
+            if (active && dup < 0) {
+                my_ins = opt_ins;
+                my_slot = opt_ins ? (head0 + ins_before) % r.cap : s;
+                my_old = opt_ins ? 0u : v_old;
+                my_prev = opt_ins ? -1 : lt;
+                my_tpos = opt_ins ? (int)pos : -1;
+            }
+            const int src = root >= 0 ? root : 0;
+            const int root_slot = __shfl_sync(0xffffffffu, my_slot, src);
+            const uint32_t root_old = __shfl_sync(0xffffffffu, my_old, src);
+            if (active && dup >= 0) { my_slot = root_slot; my_old = root_old + (uint32_t)rank; my_prev = i0 + dup; }
+            const int total = __popc(ins_mask), grow = min(total, r.cap - len);
+            len += grow; stale += total - grow;   // order.pop_front() for every insertion beyond capacity
+            head = (head0 + total) % r.cap;
+            new_unique += total;
+        } else {
+            // slow path (rare): the decisions strictly in order
+            int ins = 0;
+            for (int j = 0; j < m; j++) {
+                int ins_j = 0;
+                if (lane == j) {
+                    bool hit = false;
+                    if (dup >= 0) { my_slot = s_slot[dup]; my_old = s_cnt[dup]; my_prev = i0 + dup; hit = true; }
+                    else if (spec_hit && d >= ins) { my_slot = s; my_old = v_old; my_prev = lt; hit = true; }   // else: evicted earlier in this window
+                    if (!hit) {   // ReplayBuffer::add's else branch (memory.rs:60-74)
+                        my_ins = true; ins_j = 1; my_slot = head; my_old = 0; my_prev = -1;
+                        uint32_t tp = pos;
+                        bool check_global = spec_hit;    // the probe stopped on a (now void) hit, not on an empty entry
+                        if (check_global) tp = (tp + 1) & r.tmask;
+                        for (;;) {
+                            bool taken = false;
+                            for (int l2 = 0; l2 < j; l2++) taken |= s_tpos[l2] == (int)tp;
+                            if (!taken && (!check_global || r.table[tp] < 0)) break;
+                            tp = (tp + 1) & r.tmask;
+                            check_global = true;
+                        }
+                        my_tpos = (int)tp;
+                    }
+                    s_slot[j] = my_slot; s_cnt[j] = my_old + 1; s_tpos[j] = my_tpos;
+                }
+                ins_j = __shfl_sync(0xffffffffu, ins_j, j);
+                if (ins_j) {
+                    if (len >= r.cap) stale++; else len++;   // order.pop_front(): the oldest unique position goes
+                    head = head + 1 == r.cap ? 0 : head + 1;
+                    ins++; new_unique++;
+                }
+                __syncwarp();
+            }
+        }
+        if (active) {
+            sp.slot[gi] = my_slot; sp.old[gi] = my_old; sp.prev[gi] = my_prev;
+            if (my_prev >= 0) sp.next[my_prev] = gi;
+            if (my_ins) { r.keys[my_slot] = key; r.table[my_tpos] = my_slot; }
+            if (last) { r.visits[my_slot] = my_old + 1; r.last_touch[my_slot] = gi; }   // the window's last step on this position
+        }
+        __syncwarp();
     }
-    r.table[hole] = -1;
+    if (lane == 0) { r.state[0] = head; r.state[1] = len; r.state[2] += new_unique; r.state[3] = stale; }
 }
 
-// ReplayBuffer::add for a batch of EpisodeSteps, strictly in order (memory.rs:41-76)
-__global__ void __launch_bounds__(1024) k_replay_add(ReplayPtrs r, const az_sample* __restrict__ samples, int n, float sims) {
+// Phase B.  Block i acts only if step i is the last one of the chunk on its slot; it then owns that slot.
+__global__ void __launch_bounds__(256) k_replay_apply(ReplayPtrs r, StepPtrs sp, const az_sample* __restrict__ samples, float sims) {
     __shared__ float s_new[AZ_ACTION_SPACE];
-    __shared__ int s_slot, s_is_new;
-    __shared__ float s_old;
-    const int t = threadIdx.x;
-    int head = r.state[0], len = r.state[1], new_unique = 0;
-    for (int i = 0; i < n; i++) {
-        const az_sample* sm = samples + i;
-        for (int k = t; k < AZ_ACTION_SPACE; k += 1024) s_new[k] = 0.0f;
+    __shared__ int s_cur;
+    const int tail = blockIdx.x, t = threadIdx.x;
+    const int slot = sp.slot[tail];
+    if (r.last_touch[slot] != tail) return;
+    if (t == 0) {
+        int h = tail;
+        while (sp.old[h] != 0 && sp.prev[h] >= 0) h = sp.prev[h];
+        s_cur = h;
+    }
+    __syncthreads();
+    int cur = s_cur;
+    float row[16], val = 0.0f;
+    float* pol = r.policy + (size_t)slot * AZ_ACTION_SPACE;
+    if (sp.old[cur] != 0) {   // the chain continues an entry stored before this chunk
+#pragma unroll
+        for (int q = 0; q < 16; q++) row[q] = pol[t + 256 * q];
+        val = r.value[slot];
+    }
+    for (;;) {
+        const az_sample* sm = samples + cur;
+        for (int k = t; k < AZ_ACTION_SPACE; k += 256) s_new[k] = 0.0f;
         __syncthreads();
         const int nv = sm->n_visits;
-        for (int k = t; k < nv; k += 1024) s_new[sm->index[k]] = __fdiv_rn((float)sm->count[k], sims);   // improved_policy
-        if (t == 0) {
-            const DPos key = fen_key_of(dpos_from_wire(sm->position));
-            const u64 h = fen_key_hash(key);
-            int slot = replay_find(r, key, h);
-            if (slot >= 0) {
-                const float old_count = (float)r.visits[slot], total = __fadd_rn(old_count, 1.0f);
-                r.value[slot] = __fdiv_rn(__fadd_rn(__fmul_rn(r.value[slot], old_count), sm->final_value), total);
-                r.visits[slot] += 1;
-                s_is_new = 0; s_old = old_count;
-            } else {
-                slot = head;
-                if (len >= r.cap) replay_table_erase(r, slot);   // order.pop_front(): the oldest unique position goes
-                else len++;
-                r.keys[slot] = key;
-                r.value[slot] = sm->final_value;
-                r.visits[slot] = 1;
-                replay_table_insert(r, h, slot);
-                head = head + 1 == r.cap ? 0 : head + 1;
-                new_unique++;
-                s_is_new = 1; s_old = 0.0f;
-            }
-            s_slot = slot;
+        for (int k = t; k < nv; k += 256) s_new[sm->index[k]] = __fdiv_rn((float)sm->count[k], sims);   // improved_policy
+        __syncthreads();
+        const uint32_t old = sp.old[cur];
+        if (old == 0) {
+#pragma unroll
+            for (int q = 0; q < 16; q++) row[q] = s_new[t + 256 * q];
+            val = sm->final_value;
+        } else {   // memory.rs:45-54
+            const float old_count = (float)old, total = __fadd_rn(old_count, 1.0f);
+#pragma unroll
+            for (int q = 0; q < 16; q++) row[q] = __fdiv_rn(__fadd_rn(__fmul_rn(row[q], old_count), s_new[t + 256 * q]), total);
+            val = __fdiv_rn(__fadd_rn(__fmul_rn(val, old_count), sm->final_value), total);
         }
         __syncthreads();
-        float* pol = r.policy + (size_t)s_slot * AZ_ACTION_SPACE;
-        if (s_is_new) {
-            for (int k = t; k < AZ_ACTION_SPACE; k += 1024) pol[k] = s_new[k];
-        } else {
-            const float old_count = s_old, total = __fadd_rn(old_count, 1.0f);
-            for (int k = t; k < AZ_ACTION_SPACE; k += 1024) pol[k] = __fdiv_rn(__fadd_rn(__fmul_rn(pol[k], old_count), s_new[k]), total);
-        }
-        __syncthreads();
+        if (cur == tail) break;
+        cur = sp.next[cur];
     }
-    if (t == 0) { r.state[0] = head; r.state[1] = len; r.state[2] = new_unique; }
+#pragma unroll
+    for (int q = 0; q < 16; q++) pol[t + 256 * q] = row[q];
+    if (t == 0) r.value[slot] = val;
+}
+
+// Table maintenance: phase 0 clears, phase 1 re-inserts the live slots, phase 2 resets the stale counter -- each only if
+// more than cap/2 stale entries have accumulated (the table has at least 4 * cap entries).
+__global__ void __launch_bounds__(256) k_replay_rebuild(ReplayPtrs r, int phase) {
+    if (r.state[3] <= r.cap / 2) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (phase == 0) {
+        if (i <= r.tmask) r.table[i] = -1;
+    } else if (phase == 1) {
+        if (i < r.state[1]) {   // live slots are [0, len): the ring is dense
+            uint32_t pos = (uint32_t)fen_key_hash(r.keys[i]) & r.tmask;
+            while (atomicCAS(&r.table[pos], -1, i) != -1) pos = (pos + 1) & r.tmask;
+        }
+    } else if (i == 0) {
+        r.state[3] = 0;
+    }
 }
 
 // training batch assembly: planes (to_tensor of the stored position), policy rows, values for the chosen slots
@@ -174,7 +313,7 @@ __global__ void __launch_bounds__(1024) k_replay_import(ReplayPtrs r, int n, con
                                                         const float* __restrict__ value, const uint32_t* __restrict__ visits) {
     __shared__ int s_slot;
     const int t = threadIdx.x;
-    int head = r.state[0], len = r.state[1];
+    int head = r.state[0], len = r.state[1], stale = r.state[3];
     for (int i = 0; i < n; i++) {
         if (t == 0) {
             const DPos key = fen_key_of(dpos_from_wire(pos[i]));
@@ -182,7 +321,7 @@ __global__ void __launch_bounds__(1024) k_replay_import(ReplayPtrs r, int n, con
             int slot = replay_find(r, key, h);
             if (slot < 0) {
                 slot = head;
-                if (len >= r.cap) replay_table_erase(r, slot);
+                if (len >= r.cap) stale++;   // the evicted position's table entry goes stale
                 else len++;
                 r.keys[slot] = key;
                 replay_table_insert(r, h, slot);
@@ -197,7 +336,7 @@ __global__ void __launch_bounds__(1024) k_replay_import(ReplayPtrs r, int n, con
         for (int k = t; k < AZ_ACTION_SPACE; k += 1024) pol[k] = policy[(size_t)i * AZ_ACTION_SPACE + k];
         __syncthreads();
     }
-    if (t == 0) { r.state[0] = head; r.state[1] = len; }
+    if (t == 0) { r.state[0] = head; r.state[1] = len; r.state[3] = stale; }
 }
 
 static inline uint64_t host_splitmix64(uint64_t x) {
@@ -223,14 +362,23 @@ int az_replay_create(az_engine* e, int capacity, int max_batch, az_replay** out)
     ReplayPtrs& p = rp->p;
     p.cap = capacity;
     int ts = 1024;
-    while (ts < 2 * capacity) ts <<= 1;
+    while (ts < 4 * capacity + 4 * max_batch) ts <<= 1;   // live + stale entries stay below half of this (k_replay_rebuild)
     p.tmask = ts - 1;
+    rp->window = std::max(1, std::min(32, capacity / 2));   // an eviction can never reach back into the same window
+    rp->chunk = std::max(rp->window, capacity / 2);
+    if (const char* v = getenv("AZ_REPLAY_FORCE_SLOW")) rp->force_slow = atoi(v);
+    if (const char* v = getenv("AZ_REPLAY_WINDOW")) rp->window = std::max(1, std::min(rp->window, atoi(v)));
     AZ_CUDA(e, cudaMalloc(&p.keys, (size_t)capacity * sizeof(DPos)));
     AZ_CUDA(e, cudaMalloc(&p.policy, (size_t)capacity * AZ_ACTION_SPACE * sizeof(float)));
     AZ_CUDA(e, cudaMalloc(&p.value, (size_t)capacity * sizeof(float)));
     AZ_CUDA(e, cudaMalloc(&p.visits, (size_t)capacity * sizeof(uint32_t)));
     AZ_CUDA(e, cudaMalloc(&p.table, (size_t)ts * sizeof(int32_t)));
     AZ_CUDA(e, cudaMalloc(&p.state, 4 * sizeof(int32_t)));
+    AZ_CUDA(e, cudaMalloc(&p.last_touch, (size_t)capacity * sizeof(int32_t)));
+    AZ_CUDA(e, cudaMalloc(&rp->sp.slot, (size_t)rp->chunk * sizeof(int32_t)));
+    AZ_CUDA(e, cudaMalloc(&rp->sp.old, (size_t)rp->chunk * sizeof(uint32_t)));
+    AZ_CUDA(e, cudaMalloc(&rp->sp.prev, (size_t)rp->chunk * sizeof(int32_t)));
+    AZ_CUDA(e, cudaMalloc(&rp->sp.next, (size_t)rp->chunk * sizeof(int32_t)));
     AZ_CUDA(e, cudaMemset(p.table, 0xFF, (size_t)ts * sizeof(int32_t)));
     AZ_CUDA(e, cudaMemset(p.state, 0, 4 * sizeof(int32_t)));
     AZ_CUDA(e, cudaMalloc(&rp->d_idx, (size_t)max_batch * sizeof(int32_t)));
@@ -245,16 +393,36 @@ void az_replay_destroy(az_replay* rp) {
     cudaSetDevice(rp->eng->cfg.device);
     cudaStreamSynchronize(rp->eng->stream);
     cudaFree(rp->p.keys); cudaFree(rp->p.policy); cudaFree(rp->p.value); cudaFree(rp->p.visits); cudaFree(rp->p.table);
+    cudaFree(rp->p.last_touch); cudaFree(rp->sp.slot); cudaFree(rp->sp.old); cudaFree(rp->sp.prev); cudaFree(rp->sp.next);
     cudaFree(rp->p.state); cudaFree(rp->d_staging); cudaFree(rp->d_idx); cudaFree(rp->d_planes); cudaFree(rp->d_pol); cudaFree(rp->d_val); cudaFree(rp->d_pos);
     delete rp;
 }
 
+// re-insert the live slots into a cleared table once enough stale entries have piled up (the kernels decide on the device)
+static int replay_maintain(az_replay* rp) {
+    az_engine* e = rp->eng;
+    const int ts = rp->p.tmask + 1;
+    e->n_launches += 3;
+    k_replay_rebuild<<<(ts + 255) / 256, 256, 0, e->stream>>>(rp->p, 0);
+    k_replay_rebuild<<<(rp->p.cap + 255) / 256, 256, 0, e->stream>>>(rp->p, 1);
+    k_replay_rebuild<<<1, 32, 0, e->stream>>>(rp->p, 2);
+    AZ_CUDA(e, cudaGetLastError());
+    return 0;
+}
+
 static int replay_add_dev(az_replay* rp, const az_sample* d_samples, int n, int* new_unique_out) {
     az_engine* e = rp->eng;
-    if (n > 0) {
-        e->n_launches++;
-        k_replay_add<<<1, 1024, 0, e->stream>>>(rp->p, d_samples, n, (float)e->cfg.num_simulations);
+    AZ_CUDA(e, cudaMemsetAsync(rp->p.state + 2, 0, sizeof(int32_t), e->stream));   // new_unique of this call
+    for (int off = 0; off < n; off += rp->chunk) {
+        const int m = std::min(rp->chunk, n - off);
+        AZ_CUDA(e, cudaMemsetAsync(rp->p.last_touch, 0xFF, (size_t)rp->p.cap * sizeof(int32_t), e->stream));
+        AZ_CUDA(e, cudaMemsetAsync(rp->sp.next, 0xFF, (size_t)m * sizeof(int32_t), e->stream));
+        e->n_launches += 2;
+        k_replay_resolve<<<1, 32, 0, e->stream>>>(rp->p, rp->sp, d_samples + off, m, rp->window, rp->force_slow);
+        k_replay_apply<<<m, 256, 0, e->stream>>>(rp->p, rp->sp, d_samples + off, (float)e->cfg.num_simulations);
         AZ_CUDA(e, cudaGetLastError());
+        int r = replay_maintain(rp);
+        if (r) return r;
     }
     int32_t st[4] = {0, 0, 0, 0};
     AZ_CUDA(e, cudaMemcpyAsync(st, rp->p.state, sizeof st, cudaMemcpyDeviceToHost, e->stream));
@@ -372,6 +540,7 @@ int az_replay_import(az_replay* rp, int n, const az_position* pos, const float* 
     e->n_launches++;
     k_replay_import<<<1, 1024, 0, e->stream>>>(rp->p, n, rp->d_pos, rp->d_pol, rp->d_val, reinterpret_cast<const uint32_t*>(rp->d_idx));
     AZ_CUDA(e, cudaGetLastError());
+    if (int r = replay_maintain(rp)) return r;
     AZ_CUDA(e, cudaStreamSynchronize(e->stream));
     return AZ_OK;
 }

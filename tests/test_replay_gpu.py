@@ -149,3 +149,17 @@ def test_save_load_round_trip(played, capacity, tmp_path):
     assert visits.min() >= 1 and np.allclose(policy.sum(1), 1.0, atol=1e-3)
     a.close()
     b.close()
+
+
+@pytest.mark.parametrize("env", [{"AZ_REPLAY_FORCE_SLOW": "1"}, {"AZ_REPLAY_WINDOW": "1"}, {"AZ_REPLAY_WINDOW": "5"}])
+def test_add_paths_agree_with_oracle(env):
+    """Phase A of az_replay_add has a prefix-sum fast path and an in-order path for windows in which a speculative probe was
+    overtaken; both, and odd window sizes, must reproduce the oracle (the parity test re-run in a subprocess with the
+    path forced)."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_replay_gpu.py"), "-q", "-x", "-k", "test_add_matches_oracle"],
+                         env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:]

@@ -101,7 +101,7 @@ def main():
     nu = rb.add(samples)
     dt = time.perf_counter() - t0
     print(json.dumps({"bench": "replay_add", "steps": int(len(samples)), "new_unique": int(nu), "seconds": dt, "steps_per_sec": len(samples) / dt,
-                      "note": "az_replay_add: H2D of 1120 B/step + one CTA applying the steps in order (bit-exact running means)"}))
+                      "note": "az_replay_add: H2D of 1120 B/step + in-order resolve by one warp (32 probes at a time) + one CTA per touched slot (bit-exact running means)"}))
     rb.sample(512, seed=0)
     t0 = time.perf_counter()
     for k in range(50):
