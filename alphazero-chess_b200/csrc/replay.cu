@@ -96,9 +96,10 @@ __global__ void __launch_bounds__(32) k_replay_resolve(ReplayPtrs r, StepPtrs sp
         if (active) {   // speculative probe against the table as it stands before this window
             key = fen_key_of(dpos_from_wire(samples[gi].position));
             pos = (uint32_t)fen_key_hash(key) & r.tmask;
-            for (;; pos = (pos + 1) & r.tmask) {
+            for (int guard = 0;; pos = (pos + 1) & r.tmask) {
                 s = r.table[pos];
                 if (s < 0 || fen_key_equal(r.keys[s], key)) break;
+                if (++guard > r.tmask) __trap();   // the table always keeps empty entries (k_replay_rebuild)
             }
             if (s >= 0) { v_old = r.visits[s]; lt = r.last_touch[s]; }
             s_key[lane] = key;
@@ -195,20 +196,24 @@ __global__ void __launch_bounds__(32) k_replay_resolve(ReplayPtrs r, StepPtrs sp
 }
 
 // Phase B.  Block i acts only if step i is the last one of the chunk on its slot; it then owns that slot.
-__global__ void __launch_bounds__(256) k_replay_apply(ReplayPtrs r, StepPtrs sp, const az_sample* __restrict__ samples, float sims) {
+__global__ void __launch_bounds__(256) k_replay_apply(ReplayPtrs r, StepPtrs sp, const az_sample* __restrict__ samples, int n, float sims) {
     __shared__ float s_new[AZ_ACTION_SPACE];
     __shared__ int s_cur;
     const int tail = blockIdx.x, t = threadIdx.x;
     const int slot = sp.slot[tail];
     if (r.last_touch[slot] != tail) return;
     if (t == 0) {
-        int h = tail;
-        while (sp.old[h] != 0 && sp.prev[h] >= 0) h = sp.prev[h];
+        int h = tail, guard = 0;
+        while (sp.old[h] != 0 && sp.prev[h] >= 0) {
+            h = sp.prev[h];
+            if (++guard > n) __trap();   // a chain cannot be longer than the chunk: broken links must not hang the device
+        }
         s_cur = h;
     }
     __syncthreads();
     int cur = s_cur;
     float row[16], val = 0.0f;
+    int steps = 0;
     float* pol = r.policy + (size_t)slot * AZ_ACTION_SPACE;
     if (sp.old[cur] != 0) {   // the chain continues an entry stored before this chunk
 #pragma unroll
@@ -236,6 +241,7 @@ __global__ void __launch_bounds__(256) k_replay_apply(ReplayPtrs r, StepPtrs sp,
         __syncthreads();
         if (cur == tail) break;
         cur = sp.next[cur];
+        if (cur < 0 || cur >= n || ++steps > n) __trap();
     }
 #pragma unroll
     for (int q = 0; q < 16; q++) pol[t + 256 * q] = row[q];
@@ -419,7 +425,7 @@ static int replay_add_dev(az_replay* rp, const az_sample* d_samples, int n, int*
         AZ_CUDA(e, cudaMemsetAsync(rp->sp.next, 0xFF, (size_t)m * sizeof(int32_t), e->stream));
         e->n_launches += 2;
         k_replay_resolve<<<1, 32, 0, e->stream>>>(rp->p, rp->sp, d_samples + off, m, rp->window, rp->force_slow);
-        k_replay_apply<<<m, 256, 0, e->stream>>>(rp->p, rp->sp, d_samples + off, (float)e->cfg.num_simulations);
+        k_replay_apply<<<m, 256, 0, e->stream>>>(rp->p, rp->sp, d_samples + off, m, (float)e->cfg.num_simulations);
         AZ_CUDA(e, cudaGetLastError());
         int r = replay_maintain(rp);
         if (r) return r;
