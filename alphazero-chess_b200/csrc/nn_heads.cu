@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(512, 1)
 k_heads_mma(const __nv_bfloat16* __restrict__ tower, const __nv_bfloat16* __restrict__ w40, const float* __restrict__ b40,
             const __nv_bfloat16* __restrict__ wp2, const float* __restrict__ bp2, const __nv_bfloat16* __restrict__ wl1t,
             const float* __restrict__ bl1, const float* __restrict__ wl2, const float* __restrict__ bl2, float* __restrict__ policy_out,
-            float* __restrict__ value_out, const int* __restrict__ n_dev, int n_static, HeadScatter sc) {
+            float* __restrict__ value_out, const int* __restrict__ n_dev, int n_static, HeadScatter sc, int bpi) {
     extern __shared__ float s_exp_all[];  // [8 boards][64 co][HEXP_PITCH]: exp(logit - max) of the board in flight
     __shared__ __align__(16) __nv_bfloat16 s_w40[40 * HW40_PITCH];
     __shared__ __align__(16) __nv_bfloat16 s_w2[64 * HW2_PITCH];
@@ -54,9 +54,11 @@ k_heads_mma(const __nv_bfloat16* __restrict__ tower, const __nv_bfloat16* __rest
     if (t < 64) s_b2[t] = bp2[t];
     __syncthreads();
 
-    for (int base = blockIdx.x * 8; base < n; base += gridDim.x * 8) {
+    // bpi = boards per block and round (<= 8): the host picks it so that the last round is full (4096 boards on 148 blocks:
+    // 4 rounds of 7 instead of 3.46 -> 4 rounds of 8)
+    for (int base = blockIdx.x * bpi; base < n; base += gridDim.x * bpi) {
         const int b = base + bs;
-        const bool active = b < n;
+        const bool active = bs < bpi && b < n;
         if (active) {
             // ---------------- stage 1: D1[square][40] for this warp's 32 squares
             float d1[2][5][4];
@@ -230,7 +232,7 @@ k_heads_mma(const __nv_bfloat16* __restrict__ tower, const __nv_bfloat16* __rest
             if (lane == 0) s_vsum[warp] = part;
         }
         __syncthreads();
-        if (t < 8 && base + t < n) value_out[base + t] = tanhf(bl2[0] + s_vsum[2 * t] + s_vsum[2 * t + 1]);
+        if (t < bpi && base + t < n) value_out[base + t] = tanhf(bl2[0] + s_vsum[2 * t] + s_vsum[2 * t + 1]);
     }
 }
 
@@ -239,13 +241,21 @@ int launch_heads_mma(az_engine* e, const __nv_bfloat16* tower, const int* n_dev,
     NetWeights* w = e->net;
     const int n_max = n_dev ? w->max_boards : n_static;
     if (n_max <= 0) return 0;
-    const int grid = std::min((n_max + 7) / 8, e->sm_count);
+    int bpi = 8;
+    if (n_max > 8 * e->sm_count) {   // several rounds per block: fewest board-slots (rounds x bpi) that cover the batch
+        int best = 1 << 30;
+        for (int c = 8; c >= 5; c--) {
+            const int rounds = (n_max + e->sm_count * c - 1) / (e->sm_count * c);
+            if (rounds * c < best) { best = rounds * c; bpi = c; }
+        }
+    }
+    const int grid = std::min((n_max + bpi - 1) / bpi, e->sm_count);
     static PerDeviceOnce once;
     if (once.first()) cudaFuncSetAttribute(k_heads_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, HEADS_DYN_SMEM);
     HeadScatter sc{nullptr, nullptr, nullptr, nullptr};
     if (scatter) sc = *scatter;
     k_heads_mma<<<grid, 512, HEADS_DYN_SMEM, e->stream>>>(tower, w->h_w40, w->f_b40, w->h_wp2, w->f_bp2, w->h_wl1t, w->f_bl1, w->f_wl2, w->f_bl2,
-                                             policy_out, value_out, n_dev, n_static, sc);
+                                             policy_out, value_out, n_dev, n_static, sc, bpi);
     return check_cuda(e, cudaGetLastError(), "k_heads_mma");
 }
 
