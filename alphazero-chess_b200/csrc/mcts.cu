@@ -921,11 +921,15 @@ static int run_wave(az_engine* e, SearchState* st) {
     }
     e->n_launches++;
     static int minb = -1;
-    if (minb < 0) { const char* v = getenv("AZ_ADV_MINB"); minb = v ? atoi(v) : 4; }  // measured per wave of 4096 games: 3 -> 95 us, 4 -> 81 us (128 registers, no spills), 5 -> 81 us, 6 -> 84 us
+    if (minb < 0) { const char* v = getenv("AZ_ADV_MINB"); minb = v ? atoi(v) : 7; }
+    // groups of four warps per SM (register bound): 3 -> 162 registers, 4 -> 128, 5 -> 96, 6 -> 80, 7 -> 72 with 216 bytes of
+    // spills.  With 7, all 4096 games of a wave are resident at once (148 SMs x 28 warps) and the kernel is one round of
+    // latency chains instead of two: measured per wave 4 -> 67.6 us, 5 -> 68.5, 6 -> 69.6, 7 -> 54.7.
     switch (minb) {
         case 4: k_advance<4><<<blocks, WARPS * 32, 0, e->stream>>>(st->prm, st->ptr); break;
         case 5: k_advance<5><<<blocks, WARPS * 32, 0, e->stream>>>(st->prm, st->ptr); break;
         case 6: k_advance<6><<<blocks, WARPS * 32, 0, e->stream>>>(st->prm, st->ptr); break;
+        case 7: k_advance<7><<<blocks, WARPS * 32, 0, e->stream>>>(st->prm, st->ptr); break;
         default: k_advance<3><<<blocks, WARPS * 32, 0, e->stream>>>(st->prm, st->ptr); break;
     }
     AZ_CUDA(e, cudaGetLastError());

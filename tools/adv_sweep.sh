@@ -1,6 +1,5 @@
 #!/bin/bash
-# k_advance experiments (profiles/r1_conv_ablation.md "later experiments"): simulations a game may finish per wave
-for it in 8 1 2; do
-  AZ_ADV_MAX_ITERS=$it timeout 120 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/b_it$it.json 2>> gpurun_out/b_it.err
+# k_advance experiments (profiles/r1_conv_ablation.md "later experiments"): register bound / resident warps per SM
+for mb in 4 5 6 7; do
+  AZ_ADV_MINB=$mb timeout 120 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/b_mb$mb.json 2>> gpurun_out/b_mb.err
 done
-AZ_ADV_MAX_ITERS=1 timeout 300 python -m pytest tests/test_search_gpu.py tests/test_selfplay_gpu.py -x -q 2>&1 | tail -3
