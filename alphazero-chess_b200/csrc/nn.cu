@@ -357,8 +357,6 @@ int net_forward_bf16(az_engine* e, const int* n_dev, int n_static, float* policy
     if (sample) {
         cudaEventCreate(&ps.a); cudaEventCreate(&ps.b);
         ps.slot = e->prof_slot; e->prof_slot = (e->prof_slot + 1) % 4096;
-        if (n_dev) cudaMemcpyAsync(&e->prof_counts_host[ps.slot], n_dev, sizeof(int), cudaMemcpyDeviceToHost, e->stream);
-        else e->prof_counts_host[ps.slot] = n_static;
         cudaEventRecord(ps.a, e->stream);
     }
     int x = 0;  // buffer holding the block input
@@ -382,7 +380,13 @@ int net_forward_bf16(az_engine* e, const int* n_dev, int n_static, float* policy
     }
     if (sample) cudaEventRecord(ps.b, e->stream);
     const int hr = launch_heads_mma(e, w->a_buf[x], n_dev, n_static, policy_out, value_out, scatter);
-    if (sample) { cudaEventCreate(&ps.h1); cudaEventRecord(ps.h1, e->stream); e->prof_pending.push_back(ps); }
+    if (sample) {
+        cudaEventCreate(&ps.h1); cudaEventRecord(ps.h1, e->stream);
+        // the batch size of this wave, copied after the last bracketed phase so that the copy is not timed as part of one
+        if (n_dev) cudaMemcpyAsync(&e->prof_counts_host[ps.slot], n_dev, sizeof(int), cudaMemcpyDeviceToHost, e->stream);
+        else e->prof_counts_host[ps.slot] = n_static;
+        e->prof_pending.push_back(ps);
+    }
     return hr;
 }
 
