@@ -407,7 +407,8 @@ class ReplayBuffer:
 
 class Profile(ctypes.Structure):
     _fields_ = [("tower_ms", ctypes.c_double), ("tower_samples", ctypes.c_uint64), ("tower_boards", ctypes.c_uint64),
-                ("input_ms", ctypes.c_double), ("heads_ms", ctypes.c_double), ("advance_ms", ctypes.c_double)]
+                ("input_ms", ctypes.c_double), ("heads_ms", ctypes.c_double), ("advance_ms", ctypes.c_double),
+                ("tower_launches", ctypes.c_uint64)]
 
 
 def _engine_measurement_methods():

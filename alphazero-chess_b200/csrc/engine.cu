@@ -197,8 +197,9 @@ int az_profile_read(az_engine* e, az_profile* out) {
     }
     e->prof_pending.clear();
     out->tower_ms = e->prof_ms; out->tower_samples = e->prof_samples; out->tower_boards = e->prof_boards;
+    out->tower_launches = e->prof_launches;
     out->input_ms = e->prof_input_ms; out->heads_ms = e->prof_heads_ms; out->advance_ms = e->prof_adv_ms;
-    e->prof_ms = 0; e->prof_samples = 0; e->prof_boards = 0; e->prof_input_ms = 0; e->prof_heads_ms = 0; e->prof_adv_ms = 0;
+    e->prof_ms = 0; e->prof_samples = 0; e->prof_boards = 0; e->prof_launches = 0; e->prof_input_ms = 0; e->prof_heads_ms = 0; e->prof_adv_ms = 0;
     return AZ_OK;
 }
 uint64_t az_launch_count(const az_engine* e) { return e ? e->n_launches : 0; }

@@ -64,7 +64,7 @@ struct az_engine {
     int* prof_counts_host = nullptr;   // pinned ring of batch sizes
     int prof_slot = 0;
     double prof_ms = 0.0, prof_input_ms = 0.0, prof_heads_ms = 0.0, prof_adv_ms = 0.0;
-    uint64_t prof_samples = 0, prof_boards = 0;
+    uint64_t prof_samples = 0, prof_boards = 0, prof_launches = 0;
 
     azb::NetWeights* net = nullptr;
     azb::SearchState* search = nullptr;

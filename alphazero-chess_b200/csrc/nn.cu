@@ -362,13 +362,29 @@ int net_forward_bf16(az_engine* e, const int* n_dev, int n_static, float* policy
     int x = 0;  // buffer holding the block input
     if (fused) {
         void* act[3] = {w->a_buf[0], w->a_buf[1], w->a_buf[2]};
-        e->n_launches += 1;
-        r = tc_tower_launch(e->stream, w->d_maps, w->f_b_tower, act, n_dev, n_static, 20, fused >= 2, grid);
-        if (r) return set_err(e, AZ_ERR_CUDA, "tower launch failed");
-        x = 2;  // ten blocks rotate the three buffers: (0 + 10 * 2) % 3
+        // The tower runs over consecutive board ranges whose two activation buffers (block input/output in place, conv1
+        // output) stay resident in the 126 MB L2: a range of 2048 boards is 2 x 33.5 MB, and 512 tiles on 74 CTA pairs
+        // are 7 rounds, the same 98.8 % fill as the whole batch.  At 4096 boards two launches take 1148 us against
+        // 1250 us for one launch whose 134 MB stream through HBM in every layer (and the clocks under the power cap
+        // are higher).  AZ_TOWER_SPLIT overrides the number of ranges.
+        static int split = -1;
+        if (split < 0) { const char* v = getenv("AZ_TOWER_SPLIT"); split = v ? std::max(1, atoi(v)) : 0; }
+        const int cap_tiles = ((n_dev ? w->max_boards : n_static) + 3) / 4;
+        const int pairs = grid / 2;
+        int n_ranges = split > 0 ? split : (cap_tiles + 7 * pairs - 1) / (7 * pairs);   // at most 7 rounds (2072 boards) per range
+        if (split == 0 && cap_tiles < 6 * pairs * n_ranges) n_ranges = std::max(1, cap_tiles / (6 * pairs));  // >= 6 tiles per pair (lazy publication)
+        const int per = (cap_tiles + n_ranges - 1) / n_ranges;
+        for (int lo = 0; lo < cap_tiles; lo += per) {
+            e->n_launches += 1;
+            if (sample) e->prof_launches += 1;
+            r = tc_tower_launch(e->stream, w->d_maps, w->f_b_tower, act, n_dev, n_static, 20, fused >= 2, grid, lo, lo + per);
+            if (r) return set_err(e, AZ_ERR_CUDA, "tower launch failed");
+        }
+        x = 0;  // the fused tower works in place: block input and block output share a_buf[0], a_buf[1] holds conv1's output
     }
     for (int blk = 0; blk < (fused ? 0 : 10); blk++) {
         e->n_launches += 2;
+        if (sample) e->prof_launches += 2;
         const int y = (x + 1) % 3, z = (x + 2) % 3;
         r = tc_conv3x3_launch(e->stream, &w->map_a[x], &w->map_w_tower[2 * blk], 128, w->f_b_tower + (2 * blk) * 128, nullptr, w->a_buf[y],
                               n_dev, n_static, 1, grid);

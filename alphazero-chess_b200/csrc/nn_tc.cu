@@ -240,6 +240,7 @@ struct TowerParams {
     const int* n_boards_ptr;
     int n_boards_static;
     int n_layers;              // 20
+    int tile_lo, tile_hi;      // this launch covers tiles [tile_lo, min(all tiles, tile_hi)) (a tile = 4 boards)
     int stem;                  // 1: run the input convolution (agent.rs:117; 64 padded channels -> act[0]) as a first layer
 };
 
@@ -266,8 +267,8 @@ conv_tower_kernel(const TowerParams prm) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const int n_boards = prm.n_boards_ptr ? *prm.n_boards_ptr : prm.n_boards_static;
-    const int n_tiles = (n_boards + 3) >> 2;
-    const int first_tile = blockIdx.x >> 1, tile_step = gridDim.x >> 1;
+    const int n_tiles = min((n_boards + 3) >> 2, prm.tile_hi);
+    const int first_tile = prm.tile_lo + (blockIdx.x >> 1), tile_step = gridDim.x >> 1;
     const int T = first_tile < n_tiles ? (n_tiles - first_tile + tile_step - 1) / tile_step : 0;  // tiles of this pair
     const int stem = prm.stem;
     const int NL = prm.n_layers + stem;  // loop index L; tower layer = L - stem (-1 is the input convolution: one channel half)
@@ -290,11 +291,10 @@ conv_tower_kernel(const TowerParams prm) {
     if (warp == 0) {
         // ---------------------------------------------------------------- TMA producer (both CTAs)
         int stage = 0; uint32_t phase = 0;
-        int x = 0;
         for (int L = 0; L < NL; L++) {
             const int layer = L - stem;
             const int blk_second = layer >= 0 ? (layer & 1) : 0;
-            const int in_buf = blk_second ? (x + 1) % 3 : x;
+            const int in_buf = blk_second ? 1 : 0;   // block input in act[0], conv1 output in act[1], conv2 back into act[0]
             const CUtensorMap* in_map = layer >= 0 ? &prm.maps[in_buf] : &prm.maps[23];
             const CUtensorMap* w_map = layer >= 0 ? &prm.maps[3 + layer] : &prm.maps[24];
             const int halves = layer >= 0 ? 2 : 1;
@@ -333,7 +333,6 @@ conv_tower_kernel(const TowerParams prm) {
                         if (++stage == NS) { stage = 0; phase ^= 1; }
                     }
             }
-            if (blk_second) x = (x + 2) % 3;
         }
     } else if (warp == 1) {
         if (rank == 0) {
@@ -385,17 +384,20 @@ conv_tower_kernel(const TowerParams prm) {
         const int ch = (warp - 2) >> 2;
         const int row = q * 32 + lane;
         const int h = row >> 4, b = (row >> 3) & 1, w = row & 7;
-        int lt = 0, x = 0;
+        int lt = 0;
         uint32_t done = 0;
         // completion is published lazily (after the next accumulator wait) and only every 4th tile when the pair has
-        // enough tiles in flight; the producer needs tile i of this layer only T tiles later (T >= 8 leaves slack >= 4)
-        const bool lazy = T >= 8;
+        // enough tiles in flight; the producer needs tile i of this layer only T tiles later (T >= 6: the published count lags by at most 3 tiles and the producer runs about 2 tiles ahead of the epilogue)
+        const bool lazy = T >= 6;
         for (int L = 0; L < NL; L++) {
             const int layer = L - stem;
             const int blk_second = layer >= 0 ? (layer & 1) : 0;
-            const int out_buf = layer < 0 ? 0 : blk_second ? (x + 2) % 3 : (x + 1) % 3;
+            const int out_buf = layer < 0 ? 0 : blk_second ? 0 : 1;
             __nv_bfloat16* out = prm.act[out_buf];
-            const __nv_bfloat16* residual = blk_second ? prm.act[x] : nullptr;
+            // the residual of tile t is read (into registers, before the accumulator wait) by the same warp that then overwrites
+            // tile t, and no other tile's convolution reads these boards: the block output can replace the block input in place,
+            // which keeps the tower's footprint at two activation buffers (L2 residency)
+            const __nv_bfloat16* residual = blk_second ? prm.act[0] : nullptr;
             // the 8 epilogue warps switch layers together: whoever arrives refills the buffer last used two layers ago
             if (threadIdx.x - 64 < 128)
                 bias_s[(L & 1) * 128 + threadIdx.x - 64] = prm.bias[(layer >= 0 ? layer : prm.n_layers) * 128 + threadIdx.x - 64];
@@ -464,7 +466,6 @@ conv_tower_kernel(const TowerParams prm) {
                     if (lane == 0) { __threadfence(); epi_done[warp - 2] = done; }
                 }
             }
-            if (blk_second) x = (x + 2) % 3;
         }
     }
     tc_fence_before();
@@ -474,7 +475,7 @@ conv_tower_kernel(const TowerParams prm) {
 }
 
 int tc_tower_launch(cudaStream_t stream, const CUtensorMap* maps_dev, const float* bias, void* const* act, const int* n_boards_dev,
-                    int n_boards_static, int n_layers, int stem, int grid) {
+                    int n_boards_static, int n_layers, int stem, int grid, int tile_lo, int tile_hi) {
     static PerDeviceOnce once;
     if (once.first() &&
         cudaFuncSetAttribute(conv_tower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<2>::kTotal) != cudaSuccess)
@@ -485,6 +486,7 @@ int tc_tower_launch(cudaStream_t stream, const CUtensorMap* maps_dev, const floa
     p.maps = maps_dev; p.bias = bias;
     for (int i = 0; i < 3; i++) p.act[i] = (__nv_bfloat16*)act[i];
     p.n_boards_ptr = n_boards_dev; p.n_boards_static = n_boards_static; p.n_layers = n_layers; p.stem = stem ? 1 : 0;
+    p.tile_lo = tile_lo; p.tile_hi = tile_hi;
     conv_tower_kernel<<<grid, kThreads2, ConvSmem<2>::kTotal, stream>>>(p);
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }

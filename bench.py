@@ -249,12 +249,15 @@ def run_ours(args, rank, world, local_rank):
         if prof.tower_samples:
             mode = int(os.environ.get("AZ_TOWER_FUSED", "1"))
             fused = mode != 0
-            n_launch = 1 if fused else 20  # the 20 tower convolutions run as one persistent launch or as 20 launches
-            launch_ms = prof.tower_ms / (prof.tower_samples * n_launch)
-            boards = prof.tower_boards / prof.tower_samples
-            # algorithmic flops: 20 x (3x3, 128->128) per board, plus the input convolution's 19 real channels when it is
-            # fused into the same launch (mode 2; the 45 zero-padded channels the MMA also multiplies are not counted)
-            flops_per_launch = (az.FLOPS_PER_TOWER_CONV * (20 // n_launch) + (az.FLOPS_PER_INPUT_CONV if mode >= 2 else 0)) * boards
+            # fused: one persistent launch runs all 20 convolutions for an L2-sized range of boards (two ranges at 4096 boards);
+            # unfused: 20 launches over all boards.  Per launch: its duration, its boards and its algorithmic flops.
+            n_launches = max(int(prof.tower_launches), 1)
+            launch_ms = prof.tower_ms / n_launches
+            layers = 20 if fused else 1
+            boards = prof.tower_boards * (20 // layers) / n_launches
+            # algorithmic flops: 3x3 128->128 convolutions, plus the input convolution's 19 real channels when it is fused into the
+            # same launch (mode 2; the 45 zero-padded channels the MMA also multiplies are not counted)
+            flops_per_launch = (az.FLOPS_PER_TOWER_CONV * layers + (az.FLOPS_PER_INPUT_CONV if mode >= 2 else 0)) * boards
             achieved = flops_per_launch / (launch_ms * 1e-3) / 1e12
             traffic = None
             tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
@@ -263,12 +266,12 @@ def run_ours(args, rank, world, local_rank):
                     traffic = json.load(f).get("conv_tower_kernel_dram_bytes_per_launch" if fused else "conv3x3_tc2_dram_bytes_per_launch")
             kname = ("conv_tower_kernel (input convolution + the 20 3x3 128->128 convolutions of the tower in one persistent tcgen05 "
                      "cta_group::2 launch)" if mode >= 2 else
-                     "conv_tower_kernel (the 20 3x3 128->128 convolutions of the tower in one persistent tcgen05 cta_group::2 launch)"
+                     "conv_tower_kernel (the 20 3x3 128->128 convolutions of the tower for an L2-sized range of boards in one persistent tcgen05 cta_group::2 launch)"
                      if fused else "conv3x3_tc2_kernel<2> (tcgen05 cta_group::2 3x3 128->128 convolution, 20 of 23 launches per wave)")
             roof = {"bound": "tensor", "kernel": kname,
                     "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
                     "peak_source": f"{peak_kind} bf16_tflops_sustained", "us_per_launch": launch_ms * 1e3, "boards_per_launch": boards,
-                    "flops_per_launch": flops_per_launch}
+                    "flops_per_launch": flops_per_launch, "launches_per_wave": n_launches / prof.tower_samples}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
@@ -284,7 +287,7 @@ def run_ours(args, rank, world, local_rank):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic (random-init 10x128 net, seed 42; games from the start position with Dirichlet noise)",
             "config": {"workload": f"{G} concurrent games x {S} sims/move per GPU (BASELINE configs[2]; x N GPUs = configs[3] at N=8)",
                        "games_per_gpu": G, "sims_per_move": S, "step": "one ply for every game (sims waves)",
-                       "l2": "working set (tree pools + 3 x 64 MiB activation buffers per 4096 boards) exceeds the 126 MB L2; no flush needed",
+                       "l2": "a step streams the tree pools (2.3 GB per 4096 games), planes and priors through HBM: larger than the 126 MB L2, no flush needed; inside a wave the tower keeps each 2048-board range of activations L2-resident by design",
                        "parallelism": f"games sharded {world} x {G}, no data-path collective"},
             "positions_per_sec": positions / (ms_all * 1e-3),
             "nn_evals_per_sec": evals / (ms_all * 1e-3),

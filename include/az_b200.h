@@ -202,6 +202,7 @@ typedef struct az_profile {
     double input_ms;        /* input convolution of the sampled forwards */
     double heads_ms;        /* policy/value heads of the sampled forwards */
     double advance_ms;      /* search kernel (k_advance) that produced the sampled batches (0 outside search/self-play) */
+    uint64_t tower_launches; /* tower kernel launches inside the sampled forwards (one per L2-sized board range) */
 } az_profile;
 int az_timer_start(az_engine* eng);
 int az_timer_stop(az_engine* eng, float* ms_out);
