@@ -1,11 +1,11 @@
 #!/bin/bash
-# Round-end multi-GPU evidence on one 8-GPU box: 2-GPU tests, the sharded generation loop and bench.py at N = 4 and 8.
-timeout 600 python -m pytest tests/test_multi_device_gpu.py -x -q 2>&1 | tail -3
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29621 \
-  tools/run_generations.py --games 1024 --sims 64 --iterations 2 --min-replay 5000 --eval-games 32 > gpurun_out/gen8.log 2> gpurun_out/gen8.err
-tail -2 gpurun_out/gen8.log | cut -c1-600
-for n in 4 8; do
-  timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29630 + n)) \
-    bench.py --gpus $n --steps 3 --warmup 3 > gpurun_out/bench_${n}gpu.json 2> gpurun_out/bench_${n}gpu.err
-  tail -1 gpurun_out/bench_${n}gpu.json | cut -c1-200
-done
+# Round-end multi-GPU evidence on one box: the sharded generation loop and bench.py at N = $1 GPUs.
+N=${1:-8}
+if [ "$N" = "8" ]; then
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29621 \
+    tools/run_generations.py --games 1024 --sims 64 --iterations 2 --min-replay 5000 --eval-games 32 > gpurun_out/gen8.log 2> gpurun_out/gen8.err
+  tail -2 gpurun_out/gen8.log | cut -c1-400
+fi
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29630 + N)) \
+  bench.py --gpus $N --steps 3 --warmup 3 > gpurun_out/bench_${N}gpu.json 2> gpurun_out/bench_${N}gpu.err
+tail -1 gpurun_out/bench_${N}gpu.json | cut -c1-200
