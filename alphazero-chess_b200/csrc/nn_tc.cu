@@ -168,7 +168,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
                 mbar_wait(&tfull_bar[acc], accphase, 15);
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);
+                if (lane == 0) { if (dbg & 32) mbar_arrive_cluster(&tempty_bar[acc], 0); else mbar_arrive_cluster_relaxed(&tempty_bar[acc], 0); }
                 continue;
             }
             const bool has_res = residual != nullptr && valid && !(dbg & 8);
@@ -189,7 +189,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
                 if (chunk == 1) {
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);
+                    if (lane == 0) { if (dbg & 32) mbar_arrive_cluster(&tempty_bar[acc], 0); else mbar_arrive_cluster_relaxed(&tempty_bar[acc], 0); }
                 }
                 if (valid) {
 #pragma unroll
@@ -240,6 +240,7 @@ struct TowerParams {
     const int* n_boards_ptr;
     int n_boards_static;
     int n_layers;              // 20
+    int release_arrive;        // 1: hand accumulators back with a release arrive (AZ_TC_RELEASE_ARRIVE=1, the first version)
     int tile_lo, tile_hi;      // this launch covers tiles [tile_lo, min(all tiles, tile_hi)) (a tile = 4 boards)
     int stem;                  // 1: run the input convolution (agent.rs:117; 64 padded channels -> act[0]) as a first layer
 };
@@ -431,7 +432,7 @@ conv_tower_kernel(const TowerParams prm) {
                     if (chunk == 1) {
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive_cluster(&tempty_bar[acc], 0);
+                        if (lane == 0) { if (prm.release_arrive) mbar_arrive_cluster(&tempty_bar[acc], 0); else mbar_arrive_cluster_relaxed(&tempty_bar[acc], 0); }
                     }
                     if (valid) {
 #pragma unroll
@@ -487,6 +488,9 @@ int tc_tower_launch(cudaStream_t stream, const CUtensorMap* maps_dev, const floa
     for (int i = 0; i < 3; i++) p.act[i] = (__nv_bfloat16*)act[i];
     p.n_boards_ptr = n_boards_dev; p.n_boards_static = n_boards_static; p.n_layers = n_layers; p.stem = stem ? 1 : 0;
     p.tile_lo = tile_lo; p.tile_hi = tile_hi;
+    static int rel = -1;
+    if (rel < 0) { const char* v = getenv("AZ_TC_RELEASE_ARRIVE"); rel = v ? atoi(v) : 0; }
+    p.release_arrive = rel;
     conv_tower_kernel<<<grid, kThreads2, ConvSmem<2>::kTotal, stream>>>(p);
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
@@ -544,6 +548,9 @@ int tc_conv3x3_launch(cudaStream_t stream, const CUtensorMap* in_map, const CUte
     }
     if (grid <= 0) grid = 148;
     grid &= ~1;  // CTA pairs
+    static int rel = -1;
+    if (rel < 0) { const char* v = getenv("AZ_TC_RELEASE_ARRIVE"); rel = v ? atoi(v) : 0; }
+    if (rel) dbg |= 32;
     if (cin == 64)
         conv3x3_tc2_kernel<1><<<grid, kThreads2, ConvSmem<1>::kTotal, stream>>>(*in_map, *w_map, bias, (const __nv_bfloat16*)residual,
                                                                                (__nv_bfloat16*)out, n_boards_dev, n_boards_static, relu, dbg);
