@@ -374,10 +374,15 @@ int net_forward_bf16(az_engine* e, const int* n_dev, int n_static, float* policy
         int n_ranges = split > 0 ? split : (cap_tiles + 7 * pairs - 1) / (7 * pairs);   // at most 7 rounds (2072 boards) per range
         if (split == 0 && cap_tiles < 6 * pairs * n_ranges) n_ranges = std::max(1, cap_tiles / (6 * pairs));  // >= 6 tiles per pair (lazy publication)
         const int per = (cap_tiles + n_ranges - 1) / n_ranges;
-        for (int lo = 0; lo < cap_tiles; lo += per) {
+        // One launch walks all ranges (all 20 layers of a range, then the next range: the weight pipeline simply continues),
+        // which saves a launch fill/drain per extra range; AZ_TOWER_INKERNEL=0 launches once per range instead.
+        static int inkernel = -1;
+        if (inkernel < 0) { const char* v = getenv("AZ_TOWER_INKERNEL"); inkernel = v ? atoi(v) : 1; }
+        for (int lo = 0; lo < cap_tiles; lo += inkernel ? cap_tiles : per) {
             e->n_launches += 1;
             if (sample) e->prof_launches += 1;
-            r = tc_tower_launch(e->stream, w->d_maps, w->f_b_tower, act, n_dev, n_static, 20, fused >= 2, grid, lo, lo + per);
+            r = inkernel ? tc_tower_launch(e->stream, w->d_maps, w->f_b_tower, act, n_dev, n_static, 20, fused >= 2, grid, 0, 0x7FFFFFFF, per)
+                         : tc_tower_launch(e->stream, w->d_maps, w->f_b_tower, act, n_dev, n_static, 20, fused >= 2, grid, lo, lo + per);
             if (r) return set_err(e, AZ_ERR_CUDA, "tower launch failed");
         }
         x = 0;  // the fused tower works in place: block input and block output share a_buf[0], a_buf[1] holds conv1's output

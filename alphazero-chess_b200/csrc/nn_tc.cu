@@ -241,7 +241,8 @@ struct TowerParams {
     int n_boards_static;
     int n_layers;              // 20
     int release_arrive;        // 1: hand accumulators back with a release arrive (AZ_TC_RELEASE_ARRIVE=1, the first version)
-    int tile_lo, tile_hi;      // this launch covers tiles [tile_lo, min(all tiles, tile_hi)) (a tile = 4 boards)
+    int tile_lo, tile_hi;      // this launch covers tiles [tile_lo, min(all tiles, tile_hi)) (a tile = 4 boards) ...
+    int range_tiles;           // ... as consecutive ranges of this many tiles: all layers of one range, then the next range
     int stem;                  // 1: run the input convolution (agent.rs:117; 64 padded channels -> act[0]) as a first layer
 };
 
@@ -269,8 +270,17 @@ conv_tower_kernel(const TowerParams prm) {
     const uint32_t rank = cluster_ctarank();
     const int n_boards = prm.n_boards_ptr ? *prm.n_boards_ptr : prm.n_boards_static;
     const int n_tiles = min((n_boards + 3) >> 2, prm.tile_hi);
-    const int first_tile = prm.tile_lo + (blockIdx.x >> 1), tile_step = gridDim.x >> 1;
-    const int T = first_tile < n_tiles ? (n_tiles - first_tile + tile_step - 1) / tile_step : 0;  // tiles of this pair
+    const int tile_step = gridDim.x >> 1;
+    const int n_ranges = n_tiles > prm.tile_lo ? (n_tiles - prm.tile_lo + prm.range_tiles - 1) / prm.range_tiles : 0;
+    // Per range r every role derives the same numbers: the pair's first tile, its tile count T (ranges without tiles for
+    // this pair are skipped by all roles alike), and three running counters -- u0 / u1 = how often the weight groups of
+    // channel half 0 / 1 have been loaded so far (barrier parities), cum = tiles this pair finished in earlier ranges.
+#define TOWER_RANGE_BEGIN()                                                                                      \
+    const int range_lo = prm.tile_lo + rg * prm.range_tiles;                                                      \
+    const int range_hi = min(n_tiles, range_lo + prm.range_tiles);                                               \
+    const int first_tile = range_lo + (blockIdx.x >> 1);                                                         \
+    const int T = first_tile < range_hi ? (range_hi - first_tile + tile_step - 1) / tile_step : 0;               \
+    if (T == 0) continue;
     const int stem = prm.stem;
     const int NL = prm.n_layers + stem;  // loop index L; tower layer = L - stem (-1 is the input convolution: one channel half)
 
@@ -292,6 +302,10 @@ conv_tower_kernel(const TowerParams prm) {
     if (warp == 0) {
         // ---------------------------------------------------------------- TMA producer (both CTAs)
         int stage = 0; uint32_t phase = 0;
+        int u0 = 0, u1 = 0;
+        uint32_t cum = 0;
+        for (int rg = 0; rg < n_ranges; rg++) {
+        TOWER_RANGE_BEGIN();
         for (int L = 0; L < NL; L++) {
             const int layer = L - stem;
             const int blk_second = layer >= 0 ? (layer & 1) : 0;
@@ -302,7 +316,7 @@ conv_tower_kernel(const TowerParams prm) {
             for (int i = 0; i < T; i++) {
                 const int t = first_tile + i * tile_step;
                 if (L > 0) {  // this tile's input was written by this CTA's epilogue one layer ago
-                    const uint32_t need = (uint32_t)((L - 1) * T + i + 1);
+                    const uint32_t need = cum + (uint32_t)((L - 1) * T + i + 1);
                     long long t0 = clock64();
                     for (;;) {
                         bool ok = lane >= 8 || epi_done[lane & 7] >= need;
@@ -315,7 +329,7 @@ conv_tower_kernel(const TowerParams prm) {
                     for (int dxi = 0; dxi < 3; dxi++) {
                         const int grp = half * 3 + dxi;
                         if (i == 0) {  // (re)load this group's three weight tiles for the new layer
-                            const int used = half == 0 ? L : layer;  // earlier layers that went through this group
+                            const int used = half == 0 ? u0 : u1;  // earlier layers (of any range) that went through this group
                             if (used > 0) mbar_wait(&wempty_bar[grp], (uint32_t)((used - 1) & 1), 21);
                             if (elect_one()) {
                                 if (rank == 0) mbar_arrive_expect_tx(&wfull_bar[grp], 2 * kGroupBytes);
@@ -334,6 +348,10 @@ conv_tower_kernel(const TowerParams prm) {
                         if (++stage == NS) { stage = 0; phase ^= 1; }
                     }
             }
+            u0++;
+            if (halves == 2) u1++;
+        }
+        cum += (uint32_t)(NL * T);
         }
     } else if (warp == 1) {
         if (rank == 0) {
@@ -342,6 +360,9 @@ conv_tower_kernel(const TowerParams prm) {
             const uint64_t dbase = umma_desc_base_sw128();
             const uint32_t w_lo = (smem_u32(w_sm) & 0x3FFFF) >> 4;
             int stage = 0; uint32_t phase = 0; int lt = 0;
+            int u0 = 0, u1 = 0;
+            for (int rg = 0; rg < n_ranges; rg++) {
+            TOWER_RANGE_BEGIN();
             for (int L = 0; L < NL; L++) {
                 const int layer = L - stem;
                 const int halves = layer >= 0 ? 2 : 1;
@@ -354,7 +375,7 @@ conv_tower_kernel(const TowerParams prm) {
                         for (int dxi = 0; dxi < 3; dxi++) {
                             const int grp = half * 3 + dxi;
                             mbar_wait(&full_bar[stage], phase, 24);
-                            if (i == 0) mbar_wait(&wfull_bar[grp], (uint32_t)((half == 0 ? L : layer) & 1), 25);
+                            if (i == 0) mbar_wait(&wfull_bar[grp], (uint32_t)((half == 0 ? u0 : u1) & 1), 25);
                             tc_fence_after();
                             if (elect_one()) {
                                 const uint32_t a_lo = (smem_u32(a_sm + stage * kStageBytes) & 0x3FFFF) >> 4;
@@ -377,6 +398,9 @@ conv_tower_kernel(const TowerParams prm) {
                     if (elect_one()) umma2_commit_mc(&tfull_bar[acc]);
                     __syncwarp();
                 }
+                u0++;
+                if (halves == 2) u1++;
+            }
             }
         }
     } else {
@@ -385,12 +409,14 @@ conv_tower_kernel(const TowerParams prm) {
         const int ch = (warp - 2) >> 2;
         const int row = q * 32 + lane;
         const int h = row >> 4, b = (row >> 3) & 1, w = row & 7;
-        int lt = 0;
+        int lt = 0, g = 0;
         uint32_t done = 0;
+        for (int rg = 0; rg < n_ranges; rg++) {
+        TOWER_RANGE_BEGIN();
         // completion is published lazily (after the next accumulator wait) and only every 4th tile when the pair has
         // enough tiles in flight; the producer needs tile i of this layer only T tiles later (T >= 6: the published count lags by at most 3 tiles and the producer runs about 2 tiles ahead of the epilogue)
         const bool lazy = T >= 6;
-        for (int L = 0; L < NL; L++) {
+        for (int L = 0; L < NL; L++, g++) {
             const int layer = L - stem;
             const int blk_second = layer >= 0 ? (layer & 1) : 0;
             const int out_buf = layer < 0 ? 0 : blk_second ? 0 : 1;
@@ -401,9 +427,9 @@ conv_tower_kernel(const TowerParams prm) {
             const __nv_bfloat16* residual = blk_second ? prm.act[0] : nullptr;
             // the 8 epilogue warps switch layers together: whoever arrives refills the buffer last used two layers ago
             if (threadIdx.x - 64 < 128)
-                bias_s[(L & 1) * 128 + threadIdx.x - 64] = prm.bias[(layer >= 0 ? layer : prm.n_layers) * 128 + threadIdx.x - 64];
+                bias_s[(g & 1) * 128 + threadIdx.x - 64] = prm.bias[(layer >= 0 ? layer : prm.n_layers) * 128 + threadIdx.x - 64];
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            const float* bias = bias_s + (L & 1) * 128 + ch * 64;
+            const float* bias = bias_s + (g & 1) * 128 + ch * 64;
             for (int i = 0; i < T; i++, lt++) {
                 const int t = first_tile + i * tile_step;
                 const int acc = lt & 1; const uint32_t accphase = (lt >> 1) & 1;
@@ -468,7 +494,9 @@ conv_tower_kernel(const TowerParams prm) {
                 }
             }
         }
+        }
     }
+#undef TOWER_RANGE_BEGIN
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();
@@ -476,7 +504,7 @@ conv_tower_kernel(const TowerParams prm) {
 }
 
 int tc_tower_launch(cudaStream_t stream, const CUtensorMap* maps_dev, const float* bias, void* const* act, const int* n_boards_dev,
-                    int n_boards_static, int n_layers, int stem, int grid, int tile_lo, int tile_hi) {
+                    int n_boards_static, int n_layers, int stem, int grid, int tile_lo, int tile_hi, int range_tiles) {
     static PerDeviceOnce once;
     if (once.first() &&
         cudaFuncSetAttribute(conv_tower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<2>::kTotal) != cudaSuccess)
@@ -487,7 +515,7 @@ int tc_tower_launch(cudaStream_t stream, const CUtensorMap* maps_dev, const floa
     p.maps = maps_dev; p.bias = bias;
     for (int i = 0; i < 3; i++) p.act[i] = (__nv_bfloat16*)act[i];
     p.n_boards_ptr = n_boards_dev; p.n_boards_static = n_boards_static; p.n_layers = n_layers; p.stem = stem ? 1 : 0;
-    p.tile_lo = tile_lo; p.tile_hi = tile_hi;
+    p.tile_lo = tile_lo; p.tile_hi = tile_hi; p.range_tiles = range_tiles > 0 ? range_tiles : (1 << 30);
     static int rel = -1;
     if (rel < 0) { const char* v = getenv("AZ_TC_RELEASE_ARRIVE"); rel = v ? atoi(v) : 0; }
     p.release_arrive = rel;

@@ -13,5 +13,5 @@ int tc_conv3x3_launch(cudaStream_t stream, const CUtensorMap* in_map, const CUte
                       const void* residual, void* out, const int* n_boards_dev, int n_boards_static, int relu, int grid, int dbg = 0);
 // the 20-layer residual tower in one persistent launch; maps_dev = device array {act0, act1, act2, w[0..19]}
 int tc_tower_launch(cudaStream_t stream, const CUtensorMap* maps_dev, const float* bias, void* const* act, const int* n_boards_dev,
-                    int n_boards_static, int n_layers, int stem, int grid, int tile_lo = 0, int tile_hi = 0x7FFFFFFF);
+                    int n_boards_static, int n_layers, int stem, int grid, int tile_lo = 0, int tile_hi = 0x7FFFFFFF, int range_tiles = 0);
 }  // namespace azb
