@@ -33,3 +33,15 @@ def test_oracle_reproduces_frozen_game():
     assert hashlib.sha256(ep["visits"][:n].tobytes()).hexdigest() == g["visits_sha256"]
     assert hashlib.sha256(ep["positions"][:n].tobytes()).hexdigest() == g["positions_sha256"]
     assert float(ep["final_value"][0]) == g["final_value_first"]
+
+
+def test_oracle_reproduces_frozen_move_lists():
+    with open(os.path.join(ROOT, "tests", "golden", "movegen.json")) as f:
+        gold = json.load(f)["positions"]
+    assert len(gold) >= 20
+    for g in gold:
+        p = orc.from_fen(g["fen"])
+        mv, idx = orc.legal_moves(p)
+        assert [int(m) for m in mv] == g["moves"] and [int(i) for i in idx] == g["index"], g["fen"]
+        assert orc.outcome(p) == g["outcome"]
+        assert hashlib.sha256(orc.to_tensor(p).tobytes()).hexdigest() == g["planes_sha256"]

@@ -56,3 +56,17 @@ def test_engine_reproduces_frozen_game():
     assert hashlib.sha256(visits.tobytes()).hexdigest() == g["visits_sha256"]
     assert hashlib.sha256(np.ascontiguousarray(rec["position"]).tobytes()).hexdigest() == g["positions_sha256"]
     assert float(rec["final_value"][0]) == g["final_value_first"]
+
+
+def test_engine_reproduces_frozen_move_lists():
+    with open(os.path.join(ROOT, "tests", "golden", "movegen.json")) as f:
+        gold = json.load(f)["positions"]
+    pos = np.array([az.position_from_fen(g["fen"]) for g in gold], az.POSITION_DTYPE)
+    with az.Engine(max_games=64) as e:
+        moves, index, count = e.movegen(pos)
+        planes = e.encode(pos)
+    for k, g in enumerate(gold):
+        assert count[k] == len(g["moves"]), g["fen"]
+        assert [int(m) for m in moves[k, : count[k]]] == g["moves"], g["fen"]
+        assert [int(i) for i in index[k, : count[k]]] == g["index"], g["fen"]
+        assert hashlib.sha256(np.ascontiguousarray(planes[k]).tobytes()).hexdigest() == g["planes_sha256"], g["fen"]
