@@ -310,6 +310,14 @@ class Engine:
         return out[: n.value]
 
 
+    def selfplay_staged(self, slot, max_samples=512):
+        """Test hook: the EpisodeSteps the unfinished game in `slot` has recorded so far."""
+        out = np.empty(max_samples, SAMPLE_DTYPE)
+        n = ctypes.c_int(0)
+        self._check(self._L.az_dbg_selfplay_staged(self._h, int(slot), _ptr(out), int(max_samples), ctypes.byref(n)), "az_dbg_selfplay_staged")
+        return out[: n.value]
+
+
 class ReplayBuffer:
     """memory.rs ReplayBuffer, device resident (az_replay_*)."""
 

@@ -1132,4 +1132,19 @@ int az_selfplay_drain(az_engine* e, az_sample* out, int max_samples, int* n_out)
     return AZ_OK;
 }
 
+/* test hook: the EpisodeSteps the game in slot `slot` has staged so far (they are published when the game ends) */
+int az_dbg_selfplay_staged(az_engine* e, int slot, az_sample* out, int max_samples, int* n_out) {
+    if (!e || !out || !n_out) return AZ_ERR_INVALID_ARGUMENT;
+    SearchState* st = e->search;
+    if (!st->selfplay_active || !st->ptr.game_samples) return set_err(e, AZ_ERR_STATE, "az_selfplay_begin has not been called");
+    if (slot < 0 || slot >= st->prm.n_games) return set_err(e, AZ_ERR_INVALID_ARGUMENT, "slot out of range");
+    cudaSetDevice(e->cfg.device);
+    GameCtl c;
+    AZ_CUDA(e, cudaMemcpy(&c, st->ptr.ctl + slot, sizeof c, cudaMemcpyDeviceToHost));
+    const int n = std::min<int>((int)c.n_samples, max_samples);
+    if (n) AZ_CUDA(e, cudaMemcpy(out, st->ptr.game_samples + (size_t)slot * MAX_SAMPLE_PLIES, (size_t)n * sizeof(az_sample), cudaMemcpyDeviceToHost));
+    *n_out = n;
+    return AZ_OK;
+}
+
 }  // extern "C"

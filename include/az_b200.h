@@ -213,6 +213,8 @@ uint64_t az_launch_count(const az_engine* eng); /* kernels launched by this engi
 /* ---- unit-test entry points (device pointers) ------------------------------------------------------------------ */
 /* legal moves through the warp-cooperative generator of the search kernel (one warp per position) */
 int az_dbg_movegen_warp(az_engine* eng, int n, const az_position* pos, az_move* moves_out, int32_t* count_out);
+/* the EpisodeSteps staged so far by the unfinished game in slot `slot` (published to the sample queue when it ends) */
+int az_dbg_selfplay_staged(az_engine* eng, int slot, az_sample* out, int max_samples, int* n_out);
 int az_dbg_conv3x3_tc(const void* in_bf16, int cin, const void* w_bf16, const float* bias, const void* residual,
                       void* out_bf16, int n_boards, int relu, int iters, float* ms_out);
 

@@ -93,12 +93,14 @@ struct OrcSearchParams {
     float c_puct, dirichlet_alpha, dirichlet_eps;
     uint32_t temperature_annealing;
     uint64_t seed;
+    float temperature;   // TEMPERATURE (parameters.rs:33); 0 is read as 1.0
 };
 
 static SearchParams to_sp(const OrcSearchParams* p) {
     SearchParams sp;
     sp.num_simulations = p->num_simulations; sp.c_puct = p->c_puct; sp.dirichlet_alpha = p->dirichlet_alpha;
     sp.dirichlet_eps = p->dirichlet_eps; sp.temperature_annealing = p->temperature_annealing; sp.seed = p->seed;
+    sp.temperature = p->temperature > 0.0f ? p->temperature : 1.0f;
     return sp;
 }
 
@@ -158,6 +160,7 @@ void orc_stub_eval(uint64_t seed, const Pos* p, float* policy, float* value) { s
 uint64_t orc_rng_u64(uint64_t seed, uint64_t game, uint64_t ply, uint64_t stream, uint64_t counter) {
     return rng_u64(seed, game, ply, stream, counter);
 }
+void orc_improved_policy(const float* visits, float temperature, float* out) { improved_policy(visits, temperature, out); }
 double orc_det_log(double x) { return det_log(x); }
 double orc_det_exp(double x) { return det_exp(x); }
 void orc_dirichlet(uint64_t seed, uint64_t game, uint64_t ply, float alpha, int n, float* out) {
@@ -264,11 +267,9 @@ int orc_selfplay_episode(const OrcSearchParams* params, const OrcEvaluator* evr,
     for (u64 ply = 0; (int)ply < max_steps; ply++) {
         for (int i = 0; i < sp.num_simulations; i++) tree->simulation(sp, cached_eval, &cc, nullptr);
         sims += sp.num_simulations;
-        // improved policy = visits^(1/T)/sum with T = 1.0 (tree.rs:173-177)
+        // improved policy = visits^(1/T)/sum (tree.rs:173-177; T = 1.0 by default, then powf is the identity)
         std::array<float, ACTION_SPACE> improved;
-        float wsum = 0.0f;
-        for (int i = 0; i < ACTION_SPACE; i++) wsum += (*tree->visits)[i];
-        for (int i = 0; i < ACTION_SPACE; i++) improved[i] = (*tree->visits)[i] / wsum;
+        improved_policy(tree->visits->data(), sp.temperature, improved.data());
         float turn = state.position.turn == WHITE ? 1.0f : -1.0f;
         positions_out[n] = state.position;
         if (visits_out) std::memcpy(visits_out + (size_t)n * ACTION_SPACE, tree->visits->data(), sizeof(float) * ACTION_SPACE);

@@ -194,6 +194,18 @@ float MCTree::expand(const SearchParams& sp, eval_fn ev, void* ctx, int max_inde
     return -1.0f;
 }
 
+float pow_inv_temperature(float visits, float inv_t) {
+    if (inv_t == 1.0f || visits == 0.0f) return visits;
+    return (float)det_exp(det_log((double)visits) * (double)inv_t);
+}
+
+void improved_policy(const float* visits, float temperature, float* out) {  // tree.rs:173-177
+    const float inv_t = 1.0f / temperature;
+    float wsum = 0.0f;
+    for (int i = 0; i < ACTION_SPACE; i++) { out[i] = pow_inv_temperature(visits[i], inv_t); wsum += out[i]; }
+    for (int i = 0; i < ACTION_SPACE; i++) out[i] = out[i] / wsum;
+}
+
 int MCTree::max_subtree_depth() const {  // tree.rs:258-269
     int best = -1;
     for (auto& kv : nodes) { int d = kv.second->max_subtree_depth(); if (d > best) best = d; }

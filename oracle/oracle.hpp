@@ -132,7 +132,13 @@ struct SearchParams {
     float dirichlet_eps = 0.25f;  // parameters.rs:29
     uint32_t temperature_annealing = 15;  // parameters.rs:31
     u64 seed = 42;
+    float temperature = 1.0f;     // parameters.rs:33
 };
+// tree.rs:173-177: weights[i] = visits[i].powf(1.0 / T); out[i] = weights[i] / sum(weights).  powf is restated as
+// (float)exp(log((double)x) * (double)(1/T)) with the project's det_log / det_exp (identity when T == 1), shared with the
+// CUDA engine; against libm's powf this can differ in the last bit for T != 1.
+float pow_inv_temperature(float visits, float inv_t);
+void improved_policy(const float* visits, float temperature, float* out);
 
 struct MCTree {  // tree.rs:25-34 (dense 4096-wide arrays, as the reference)
     std::map<int, std::unique_ptr<MCTree>> nodes;

@@ -18,7 +18,8 @@ ACTION_SPACE = 4096
 
 class SearchParams(ctypes.Structure):
     _fields_ = [("num_simulations", ctypes.c_int32), ("c_puct", ctypes.c_float), ("dirichlet_alpha", ctypes.c_float),
-                ("dirichlet_eps", ctypes.c_float), ("temperature_annealing", ctypes.c_uint32), ("seed", ctypes.c_uint64)]
+                ("dirichlet_eps", ctypes.c_float), ("temperature_annealing", ctypes.c_uint32), ("seed", ctypes.c_uint64),
+                ("temperature", ctypes.c_float)]
 
 
 EVAL_FN = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float))
@@ -199,8 +200,16 @@ def make_evaluator(kind="stub", stub_seed=0, net=None, callback=None):
     return ev
 
 
-def make_params(num_simulations=256, c_puct=3.0, alpha=0.3, eps=0.25, anneal=15, seed=42):
-    return SearchParams(num_simulations, c_puct, alpha, eps, anneal, seed)
+def make_params(num_simulations=256, c_puct=3.0, alpha=0.3, eps=0.25, anneal=15, seed=42, temperature=1.0):
+    return SearchParams(num_simulations, c_puct, alpha, eps, anneal, seed, temperature)
+
+
+def improved_policy(visits, temperature=1.0):
+    """tree.rs:173-177: visits^(1/T) / sum."""
+    v = np.ascontiguousarray(visits, np.float32)
+    out = np.zeros(ACTION_SPACE, np.float32)
+    lib().orc_improved_policy(_p(v), ctypes.c_float(temperature), _p(out))
+    return out
 
 
 def search(root, params, evaluator, history=None, noise_game=-1, noise_ply=0):
