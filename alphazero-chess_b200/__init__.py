@@ -41,13 +41,14 @@ class Config(ctypes.Structure):
         ("c_puct", ctypes.c_float), ("dirichlet_alpha", ctypes.c_float), ("dirichlet_epsilon", ctypes.c_float),
         ("temperature_annealing", ctypes.c_uint32), ("num_halfmoves", ctypes.c_uint32), ("num_fullmoves", ctypes.c_uint32),
         ("repetitions", ctypes.c_uint32), ("seed", ctypes.c_uint64), ("precision", ctypes.c_int32), ("cache_log2", ctypes.c_int32),
-        ("edge_capacity_per_node", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("edge_capacity_per_node", ctypes.c_int32), ("temperature", ctypes.c_float),
     ]
 
 
 class SelfplayStats(ctypes.Structure):
     _fields_ = [(n, ctypes.c_uint64) for n in ("simulations", "positions", "evaluations", "cache_hits", "terminal_leaves",
-                                               "games_finished", "sum_leaf_depth", "sum_edges", "waves", "pending_samples")]
+                                               "games_finished", "sum_leaf_depth", "sum_edges", "waves", "pending_samples",
+                                               "active_games", "parked_games", "cache_evictions")]
 
 
 class EngineError(RuntimeError):
@@ -294,8 +295,12 @@ class Engine:
         return visits, scores, depth
 
     # ---- training.rs ------------------------------------------------------------------------------------------
-    def selfplay_begin(self, n_games, first_game_id=0):
-        self._check(self._L.az_selfplay_begin(self._h, int(n_games), ctypes.c_uint64(first_game_id)), "az_selfplay_begin")
+    def selfplay_begin(self, n_games, first_game_id=0, total_games=0):
+        """run_all_episodes set-up.  total_games = 0: every finished game restarts with a fresh id (throughput runs);
+        total_games = N: exactly the games first_game_id .. first_game_id + N - 1 are played to completion on n_games
+        concurrent slots (training.rs:352-361,376-377) and stats.active_games reaches 0 when the last one has ended."""
+        self._check(self._L.az_selfplay_begin_n(self._h, int(n_games), ctypes.c_uint64(first_game_id), ctypes.c_uint64(total_games)),
+                    "az_selfplay_begin_n")
 
     def selfplay_step(self, waves):
         st = SelfplayStats()
@@ -309,6 +314,13 @@ class Engine:
         self._check(self._L.az_selfplay_drain(self._h, _ptr(out), cap, ctypes.byref(n)), "az_selfplay_drain")
         return out[: n.value]
 
+
+    def selfplay_drain_dev(self, device_ptr, max_samples):
+        """az_selfplay_drain into device memory (device_ptr: room for max_samples az_sample records); returns the count."""
+        n = ctypes.c_int(0)
+        self._check(self._L.az_selfplay_drain_dev(self._h, ctypes.c_void_p(int(device_ptr)), int(max_samples), ctypes.byref(n)),
+                    "az_selfplay_drain_dev")
+        return n.value
 
     def selfplay_staged(self, slot, max_samples=512):
         """Test hook: the EpisodeSteps the unfinished game in `slot` has recorded so far."""
@@ -345,6 +357,12 @@ class ReplayBuffer:
         s = np.ascontiguousarray(samples, SAMPLE_DTYPE)
         nu = ctypes.c_int(0)
         self._e._check(self._L.az_replay_add(self._h, _ptr(s), int(s.shape[0]), ctypes.byref(nu)), "az_replay_add")
+        return nu.value
+
+    def add_dev(self, device_ptr, n):
+        """ReplayBuffer::add for n az_sample records already in device memory (e.g. delivered by an NCCL gather)."""
+        nu = ctypes.c_int(0)
+        self._e._check(self._L.az_replay_add_dev(self._h, ctypes.c_void_p(int(device_ptr)), int(n), ctypes.byref(nu)), "az_replay_add_dev")
         return nu.value
 
     def add_pending(self):
@@ -452,9 +470,12 @@ FLOPS_PER_TOWER_CONV = 2 * 64 * 128 * 1152  # one 3x3 128->128 convolution on on
 FLOPS_PER_INPUT_CONV = 2 * 64 * 128 * 19 * 9  # the 3x3 19->128 input convolution on one board
 
 
-def improved_policy(sample, num_simulations):
-    """Dense EpisodeStep::improved_policy (Box<[f32; 4096]>) of a drained sample."""
+def improved_policy(sample, num_simulations=None):
+    """Dense EpisodeStep::improved_policy (Box<[f32; 4096]>) of a drained sample at T = 1: visits / sum(visits)
+    (tree.rs:173-177); the sum is the search's simulation count, which `num_simulations` may state explicitly."""
     dense = np.zeros(ACTION_SPACE, np.float32)
     k = int(sample["n_visits"])
-    dense[sample["index"][:k]] = sample["count"][:k].astype(np.float32) / np.float32(num_simulations)
+    counts = sample["count"][:k].astype(np.float32)
+    total = np.float32(num_simulations) if num_simulations else np.float32(counts.sum(dtype=np.float64))
+    dense[sample["index"][:k]] = counts / total
     return dense

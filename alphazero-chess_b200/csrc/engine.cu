@@ -45,6 +45,7 @@ void az_config_default(az_config* c) {
     c->precision = 0;
     c->cache_log2 = 0;
     c->edge_capacity_per_node = 0;
+    c->temperature = 1.0f;          // parameters.rs:33
 }
 
 const char* az_last_error(const az_engine* e) { return e ? e->err.c_str() : "null engine"; }

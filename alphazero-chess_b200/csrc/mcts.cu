@@ -10,6 +10,7 @@
 // one batch (the reference's recv_many batch, training.rs:369).
 #include "mcts.h"
 #include "nn.h"
+#include "det_math.cuh"
 #include <cstdio>
 #include <cstring>
 #include <algorithm>
@@ -44,32 +45,6 @@ __device__ __forceinline__ u64 rng_u64(u64 seed, u64 game, u64 ply, u64 stream, 
 __device__ __forceinline__ double rng_uniform(u64 seed, u64 game, u64 ply, u64 stream, u64 counter) {
     u64 h = rng_u64(seed, game, ply, stream, counter);
     return ((double)(h >> 12) + 0.5) * (1.0 / 4503599627370496.0);
-}
-__device__ double det_log(double x) {
-    u64 bits = (u64)__double_as_longlong(x);
-    int e = (int)((bits >> 52) & 0x7FF) - 1023;
-    bits = (bits & 0x000FFFFFFFFFFFFFULL) | 0x3FF0000000000000ULL;
-    double m = __longlong_as_double((long long)bits);
-    if (m > 1.4142135623730951) { m = m * 0.5; e += 1; }
-    double s = (m - 1.0) / (m + 1.0);
-    double s2 = s * s;
-    double t = 1.0 / 23.0;
-    t = t * s2 + 1.0 / 21.0; t = t * s2 + 1.0 / 19.0; t = t * s2 + 1.0 / 17.0; t = t * s2 + 1.0 / 15.0;
-    t = t * s2 + 1.0 / 13.0; t = t * s2 + 1.0 / 11.0; t = t * s2 + 1.0 / 9.0; t = t * s2 + 1.0 / 7.0;
-    t = t * s2 + 1.0 / 5.0; t = t * s2 + 1.0 / 3.0; t = t * s2 + 1.0;
-    return (double)e * 0.6931471805599453 + 2.0 * s * t;
-}
-__device__ double det_exp(double x) {
-    double kf = x * 1.4426950408889634;
-    long long k = (long long)(kf < 0 ? kf - 0.5 : kf + 0.5);
-    double r = x - (double)k * 0.6931471805599453;
-    double t = 1.0 / 6227020800.0;
-    t = t * r + 1.0 / 479001600.0; t = t * r + 1.0 / 39916800.0; t = t * r + 1.0 / 3628800.0;
-    t = t * r + 1.0 / 362880.0; t = t * r + 1.0 / 40320.0; t = t * r + 1.0 / 5040.0; t = t * r + 1.0 / 720.0;
-    t = t * r + 1.0 / 120.0; t = t * r + 1.0 / 24.0; t = t * r + 1.0 / 6.0; t = t * r + 0.5; t = t * r + 1.0;
-    t = t * r + 1.0;
-    double sc = __longlong_as_double((long long)((u64)(k + 1023) << 52));
-    return t * sc;
 }
 // Gamma(alpha, 1), Marsaglia-Tsang with the alpha < 1 boost (the scheme of rand_distr 0.4.3)
 __device__ double gamma_sample(u64 seed, u64 game, u64 ply, u64 stream, double alpha) {
@@ -143,7 +118,7 @@ struct Ctx {
     size_t nbase, ebase;   // first node / edge of this game
     GameCtl c;
     // statistics accumulated by lane 0
-    unsigned int st_sims, st_pos, st_evals, st_term, st_games, st_depth, st_edges, st_hits;
+    unsigned int st_sims, st_pos, st_evals, st_term, st_games, st_depth, st_edges, st_hits, st_evict;
 };
 
 // Expands `mv` from `parent` on lane 0: child position, its legal moves (into shared memory), mate / stalemate /
@@ -361,52 +336,149 @@ __device__ __forceinline__ void select_leaf(Ctx& x, int& leaf_node, int& leaf_ed
 
 
 // ------------------------------------------------------------------------------------------- evaluation cache
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// entries are reused after eviction, so their contents are read from L2 (ld.cg), never from a possibly stale L1 line
 __device__ __forceinline__ bool cache_key_equal(const CacheEntry* e, const DPos* key, int lane) {
     bool eq = true;
-    if (lane < 8) eq = reinterpret_cast<const volatile u64*>(&e->key)[lane] == reinterpret_cast<const u64*>(key)[lane];
+    if (lane < 8) eq = __ldcg(reinterpret_cast<const u64*>(&e->key) + lane) == reinterpret_cast<const u64*>(key)[lane];
     return __all_sync(0xffffffffu, eq);
 }
 constexpr int CACHE_PROBES = 8;
-// whole warp; the key is in sh->key.  Returns the slot holding it or -1.
-__device__ __forceinline__ int cache_lookup(Ctx& x, u64 h) {
-    const uint32_t tag = (uint32_t)(h >> 34);
+__device__ __forceinline__ uint32_t cache_tag(u64 h) { return (uint32_t)(h >> 46); }   // 18 bits
+// whole warp; the key is in sh->key.  Returns the slot holding it (and the state word observed) or -1.
+__device__ __forceinline__ int cache_lookup(Ctx& x, u64 h, uint32_t& seen) {
+    const uint32_t tag = cache_tag(h);
     for (int probe = 0; probe < CACHE_PROBES; probe++) {
         const uint32_t slot = (uint32_t)(h + probe) & x.prm.cache_mask;
-        const uint32_t s = *reinterpret_cast<volatile uint32_t*>(&x.ptr.cache_state[slot]);
-        if (s == 0) return -1;
-        if ((s & 3) == 2 && (s >> 2) == tag && cache_key_equal(&x.ptr.cache_entry[slot], &x.sh->key, x.lane)) return (int)slot;
+        const uint32_t s = ld_acquire_u32(&x.ptr.cache_state[slot]);
+        if (s == 0) return -1;   // slots are replaced, never emptied: an empty slot ends every probe sequence
+        if ((s & 3) == 2 && (s >> 14) == tag && cache_key_equal(&x.ptr.cache_entry[slot], &x.sh->key, x.lane)) { seen = s; return (int)slot; }
     }
     return -1;
 }
-// whole warp: publishes (sh->key -> priors of `node`, value) unless it is already there or the neighbourhood is full
+// whole warp, after the entry's contents were copied: true if the slot still holds what cache_lookup saw
+__device__ __forceinline__ bool cache_validate(Ctx& x, int slot, uint32_t seen) {
+    __threadfence();   // the copies above are ordered before the second look at the state word
+    __syncwarp();
+    const uint32_t s2 = *reinterpret_cast<volatile uint32_t*>(&x.ptr.cache_state[slot]);
+    const bool ok = __all_sync(0xffffffffu, ((s2 ^ seen) & ~CACHE_EPOCH_MASK) == 0);
+    if (ok && x.lane == 0 && ((seen >> 2) & 63) != x.prm.cache_epoch)   // a hit keeps the entry young (failure is harmless)
+        atomicCAS(&x.ptr.cache_state[slot], seen, (seen & ~CACHE_EPOCH_MASK) | (x.prm.cache_epoch << 2));
+    return ok;
+}
+// whole warp: publishes (sh->key -> priors of `node`, value) unless it is already there; a full neighbourhood gives up
+// its stalest entry (not inserted or hit for CACHE_MIN_AGE epochs or more)
 __device__ __forceinline__ void cache_insert(Ctx& x, u64 h, int node, float value) {
-    const uint32_t tag = (uint32_t)(h >> 34);
+    const uint32_t tag = cache_tag(h);
     const size_t off = x.ebase + x.ptr.node_edge_off[x.nbase + node];
     const int L = x.ptr.node_nedges[x.nbase + node];
-    for (int probe = 0; probe < CACHE_PROBES; probe++) {
+    int target = -1, victim = -1, victim_age = CACHE_MIN_AGE - 1;
+    uint32_t target_seq = 0, victim_s = 0;
+    for (int probe = 0; probe < CACHE_PROBES && target < 0; probe++) {
         const uint32_t slot = (uint32_t)(h + probe) & x.prm.cache_mask;
-        uint32_t s = *reinterpret_cast<volatile uint32_t*>(&x.ptr.cache_state[slot]);
-        if ((s & 3) == 2 && (s >> 2) == tag && cache_key_equal(&x.ptr.cache_entry[slot], &x.sh->key, x.lane)) return;
-        if (s != 0) continue;
-        uint32_t old = 1;
-        if (x.lane == 0) old = atomicCAS(&x.ptr.cache_state[slot], 0u, 1u);
-        old = __shfl_sync(0xffffffffu, old, 0);
-        if (old != 0) continue;
-        CacheEntry* e = &x.ptr.cache_entry[slot];
-        if (x.lane < 4) reinterpret_cast<uint4*>(&e->key)[x.lane] = reinterpret_cast<const uint4*>(&x.sh->key)[x.lane];
-        if (x.lane == 4) { e->value = value; e->n_priors = (uint32_t)L; }
-        for (int i = x.lane; i < L; i += 32) e->prior[i] = x.ptr.edge_P[off + i];
-        __threadfence();
-        __syncwarp();
-        if (x.lane == 0) atomicExch(&x.ptr.cache_state[slot], (tag << 2) | 2u);
-        return;
+        const uint32_t s = ld_acquire_u32(&x.ptr.cache_state[slot]);
+        if ((s & 3) == 2 && (s >> 14) == tag && cache_key_equal(&x.ptr.cache_entry[slot], &x.sh->key, x.lane)) return;
+        if (s == 0) {
+            uint32_t old = 1;
+            if (x.lane == 0) old = atomicCAS(&x.ptr.cache_state[slot], 0u, 1u);
+            old = __shfl_sync(0xffffffffu, old, 0);
+            if (old == 0) target = (int)slot;
+        } else if ((s & 3) == 2) {
+            const int age = (int)((x.prm.cache_epoch - (s >> 2)) & 63);
+            if (age > victim_age) { victim = (int)slot; victim_age = age; victim_s = s; }
+        }
     }
+    if (target < 0) {
+        if (victim < 0) return;
+        uint32_t old = ~victim_s;
+        if (x.lane == 0) old = atomicCAS(&x.ptr.cache_state[victim], victim_s, (victim_s & ~3u) | 1u);
+        old = __shfl_sync(0xffffffffu, old, 0);
+        if (old != victim_s) return;   // somebody else hit or replaced it meanwhile
+        target = victim;
+        target_seq = ((victim_s >> 8) + 1) & 63;
+        if (x.lane == 0) x.st_evict++;
+    }
+    CacheEntry* e = &x.ptr.cache_entry[target];
+    if (x.lane < 4) reinterpret_cast<uint4*>(&e->key)[x.lane] = reinterpret_cast<const uint4*>(&x.sh->key)[x.lane];
+    if (x.lane == 4) { e->value = value; e->n_priors = (uint32_t)L; }
+    for (int i = x.lane; i < L; i += 32) e->prior[i] = x.ptr.edge_P[off + i];
+    __threadfence();
+    __syncwarp();
+    if (x.lane == 0) atomicExch(&x.ptr.cache_state[target], (tag << 14) | (target_seq << 8) | (x.prm.cache_epoch << 2) | 2u);
 }
 
 __device__ __forceinline__ void setup_root_from_shared(Ctx& x) {
     // fresh tree whose root is sh->child / sh->moves (priors are written by the caller)
     x.c.n_nodes = 0; x.c.n_edges = 0; x.c.sims_done = 0; x.c.max_depth = 0; x.c.pending_node = -1;
     create_node(x, 0);
+}
+
+// Start position, shared start-position priors, fresh noise (training.rs:352-361) -- or, when the generation's budget of
+// games is used up (az_selfplay_begin_n), the slot goes idle.
+__device__ void start_new_game(Ctx& x) {
+    unsigned long long gid = 0;
+    if (x.lane == 0) gid = atomicAdd(&x.ptr.counters->next_game_id, 1ULL);
+    gid = __shfl_sync(0xffffffffu, gid, 0);
+    if (x.prm.last_game_id != 0 && gid >= x.prm.last_game_id) { x.c.status = 1; x.c.n_samples = 0; return; }
+    x.c.game_id = gid; x.c.ply = 0; x.c.n_samples = 0; x.c.hist_len = 1;
+    if (x.lane == 0) {
+        az_position sp;
+        sp.roles[0] = 0x00FF00000000FF00ULL; sp.roles[1] = 0x4200000000000042ULL; sp.roles[2] = 0x2400000000000024ULL;
+        sp.roles[3] = 0x8100000000000081ULL; sp.roles[4] = 0x0800000000000008ULL; sp.roles[5] = 0x1000000000000010ULL;
+        sp.colors[0] = 0xFFFFULL; sp.colors[1] = 0xFFFF000000000000ULL;
+        sp.turn = 0; sp.castling = 15; sp.ep_square = -1; sp.reserved = 0; sp.halfmoves = 0; sp.fullmoves = 1;
+        DPos s = dpos_from_wire(sp);
+        ListSink sink{x.sh->moves, 0};
+        GenInfo gi = gen_legal(s, sink);
+        set_key_bits(s, gi.has_legal_ep);
+        x.sh->child = s; x.sh->n_moves = sink.n; x.sh->term = 0;
+        x.ptr.hist[(size_t)x.g * HIST_CAP] = s;
+    }
+    __syncwarp();
+    setup_root_from_shared(x);
+    const int L0 = x.ptr.node_nedges[x.nbase];
+    for (int e = x.lane; e < L0; e += 32) x.ptr.edge_P[x.ebase + e] = x.ptr.start_prior[e];
+    __syncwarp();
+    apply_noise(x, 0, x.c.game_id, 0);
+}
+
+// The game in this slot is over and `scale` = result x decay (training.rs:332-335).  Its staged EpisodeSteps move to the
+// sample queue only if ALL of them fit (the counter never covers unwritten slots); otherwise the game parks (status 4)
+// with its samples staged and tries again in the next wave, after the host has drained.  Nothing is ever dropped.
+__device__ void finish_game(Ctx& x, float scale) {
+    const int ns = (int)x.c.n_samples;
+    unsigned long long base = 0;
+    int ok = 0;
+    if (x.lane == 0) {
+        unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&x.ptr.counters->samples_out);
+        for (;;) {
+            if (cur + (unsigned long long)ns > (unsigned long long)x.prm.sample_cap) break;
+            const unsigned long long prev = atomicCAS(&x.ptr.counters->samples_out, cur, cur + (unsigned long long)ns);
+            if (prev == cur) { base = cur; ok = 1; break; }
+            cur = prev;
+        }
+    }
+    ok = __shfl_sync(0xffffffffu, ok, 0);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (!ok) {
+        x.c.status = 4;
+        x.c.park_scale = __float_as_uint(scale);
+        return;
+    }
+    x.c.status = 0;
+    az_sample* src = x.ptr.game_samples + (size_t)x.g * MAX_SAMPLE_PLIES;
+    for (int i = x.lane; i < ns; i += 32) src[i].final_value = __fmul_rn(src[i].final_value, scale);
+    __syncwarp();
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(x.ptr.out_samples + base);
+    const int n16 = ns * (int)(sizeof(az_sample) / 16);
+    for (int i = x.lane; i < n16; i += 32) d4[i] = s4[i];
+    if (x.lane == 0) x.st_games++;
+    start_new_game(x);
 }
 
 // training.rs:303-335 for one finished search: record the EpisodeStep, pick the move, advance or finish the game.
@@ -447,26 +519,31 @@ __device__ void move_step(Ctx& x) {
             smp->count[i] = sc;
         }
     }
+    // ---- improved policy weights (tree.rs:173-175): w = visits^(1/T) per visited index, summed in index order (the zeros of
+    // the reference's dense vector add nothing); T = 1 gives w = visits and the sum = S exactly
+    for (int i = x.lane; i < nv; i += 32) x.sh->fval[i] = pow_inv_temperature(x.ptr.edge_N[off + x.sh->sidx[i]], x.prm.inv_temperature);
+    __syncwarp();
     // ---- action (training.rs:310-321)
     int action_edge = 0;
     if (x.lane == 0) {
-        const float S = x.ptr.node_total[ni];  // weights_sum (T = 1: visits^(1/T) = visits)
+        float S = 0.0f;  // weights_sum
+        for (int i = 0; i < nv; i++) S = __fadd_rn(S, x.sh->fval[i]);
         if ((uint32_t)meta_fullmoves(root.meta) >= x.prm.anneal) {
             float best = -1.0f;  // Iterator::max_by keeps the LAST maximum in index order
             for (int i = 0; i < nv; i++) {
-                const float w = __fdiv_rn(x.ptr.edge_N[off + x.sh->sidx[i]], S);
+                const float w = __fdiv_rn(x.sh->fval[i], S);
                 if (w >= best) { best = w; action_edge = x.sh->sidx[i]; }
             }
         } else {
             float total = 0.0f;  // WeightedIndex: cumulative f32 weights in index order
-            for (int i = 0; i < nv; i++) total = __fadd_rn(total, __fdiv_rn(x.ptr.edge_N[off + x.sh->sidx[i]], S));
+            for (int i = 0; i < nv; i++) total = __fadd_rn(total, __fdiv_rn(x.sh->fval[i], S));
             const u64 h = rng_u64(x.prm.seed, x.c.game_id, x.c.ply, 1, 0);
             const float u = __fmul_rn((float)(h >> 40), 1.0f / 16777216.0f);
             const float chosen = __fmul_rn(u, total);
             float cum = 0.0f;
             action_edge = nv > 0 ? x.sh->sidx[nv - 1] : 0;
             for (int i = 0; i < nv; i++) {
-                cum = __fadd_rn(cum, __fdiv_rn(x.ptr.edge_N[off + x.sh->sidx[i]], S));
+                cum = __fadd_rn(cum, __fdiv_rn(x.sh->fval[i], S));
                 if (cum > chosen) { action_edge = x.sh->sidx[i]; break; }
             }
         }
@@ -516,47 +593,7 @@ __device__ void move_step(Ctx& x) {
     const float mover = turn == 0 ? 1.0f : -1.0f;
     const float result = term == 1 ? 0.0f : mover;
     const float decay = __fsub_rn(1.0f, __fdiv_rn((float)meta_fullmoves(x.sh->child.meta), __fmul_rn(2.0f, (float)x.prm.num_fullmoves)));
-    const float scale = __fmul_rn(result, decay);
-    const int ns = (int)x.c.n_samples;
-    unsigned long long base = 0;
-    if (x.lane == 0) base = atomicAdd(&x.ptr.counters->samples_out, (unsigned long long)ns);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (base + ns <= (unsigned long long)x.prm.sample_cap) {
-        az_sample* src = x.ptr.game_samples + (size_t)x.g * MAX_SAMPLE_PLIES;
-        for (int i = x.lane; i < ns; i += 32) src[i].final_value = __fmul_rn(src[i].final_value, scale);
-        __syncwarp();
-        const uint4* s4 = reinterpret_cast<const uint4*>(src);
-        uint4* d4 = reinterpret_cast<uint4*>(x.ptr.out_samples + base);
-        const int n16 = ns * (int)(sizeof(az_sample) / 16);
-        for (int i = x.lane; i < n16; i += 32) d4[i] = s4[i];
-    } else if (x.lane == 0) {
-        atomicAdd(&x.ptr.counters->errors, 1ULL);  // sample queue overflow: the host did not drain
-    }
-    if (x.lane == 0) x.st_games++;
-    // new game (training.rs:352-361): start position, shared start-position priors, noise
-    unsigned long long gid = 0;
-    if (x.lane == 0) gid = atomicAdd(&x.ptr.counters->next_game_id, 1ULL);
-    gid = __shfl_sync(0xffffffffu, gid, 0);
-    x.c.game_id = gid; x.c.ply = 0; x.c.n_samples = 0; x.c.hist_len = 1;
-    if (x.lane == 0) {
-        az_position sp;
-        sp.roles[0] = 0x00FF00000000FF00ULL; sp.roles[1] = 0x4200000000000042ULL; sp.roles[2] = 0x2400000000000024ULL;
-        sp.roles[3] = 0x8100000000000081ULL; sp.roles[4] = 0x0800000000000008ULL; sp.roles[5] = 0x1000000000000010ULL;
-        sp.colors[0] = 0xFFFFULL; sp.colors[1] = 0xFFFF000000000000ULL;
-        sp.turn = 0; sp.castling = 15; sp.ep_square = -1; sp.reserved = 0; sp.halfmoves = 0; sp.fullmoves = 1;
-        DPos s = dpos_from_wire(sp);
-        ListSink sink{x.sh->moves, 0};
-        GenInfo gi = gen_legal(s, sink);
-        set_key_bits(s, gi.has_legal_ep);
-        x.sh->child = s; x.sh->n_moves = sink.n; x.sh->term = 0;
-        x.ptr.hist[(size_t)x.g * HIST_CAP] = s;
-    }
-    __syncwarp();
-    setup_root_from_shared(x);
-    const int L0 = x.ptr.node_nedges[x.nbase];
-    for (int e = x.lane; e < L0; e += 32) x.ptr.edge_P[x.ebase + e] = x.ptr.start_prior[e];
-    __syncwarp();
-    apply_noise(x, 0, x.c.game_id, 0);
+    finish_game(x, __fmul_rn(result, decay));
 }
 
 // ------------------------------------------------------------------------------------------- the wave kernel
@@ -575,12 +612,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB * 4 / WARPS) k_advance(Search
     const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (g >= prm.n_games) return;
     Ctx x{prm, ptr, &shared[threadIdx.x >> 5], g, (int)(threadIdx.x & 31), (size_t)g * prm.node_cap, (size_t)g * prm.edge_cap,
-          ptr.ctl[g], 0, 0, 0, 0, 0, 0, 0, 0};
-    if (x.c.status != 0) return;
+          ptr.ctl[g], 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (x.c.status != 0 && x.c.status != 4) return;
 
     ADV_T0();
+    // ---- 0. game over, samples staged: publish now if the host has drained the queue, else stay parked
+    if (x.c.status == 4) finish_game(x, __uint_as_float(x.c.park_scale));
+    const bool runnable = x.c.status == 0;
     // ---- 1. the evaluation requested in the previous wave has arrived
-    if (x.c.pending_node >= 0) {
+    if (runnable && x.c.pending_node >= 0) {
         const int node = x.c.pending_node, slot = x.c.pending_slot;
         const size_t off = x.ebase + ptr.node_edge_off[x.nbase + node];
         const int L = ptr.node_nedges[x.nbase + node];
@@ -606,12 +646,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB * 4 / WARPS) k_advance(Search
 
     ADV_T(0);
     // ---- 2. run until the network is needed again
-    for (int iter = 0; iter < prm.max_iters; iter++) {
+    for (int iter = 0; runnable && iter < prm.max_iters; iter++) {
         if ((int)x.c.sims_done >= prm.S) {
             if (prm.mode == 0) { x.c.status = 1; break; }
             move_step(x);
             ADV_T(6);
-            if (x.c.status != 0) break;
+            if (x.c.status != 0) break;   // idle (generation complete), parked (sample queue full) or an error
             continue;
         }
         int node, edge, depth;
@@ -640,17 +680,20 @@ __global__ void __launch_bounds__(WARPS * 32, MINB * 4 / WARPS) k_advance(Search
         if (prm.cache_mask && prm.mode == 1) {  // cache.get (tree.rs:214-218): a hit needs no network evaluation
             if (x.lane == 0) x.sh->key = fen_key_of(x.sh->child);
             __syncwarp();
-            const int slot = cache_lookup(x, fen_key_hash(x.sh->key));
+            uint32_t seen = 0;
+            const int slot = cache_lookup(x, fen_key_hash(x.sh->key), seen);
             if (slot >= 0) {
                 const CacheEntry* ce = &ptr.cache_entry[slot];
                 const size_t coff = x.ebase + ptr.node_edge_off[x.nbase + child];
                 const int Lc = ptr.node_nedges[x.nbase + child];
-                for (int e = x.lane; e < Lc; e += 32) ptr.edge_P[coff + e] = ce->prior[e];
-                __syncwarp();
-                backup(x, ce->value, depth + 1);
-                x.c.sims_done++;
-                if (x.lane == 0) { x.st_sims++; x.st_hits++; }
-                continue;
+                for (int e = x.lane; e < Lc; e += 32) ptr.edge_P[coff + e] = __ldcg(&ce->prior[e]);
+                const float cv = __ldcg(&ce->value);
+                if (cache_validate(x, slot, seen)) {   // else: the entry was being replaced; evaluate as a miss (edge_P is overwritten)
+                    backup(x, cv, depth + 1);
+                    x.c.sims_done++;
+                    if (x.lane == 0) { x.st_sims++; x.st_hits++; }
+                    continue;
+                }
             }
         }
         x.c.pending_node = child;
@@ -663,7 +706,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB * 4 / WARPS) k_advance(Search
     if (x.lane == 0) {
         ptr.ctl[g] = x.c;
         // statistics: same field order as Counters; 64 stripes keep 4096 warps from queueing on eight addresses
-        unsigned long long* ct = ptr.stats + (size_t)(blockIdx.x & (STAT_STRIPES - 1)) * 16;
+        unsigned long long* ct = ptr.stats + (size_t)(blockIdx.x & (STAT_STRIPES - 1)) * STAT_WIDTH;
         if (x.st_sims) atomicAdd(&ct[0], (unsigned long long)x.st_sims);
         if (x.st_pos) atomicAdd(&ct[1], (unsigned long long)x.st_pos);
         if (x.st_evals) atomicAdd(&ct[2], (unsigned long long)x.st_evals);
@@ -672,6 +715,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB * 4 / WARPS) k_advance(Search
         if (x.st_games) atomicAdd(&ct[5], (unsigned long long)x.st_games);
         if (x.st_depth) atomicAdd(&ct[6], (unsigned long long)x.st_depth);
         if (x.st_edges) atomicAdd(&ct[7], (unsigned long long)x.st_edges);
+        if (x.st_evict) atomicAdd(&ct[16], (unsigned long long)x.st_evict);
 #ifdef AZ_ADV_TIMING
         t_acc[7] = (unsigned long long)(clock64() - t_start);
         for (int k = 0; k < 8; k++) atomicAdd(&ct[8 + k], t_acc[k]);
@@ -690,7 +734,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_init_search(SearchParams prm, Se
     GameCtl c;
     memset(&c, 0, sizeof c);
     Ctx x{prm, ptr, &shared[threadIdx.x >> 5], g, (int)(threadIdx.x & 31), (size_t)g * prm.node_cap, (size_t)g * prm.edge_cap, c,
-          0, 0, 0, 0, 0, 0, 0, 0};
+          0, 0, 0, 0, 0, 0, 0, 0, 0};
     x.c.game_id = noise_ids ? noise_ids[g] : 0;
     x.c.noise_ply = noise_plies ? noise_plies[g] : 0;
     x.c.flags = noise_ids ? 1 : 0;
@@ -736,7 +780,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_init_selfplay(SearchParams prm, 
     GameCtl c;
     memset(&c, 0, sizeof c);
     Ctx x{prm, ptr, &shared[threadIdx.x >> 5], g, (int)(threadIdx.x & 31), (size_t)g * prm.node_cap, (size_t)g * prm.edge_cap, c,
-          0, 0, 0, 0, 0, 0, 0, 0};
+          0, 0, 0, 0, 0, 0, 0, 0, 0};
     x.c.game_id = first_game_id + g;
     x.c.hist_len = 1;
     if (x.lane == 0) {
@@ -800,7 +844,8 @@ __global__ void k_count_active(SearchParams prm, SearchPtrs ptr, int* out) {
     if (g < prm.n_games) {
         const uint32_t s = ptr.ctl[g].status;
         if (s == 0) atomicAdd(&out[0], 1);
-        if (s >= 2) atomicAdd(&out[1], 1);
+        if (s == 2 || s == 3) atomicAdd(&out[1], 1);
+        if (s == 4) atomicAdd(&out[2], 1);
     }
 }
 
@@ -835,10 +880,17 @@ int search_create(az_engine* e) {
     // A game whose leaf was terminal could go on selecting within the same wave, but those few warps (about 8 of 4096) then
     // run two or three times longer than the rest and set the kernel's duration; they continue in the next wave instead
     // (measured per wave: 8 -> 73.6 us, 2 -> 66.4 us, 1 -> 64.2 us; results do not depend on the schedule).
-    p.mode = 0; p.max_iters = 2;
+    // With the evaluation cache a hit completes a simulation without the network, so games may go further per wave.
+    p.mode = 0; p.max_iters = c.cache_log2 > 0 ? 4 : 2;
     if (const char* v = getenv("AZ_ADV_MAX_ITERS")) p.max_iters = std::max(1, atoi(v));
+    p.last_game_id = 0; p.cache_epoch = 0;
+    if (!(c.temperature > 0.0f)) return set_err(e, AZ_ERR_INVALID_ARGUMENT, "temperature must be positive");
+    p.inv_temperature = 1.0f / c.temperature;
     p.fp32_planes = c.precision == 1 ? 1 : 0;
+    // finished games' samples wait here for az_selfplay_drain / az_replay_add_pending; a game that does not fit parks until
+    // the host has drained (finish_game), so the only hard requirement is room for one whole game
     p.sample_cap = std::max(G * 128, 1 << 16);
+    if (const char* v = getenv("AZ_SAMPLE_CAP")) p.sample_cap = std::max(MAX_SAMPLE_PLIES, atoi(v));   // tests: force parking
     SearchPtrs& q = st->ptr;
     const size_t NN = (size_t)G * p.node_cap, NE = (size_t)G * p.edge_cap;
     int r = 0;
@@ -847,11 +899,12 @@ int search_create(az_engine* e) {
     r |= salloc(e, st, &q.edge_P, NE); r |= salloc(e, st, &q.edge_N, NE); r |= salloc(e, st, &q.edge_W, NE);
     r |= salloc(e, st, &q.edge_child, NE); r |= salloc(e, st, &q.edge_mv, NE);
     r |= salloc(e, st, &q.ctl, (size_t)G); r |= salloc(e, st, &q.path, NN); r |= salloc(e, st, &q.hist, (size_t)G * HIST_CAP);
-    r |= salloc(e, st, &q.batch_count, 4); r |= salloc(e, st, &q.req_pos, (size_t)e->max_batch);
+    r |= salloc(e, st, &q.batch_count, 8); r |= salloc(e, st, &q.req_pos, (size_t)e->max_batch);
     r |= salloc(e, st, &q.req_f32, (size_t)e->max_batch * AZ_NUM_PLANES * 64);
     r |= salloc(e, st, &q.req_edge_off, (size_t)e->max_batch); r |= salloc(e, st, &q.req_nedges, (size_t)e->max_batch);
     r |= salloc(e, st, &q.start_prior, 32); r |= salloc(e, st, &q.counters, 1);
-    r |= salloc(e, st, &q.stats, (size_t)STAT_STRIPES * 16);
+    r |= salloc(e, st, &q.stats, (size_t)STAT_STRIPES * STAT_WIDTH);
+    r |= salloc(e, st, &st->d_noise_ids, (size_t)G); r |= salloc(e, st, &st->d_noise_plies, (size_t)G);
     if (r) return AZ_ERR_OUT_OF_MEMORY;
     p.cache_mask = 0; q.cache_state = nullptr; q.cache_entry = nullptr;
     if (c.cache_log2 > 0) {
@@ -867,8 +920,8 @@ int search_create(az_engine* e) {
     q.game_samples = nullptr;
     q.out_samples = nullptr;
     cudaMemset(q.counters, 0, sizeof(Counters));
-    cudaMemset(q.stats, 0, (size_t)STAT_STRIPES * 16 * sizeof(unsigned long long));
-    cudaMemset(q.batch_count, 0, 16);
+    cudaMemset(q.stats, 0, (size_t)STAT_STRIPES * STAT_WIDTH * sizeof(unsigned long long));
+    cudaMemset(q.batch_count, 0, 32);
     return 0;
 }
 
@@ -913,6 +966,7 @@ int search_clear_pending(az_engine* e) {
 static int run_wave(az_engine* e, SearchState* st) {
     const int blocks = (st->prm.n_games + WARPS - 1) / WARPS;
     st->prm.priors_scattered = (e->stub_kind == 0 && e->cfg.precision != 1) ? 1 : 0;
+    if (st->prm.mode == 1) st->prm.cache_epoch = (uint32_t)((st->wave_counter++ / (unsigned long long)std::max(st->prm.S, 1)) & 63);
     AZ_CUDA(e, cudaMemsetAsync(st->ptr.batch_count, 0, sizeof(int), e->stream));
     if (e->prof_every > 0 && e->stub_kind == 0 && e->cfg.precision != 1 && (e->prof_counter % (uint64_t)e->prof_every) == 0 &&
         !e->prof_adv_event) {
@@ -970,6 +1024,16 @@ int az_search(az_engine* e, int n, const az_position* roots, const az_position* 
     AZ_CUDA(e, cudaMemcpyAsync(e->d_wire, roots, (size_t)n * sizeof(az_position), cudaMemcpyHostToDevice, e->stream));
     const az_position* d_hist = nullptr;
     if (history && hist_offsets) {
+        // GameState::pos_count already holds the current position (chess.rs:23,52-53): the last history entry IS the root
+        for (int g = 0; g < n; g++) {
+            if (hist_offsets[g + 1] < hist_offsets[g]) return set_err(e, AZ_ERR_INVALID_ARGUMENT, "hist_offsets must be non-decreasing");
+            if (hist_offsets[g + 1] == hist_offsets[g]) continue;
+            const az_position& last = history[hist_offsets[g + 1] - 1];
+            const az_position& r0 = roots[g];
+            if (std::memcmp(last.roles, r0.roles, sizeof last.roles) || std::memcmp(last.colors, r0.colors, sizeof last.colors) ||
+                last.turn != r0.turn || last.castling != r0.castling || last.ep_square != r0.ep_square)
+                return set_err(e, AZ_ERR_INVALID_ARGUMENT, "the last history entry of a game must be its root position");
+        }
         size_t total = hist_offsets[n];
         if (total > e->hist_cap) {
             cudaFree(e->d_hist); e->d_hist = nullptr; e->hist_cap = 0;
@@ -983,8 +1047,8 @@ int az_search(az_engine* e, int n, const az_position* roots, const az_position* 
     unsigned long long* d_ids = nullptr;
     uint32_t* d_plies = nullptr;
     if (noise_game_ids) {
-        AZ_CUDA(e, cudaMalloc(&d_ids, (size_t)n * 8));
-        AZ_CUDA(e, cudaMalloc(&d_plies, (size_t)n * 4));
+        d_ids = st->d_noise_ids;   // persistent staging: no allocation (= no implicit device synchronisation) per call
+        d_plies = st->d_noise_plies;
         AZ_CUDA(e, cudaMemcpyAsync(d_ids, noise_game_ids, (size_t)n * 8, cudaMemcpyHostToDevice, e->stream));
         if (noise_plies) AZ_CUDA(e, cudaMemcpyAsync(d_plies, noise_plies, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream));
         else AZ_CUDA(e, cudaMemsetAsync(d_plies, 0, (size_t)n * 4, e->stream));
@@ -997,16 +1061,16 @@ int az_search(az_engine* e, int n, const az_position* roots, const az_position* 
     int r = evaluate_batch(e, &run);
     if (r) return r;
     // every wave completes at least one simulation per active game
-    int* d_flags = run.ptr.batch_count + 2;
+    int* d_flags = run.ptr.batch_count + 4;
     int rc = AZ_OK;
     for (int wave = 0;; wave++) {
         r = run_wave(e, &run);
         if (r) { rc = r; break; }
         if (wave + 1 >= num_simulations && (wave + 1 - num_simulations) % 4 == 0) {
-            int flags[2] = {0, 0};
-            AZ_CUDA(e, cudaMemsetAsync(d_flags, 0, 8, e->stream));
+            int flags[4] = {0, 0, 0, 0};
+            AZ_CUDA(e, cudaMemsetAsync(d_flags, 0, 16, e->stream));
             k_count_active<<<(n + 127) / 128, 128, 0, e->stream>>>(run.prm, run.ptr, d_flags);
-            AZ_CUDA(e, cudaMemcpyAsync(flags, d_flags, 8, cudaMemcpyDeviceToHost, e->stream));
+            AZ_CUDA(e, cudaMemcpyAsync(flags, d_flags, 16, cudaMemcpyDeviceToHost, e->stream));
             AZ_CUDA(e, cudaStreamSynchronize(e->stream));
             if (flags[1]) { rc = set_err(e, AZ_ERR_CAPACITY, "a per-game node/edge pool overflowed (raise edge_capacity_per_node)"); break; }
             if (flags[0] == 0) break;
@@ -1027,13 +1091,15 @@ int az_search(az_engine* e, int n, const az_position* roots, const az_position* 
         if (depth_out) AZ_CUDA(e, cudaMemcpyAsync(depth_out, e->d_count, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
         AZ_CUDA(e, cudaStreamSynchronize(e->stream));
     }
-    cudaFree(d_ids); cudaFree(d_plies);
     return rc;
 }
 
-int az_selfplay_begin(az_engine* e, int n_games, uint64_t first_game_id) {
+int az_selfplay_begin(az_engine* e, int n_games, uint64_t first_game_id) { return az_selfplay_begin_n(e, n_games, first_game_id, 0); }
+
+int az_selfplay_begin_n(az_engine* e, int n_games, uint64_t first_game_id, uint64_t total_games) {
     if (!e) return AZ_ERR_INVALID_ARGUMENT;
     SearchState* st = e->search;
+    if (total_games != 0 && (uint64_t)n_games > total_games) n_games = (int)total_games;   // never more slots than games to play
     if (n_games <= 0 || n_games > st->G) return set_err(e, AZ_ERR_CAPACITY, "more games than az_config.max_games");
     if (e->stub_kind == 0 && !e->net->loaded) return set_err(e, AZ_ERR_NO_WEIGHTS, "az_load_weights has not been called");
     cudaSetDevice(e->cfg.device);
@@ -1044,13 +1110,15 @@ int az_selfplay_begin(az_engine* e, int n_games, uint64_t first_game_id) {
         if (r) return AZ_ERR_OUT_OF_MEMORY;
     }
     st->prm.n_games = n_games; st->prm.mode = 1; st->prm.S = e->cfg.num_simulations;
+    st->prm.last_game_id = total_games ? first_game_id + total_games : 0;
+    st->wave_counter = 0; st->prm.cache_epoch = 0;
     if (st->prm.cache_mask)  // a new cache per generation (training.rs:342)
         AZ_CUDA(e, cudaMemsetAsync(q.cache_state, 0, ((size_t)st->prm.cache_mask + 1) * sizeof(uint32_t), e->stream));
     Counters zero;
     std::memset(&zero, 0, sizeof zero);
     zero.next_game_id = first_game_id + n_games;
     AZ_CUDA(e, cudaMemcpyAsync(q.counters, &zero, sizeof zero, cudaMemcpyHostToDevice, e->stream));
-    AZ_CUDA(e, cudaMemsetAsync(q.stats, 0, (size_t)STAT_STRIPES * 16 * sizeof(unsigned long long), e->stream));
+    AZ_CUDA(e, cudaMemsetAsync(q.stats, 0, (size_t)STAT_STRIPES * STAT_WIDTH * sizeof(unsigned long long), e->stream));
     // the one shared forward of the start position (training.rs:344-350)
     az_position sp;
     az_position_start(&sp);
@@ -1089,16 +1157,27 @@ int az_selfplay_step(az_engine* e, int waves, az_selfplay_stats* out) {
         if (r) return r;
     }
     Counters c;
-    unsigned long long stripes[STAT_STRIPES * 16];
+    unsigned long long stripes[STAT_STRIPES * STAT_WIDTH];
+    int flags[4] = {0, 0, 0, 0};
+    int* d_flags = st->ptr.batch_count + 4;
+    AZ_CUDA(e, cudaMemsetAsync(d_flags, 0, 16, e->stream));
+    k_count_active<<<(st->prm.n_games + 127) / 128, 128, 0, e->stream>>>(st->prm, st->ptr, d_flags);
+    AZ_CUDA(e, cudaMemcpyAsync(flags, d_flags, 16, cudaMemcpyDeviceToHost, e->stream));
     AZ_CUDA(e, cudaMemcpyAsync(&c, st->ptr.counters, sizeof c, cudaMemcpyDeviceToHost, e->stream));
     AZ_CUDA(e, cudaMemcpyAsync(stripes, st->ptr.stats, sizeof stripes, cudaMemcpyDeviceToHost, e->stream));
     AZ_CUDA(e, cudaStreamSynchronize(e->stream));
     {
         unsigned long long sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (int i = 0; i < STAT_STRIPES * 16; i++) if ((i & 15) < 8) sum[i & 7] += stripes[i];
+        unsigned long long evictions = 0;
+        for (int i = 0; i < STAT_STRIPES * STAT_WIDTH; i++) {
+            const int f = i % STAT_WIDTH;
+            if (f < 8) sum[f] += stripes[i];
+            if (f == 16) evictions += stripes[i];
+        }
+        st->cache_evictions = evictions;
 #ifdef AZ_ADV_TIMING
         unsigned long long tc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (int i = 0; i < STAT_STRIPES * 16; i++) if ((i & 15) >= 8) tc[i & 7] += stripes[i];
+        for (int i = 0; i < STAT_STRIPES * STAT_WIDTH; i++) if (i % STAT_WIDTH >= 8 && i % STAT_WIDTH < 16) tc[i % STAT_WIDTH - 8] += stripes[i];
         fprintf(stderr, "azb: k_advance phase clocks per warp-wave: consume %.0f select %.0f child %.0f rules %.0f create %.0f submit %.0f move %.0f total %.0f\n",
                 (double)tc[0] / ((double)st->prm.n_games * waves), (double)tc[1] / ((double)st->prm.n_games * waves), (double)tc[2] / ((double)st->prm.n_games * waves),
                 (double)tc[3] / ((double)st->prm.n_games * waves), (double)tc[4] / ((double)st->prm.n_games * waves), (double)tc[5] / ((double)st->prm.n_games * waves),
@@ -1111,8 +1190,9 @@ int az_selfplay_step(az_engine* e, int waves, az_selfplay_stats* out) {
         out->simulations = c.simulations; out->positions = c.positions; out->evaluations = c.evaluations; out->cache_hits = c.cache_hits;
         out->terminal_leaves = c.terminal_leaves; out->games_finished = c.games_finished; out->sum_leaf_depth = c.sum_leaf_depth;
         out->sum_edges = c.sum_edges; out->waves = (uint64_t)waves; out->pending_samples = std::min<unsigned long long>(c.samples_out, st->prm.sample_cap);
+        out->active_games = (uint64_t)(flags[0] + flags[2]); out->parked_games = (uint64_t)flags[2]; out->cache_evictions = st->cache_evictions;
     }
-    if (c.errors) return set_err(e, AZ_ERR_CAPACITY, "pool or sample-queue overflow during self-play (drain more often / raise capacities)");
+    if (c.errors || flags[1]) return set_err(e, AZ_ERR_CAPACITY, "a per-game node/edge pool overflowed during self-play (raise edge_capacity_per_node)");
     return AZ_OK;
 }
 
@@ -1128,6 +1208,24 @@ int az_selfplay_drain(az_engine* e, az_sample* out, int max_samples, int* n_out)
     if (avail && out) AZ_CUDA(e, cudaMemcpy(out, st->ptr.out_samples, (size_t)avail * sizeof(az_sample), cudaMemcpyDeviceToHost));
     unsigned long long zero = 0;
     AZ_CUDA(e, cudaMemcpy(&st->ptr.counters->samples_out, &zero, sizeof zero, cudaMemcpyHostToDevice));
+    *n_out = (int)avail;
+    return AZ_OK;
+}
+
+int az_selfplay_drain_dev(az_engine* e, az_sample* out_dev, int max_samples, int* n_out) {
+    if (!e || !n_out) return AZ_ERR_INVALID_ARGUMENT;
+    SearchState* st = e->search;
+    if (!st->selfplay_active) return set_err(e, AZ_ERR_STATE, "az_selfplay_begin has not been called");
+    cudaSetDevice(e->cfg.device);
+    Counters c;
+    AZ_CUDA(e, cudaMemcpyAsync(&c, st->ptr.counters, sizeof c, cudaMemcpyDeviceToHost, e->stream));
+    AZ_CUDA(e, cudaStreamSynchronize(e->stream));
+    const unsigned long long avail = std::min<unsigned long long>(c.samples_out, st->prm.sample_cap);
+    if (avail > (unsigned long long)max_samples) return set_err(e, AZ_ERR_CAPACITY, "drain buffer smaller than the pending sample count");
+    if (avail && out_dev)
+        AZ_CUDA(e, cudaMemcpyAsync(out_dev, st->ptr.out_samples, (size_t)avail * sizeof(az_sample), cudaMemcpyDeviceToDevice, e->stream));
+    AZ_CUDA(e, cudaMemsetAsync(&st->ptr.counters->samples_out, 0, sizeof(unsigned long long), e->stream));
+    AZ_CUDA(e, cudaStreamSynchronize(e->stream));
     *n_out = (int)avail;
     return AZ_OK;
 }

@@ -17,11 +17,12 @@ struct __align__(16) GameCtl {
     int32_t pending_slot;
     uint32_t path_len;      // edges on the path of the pending simulation
     uint32_t max_depth;
-    uint32_t status;        // 0 active, 1 search finished, 2 capacity error, 3 illegal state
+    uint32_t status;        // 0 active, 1 search finished / slot idle, 2 capacity error, 3 illegal state, 4 parked: the game is over
+                            //   and its samples wait for room in the sample queue (park_scale = result x decay)
     uint32_t noise_ply;
     uint32_t flags;         // bit0: Dirichlet noise at the root
     uint32_t n_samples;
-    uint32_t pad;
+    uint32_t park_scale;    // f32 bits
 };
 
 struct SearchParams {
@@ -38,19 +39,30 @@ struct SearchParams {
     int sample_cap;
     uint32_t cache_mask;  // slots - 1 (0: cache disabled)
     int priors_scattered; // 1: the evaluator already wrote the legal-move priors into edge_P (fused heads)
+    unsigned long long last_game_id;  // self-play: game ids >= this are not started (0: games restart forever)
+    float inv_temperature;            // 1 / TEMPERATURE as f32 (tree.rs:174)
+    uint32_t cache_epoch;             // coarse clock (one tick per ply of self-play) used to age cache entries, 6 bits
 };
 
 // Position -> (legal-move priors, value) cache: the moka Cache<Fen, CacheEntry> of training.rs:342 / tree.rs:214-218.
 // Key = everything Fen::from_position(.., EnPassantMode::PseudoLegal) contains (board, turn, castling, pseudo-legal ep,
-// halfmove clock, fullmove number), compared exactly.  Entries are immutable once published.
+// halfmove clock, fullmove number), compared exactly.  A published entry is immutable until it is evicted.
+//
+// Slot state word: [1:0] 0 empty / 1 being written / 2 published, [7:2] epoch of the last insertion or hit, [13:8] rewrite
+// sequence of the slot, [31:14] 18 tag bits of the key's hash.  Capacity management (moka's role, parameters.rs:4): when the
+// 8 probed slots are all taken, the entry that has not been inserted or hit for the most epochs (at least CACHE_MIN_AGE)
+// is replaced.  Readers are seqlock style: observe the word (acquire), compare the key, copy, fence, observe the word again;
+// any change other than the epoch bits discards the hit, so a reader never uses a half-replaced entry.
 constexpr int CACHE_MAX_PRIORS = 238;
+constexpr uint32_t CACHE_EPOCH_MASK = 63u << 2;
+constexpr int CACHE_MIN_AGE = 2;
 struct __align__(16) CacheEntry {
     DPos key;
     float value;
     uint32_t n_priors;
     float prior[CACHE_MAX_PRIORS];
 };
-static_assert(sizeof(CacheEntry) == 1024, "one cache slot is 1 KiB");
+static_assert(sizeof(CacheEntry) == 1024, "one cache slot is 1 KiB: with cudaMalloc's 256-byte alignment no two entries share a 128-byte line");
 
 struct Counters {
     unsigned long long simulations, positions, evaluations, cache_hits, terminal_leaves, games_finished, sum_leaf_depth, sum_edges,
@@ -58,6 +70,7 @@ struct Counters {
 };
 
 constexpr int STAT_STRIPES = 64;
+constexpr int STAT_WIDTH = 24;    // per stripe: 0..7 the statistics fields of Counters, 8..15 AZ_ADV_TIMING phase clocks, 16 cache evictions
 
 struct SearchPtrs {
     // nodes [G * node_cap]
@@ -93,7 +106,7 @@ struct SearchPtrs {
     uint32_t* cache_state;     // [slots] 0 empty, 1 being written, (tag << 2) | 2 published
     CacheEntry* cache_entry;   // [slots]
     Counters* counters;
-    unsigned long long* stats;         // [STAT_STRIPES][16] (8..15: AZ_ADV_TIMING phase clocks): the statistics fields of Counters, striped by block to spread the atomics
+    unsigned long long* stats;         // [STAT_STRIPES][STAT_WIDTH]: the statistics fields of Counters, striped by block to spread the atomics
 };
 
 struct SearchState {
@@ -101,6 +114,10 @@ struct SearchState {
     SearchPtrs ptr;
     int G = 0;
     bool selfplay_active = false;
+    unsigned long long cache_evictions = 0;
+    unsigned long long wave_counter = 0;   // self-play waves since az_selfplay_begin (cache epoch = wave_counter / S)
+    unsigned long long* d_noise_ids = nullptr;  // [max_games] az_search staging (no allocation per call)
+    uint32_t* d_noise_plies = nullptr;
     std::vector<void*> allocs;
 };
 

@@ -19,6 +19,7 @@
 // Sampling and batch assembly (planes, policy rows, values) are parallel over the batch.
 #include "engine.h"
 #include "mcts.h"
+#include "det_math.cuh"
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -196,8 +197,10 @@ __global__ void __launch_bounds__(32) k_replay_resolve(ReplayPtrs r, StepPtrs sp
 }
 
 // Phase B.  Block i acts only if step i is the last one of the chunk on its slot; it then owns that slot.
-__global__ void __launch_bounds__(256) k_replay_apply(ReplayPtrs r, StepPtrs sp, const az_sample* __restrict__ samples, int n, float sims) {
+__global__ void __launch_bounds__(256) k_replay_apply(ReplayPtrs r, StepPtrs sp, const az_sample* __restrict__ samples, int n, float inv_t) {
     __shared__ float s_new[AZ_ACTION_SPACE];
+    __shared__ float s_w[AZ_MAX_MOVES];
+    __shared__ float s_sum;
     __shared__ int s_cur;
     const int tail = blockIdx.x, t = threadIdx.x;
     const int slot = sp.slot[tail];
@@ -224,8 +227,20 @@ __global__ void __launch_bounds__(256) k_replay_apply(ReplayPtrs r, StepPtrs sp,
         const az_sample* sm = samples + cur;
         for (int k = t; k < AZ_ACTION_SPACE; k += 256) s_new[k] = 0.0f;
         __syncthreads();
-        const int nv = sm->n_visits;
-        for (int k = t; k < nv; k += 256) s_new[sm->index[k]] = __fdiv_rn((float)sm->count[k], sims);   // improved_policy
+        // improved_policy (tree.rs:173-177): weights = visits^(1/T), normalised by their sum taken in index order (the pairs
+        // of a sample are sorted by policy index).  At T = 1 the sum is the sample's own simulation count, whatever engine,
+        // configuration or az_search call produced it.
+        const int nv = min((int)sm->n_visits, AZ_MAX_MOVES);
+        for (int k = t; k < nv; k += 256) s_w[k] = pow_inv_temperature((float)sm->count[k], inv_t);
+        __syncthreads();
+        if (t == 0) {
+            float acc = 0.0f;
+            for (int k = 0; k < nv; k++) acc = __fadd_rn(acc, s_w[k]);
+            s_sum = acc;
+        }
+        __syncthreads();
+        const float wsum = s_sum;
+        for (int k = t; k < nv; k += 256) s_new[sm->index[k]] = __fdiv_rn(s_w[k], wsum);
         __syncthreads();
         const uint32_t old = sp.old[cur];
         if (old == 0) {
@@ -425,7 +440,7 @@ static int replay_add_dev(az_replay* rp, const az_sample* d_samples, int n, int*
         AZ_CUDA(e, cudaMemsetAsync(rp->sp.next, 0xFF, (size_t)m * sizeof(int32_t), e->stream));
         e->n_launches += 2;
         k_replay_resolve<<<1, 32, 0, e->stream>>>(rp->p, rp->sp, d_samples + off, m, rp->window, rp->force_slow);
-        k_replay_apply<<<m, 256, 0, e->stream>>>(rp->p, rp->sp, d_samples + off, m, (float)e->cfg.num_simulations);
+        k_replay_apply<<<m, 256, 0, e->stream>>>(rp->p, rp->sp, d_samples + off, m, 1.0f / e->cfg.temperature);
         AZ_CUDA(e, cudaGetLastError());
         int r = replay_maintain(rp);
         if (r) return r;
@@ -448,6 +463,12 @@ int az_replay_add(az_replay* rp, const az_sample* samples, int n, int* new_uniqu
     }
     if (n > 0) AZ_CUDA(e, cudaMemcpyAsync(rp->d_staging, samples, (size_t)n * sizeof(az_sample), cudaMemcpyHostToDevice, e->stream));
     return replay_add_dev(rp, rp->d_staging, n, new_unique_out);
+}
+
+int az_replay_add_dev(az_replay* rp, const az_sample* samples_dev, int n, int* new_unique_out) {
+    if (!rp || n < 0 || (n > 0 && !samples_dev)) return AZ_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(rp->eng->cfg.device);
+    return replay_add_dev(rp, samples_dev, n, new_unique_out);
 }
 
 int az_replay_add_pending(az_replay* rp, int* n_added_out, int* new_unique_out) {

@@ -124,41 +124,63 @@ def make_optimizer(model):
     return torch.optim.AdamW(model.parameters(), lr=BASE_LEARNING_RATE, betas=(0.9, 0.999), eps=1e-5, weight_decay=WEIGHT_DECAY)
 
 
-def train_iteration(model, optimizer, replay, iteration, num_steps=NUM_TRAIN_STEPS, batch_size=BATCH_SIZE, seed=0):
+def train_iteration(model, optimizer, replay, iteration, num_steps=NUM_TRAIN_STEPS, batch_size=BATCH_SIZE, seed=0, dist=None):
     """The inner loop of train() (training.rs:137-200): num_steps batches from the replay buffer, one AdamW step each.
-    Returns (avg policy loss, avg value loss)."""
+    Returns (avg policy loss, avg value loss).
+
+    With several ranks (dist) the step is data parallel: every rank holds the same replay buffer (DeviceSampleExchange) and
+    draws the SAME batch (same seed), computes the loss terms of its own rows rank::world scaled to the global batch, and one
+    flat all-reduce sums the gradients, so every rank applies the reference's full-batch update and the replicas stay
+    identical.  BatchNorm statistics are per rank slice unless the model was converted with SyncBatchNorm (CUDA only)."""
+    from . import sharding
+
     device = next(model.parameters()).device
+    world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
     model.train()
     lr = get_cyclical_lr(iteration)
     for g in optimizer.param_groups:
         g["lr"] = lr
-    tot_p = tot_v = 0.0
+    params = [p for p in model.parameters() if p.requires_grad]
+    flat = None
+    tot = torch.zeros(2, dtype=torch.float64, device=device)
+    done = 0
     for step in range(num_steps):
         planes, policy, value = replay.sample(batch_size, seed=(seed * 1_000_003 + iteration) * 65_537 + step)
-        if planes.shape[0] == 0:
+        n = planes.shape[0]
+        if n == 0:
             break
-        x = torch.from_numpy(planes).to(device)
-        pi = torch.from_numpy(policy).to(device)
-        z = torch.from_numpy(value).to(device)
+        x = torch.from_numpy(planes[rank::world]).to(device)
+        pi = torch.from_numpy(policy[rank::world]).to(device)
+        z = torch.from_numpy(value[rank::world]).to(device)
         p, v = model(x)
-        pl, vl, loss = compute_loss(p, pi, v, z)
+        # compute_gradients (training.rs:277-292) over the GLOBAL batch of n rows: this rank contributes its rows' terms
+        difference = v - z
+        pl = -(pi * (p + 1e-5).log()).sum() / n
+        vl = (difference * difference).sum() / n
+        loss = pl + vl * VALUE_LOSS_WEIGHT
         optimizer.zero_grad(set_to_none=True)
         loss.backward()
-        torch.nn.utils.clip_grad_value_(model.parameters(), 1.0)
+        flat = sharding.allreduce_gradients(params, dist, flat)
+        torch.nn.utils.clip_grad_value_(params, 1.0)
         optimizer.step()
-        tot_p += float(pl.detach())
-        tot_v += float(vl.detach())
-    n = max(num_steps, 1)
-    return tot_p / n, tot_v / n
+        tot += torch.stack([pl.detach(), vl.detach()]).double()
+        done += 1
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    n = max(done, 1)
+    return float(tot[0]) / n, float(tot[1]) / n
 
 
 def run_generation(engine, replay, model, optimizer, iteration, n_games, min_replay_size=MIN_REPLAY_SIZE, waves_per_call=64,
-                   num_steps=NUM_TRAIN_STEPS, batch_size=BATCH_SIZE):
-    """One iteration of train() (training.rs:70-200) on the engine: self-play until n_games games have finished, their
-    steps go from device memory straight into the replay buffer, then the training steps, then the new weights are
-    loaded into the engine.  Returns a dict of the metrics the reference logs."""
+                   num_steps=NUM_TRAIN_STEPS, batch_size=BATCH_SIZE, concurrent=None):
+    """One iteration of train() (training.rs:70-200) on the engine: EXACTLY n_games self-play games are played to completion
+    (run_all_episodes, training.rs:352-361,376-377: a slot whose game ends takes the next unplayed game or goes idle; nothing
+    is cut off), their steps go from device memory straight into the replay buffer, then the training steps, then the new
+    weights are loaded into the engine.  Returns a dict of the metrics the reference logs."""
     engine.load_weights(export_weights(model))
-    engine.selfplay_begin(n_games, first_game_id=iteration * (1 << 24))
+    slots = min(n_games, concurrent or engine.config.max_games, engine.config.max_games)
+    engine.selfplay_begin(slots, first_game_id=iteration * (1 << 24), total_games=n_games)
     new_unique = steps = 0
     while True:
         st = engine.selfplay_step(waves_per_call)
@@ -166,10 +188,12 @@ def run_generation(engine, replay, model, optimizer, iteration, n_games, min_rep
             n, nu = replay.add_pending()
             steps += n
             new_unique += nu
-        if st.games_finished >= n_games:
+        elif st.active_games == 0:
             break
-    out = {"iteration": iteration, "positions": steps, "new_unique_states": new_unique, "replay_buffer_size": len(replay),
-           "simulations": int(st.simulations), "evaluations": int(st.evaluations), "trained": False}
+    assert st.games_finished == n_games, (st.games_finished, n_games)
+    out = {"iteration": iteration, "games": int(st.games_finished), "positions": steps, "new_unique_states": new_unique,
+           "replay_buffer_size": len(replay), "simulations": int(st.simulations), "evaluations": int(st.evaluations),
+           "cache_hits": int(st.cache_hits), "trained": False}
     if len(replay) >= min_replay_size:
         pl, vl = train_iteration(model, optimizer, replay, iteration, num_steps, batch_size)
         out.update(trained=True, avg_policy_loss=pl, avg_value_loss=vl, learning_rate=get_cyclical_lr(iteration))
@@ -178,60 +202,52 @@ def run_generation(engine, replay, model, optimizer, iteration, n_games, min_rep
 
 
 def run_generation_sharded(engine, replay, model, optimizer, iteration, games_per_rank, dist, device, min_replay_size=MIN_REPLAY_SIZE,
-                           waves_per_call=64, num_steps=NUM_TRAIN_STEPS, batch_size=BATCH_SIZE):
-    """run_generation over several GPUs (BASELINE config 5): every rank plays its own games (disjoint game ids,
-    no data-path collective), the finished games' steps are gathered to rank 0 in rank order and added to ITS replay
-    buffer (the single FEN-keyed buffer of memory.rs), rank 0 runs the training steps, and the new weights go back to all
-    ranks with one broadcast and an on-device import.  `replay`, `model` and `optimizer` are only used on rank 0."""
-    from . import SAMPLE_DTYPE, sharding, weight_sizes
+                           waves_per_call=64, num_steps=NUM_TRAIN_STEPS, batch_size=BATCH_SIZE, concurrent=None, exchange=None):
+    """run_generation over several GPUs (BASELINE config 5).  Every rank plays EXACTLY games_per_rank games to
+    completion (disjoint game ids, no data-path collective) and holds its own replica of the replay buffer, model and
+    optimizer.  On CUDA the finished games' steps go device -> NCCL all-gather -> device (sharding.DeviceSampleExchange) and
+    every rank adds all ranks' steps in rank order, so the replicas of the FEN-keyed buffer (memory.rs) are identical; the
+    training steps are data parallel with one gradient all-reduce each (train_iteration); nothing is broadcast afterwards
+    because every rank has applied the same update.  On CPU (gloo tests) the same protocol runs through host arrays."""
+    from . import SAMPLE_DTYPE, sharding
 
     rank = dist.get_rank() if dist is not None and dist.is_initialized() else 0
     world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
-    sizes = weight_sizes()
-    offs = sharding.weight_offsets(sizes)
-    flat = torch.zeros(int(offs[-1]), dtype=torch.float32, device=device)
-
-    def sync_weights():
-        if rank == 0:
-            flat.copy_(torch.from_numpy(sharding.flatten_weights(export_weights(model))))
-        sharding.broadcast_weights(flat, dist, src=0)
-        if flat.is_cuda:
-            torch.cuda.synchronize(flat.device)
-            engine.load_weights_dev([flat.data_ptr() + 4 * int(o) for o in offs[:-1]])
-        else:
-            engine.load_weights(sharding.split_weights(flat.numpy(), sizes))
-
-    sync_weights()
-    engine.selfplay_begin(games_per_rank, first_game_id=sharding.first_game_id(rank) + iteration * (1 << 24))
+    on_gpu = device is not None and torch.device(device).type == "cuda"
+    if iteration == 0 and world > 1:   # replicas start from rank 0's initial weights (afterwards they evolve in lockstep)
+        for t in list(model.parameters()) + list(model.buffers()):
+            dist.broadcast(t.data, src=0)
+    engine.load_weights(export_weights(model))
+    slots = min(games_per_rank, concurrent or engine.config.max_games, engine.config.max_games)
+    engine.selfplay_begin(slots, first_game_id=sharding.first_game_id(rank) + iteration * (1 << 24), total_games=games_per_rank)
+    if on_gpu and exchange is None:
+        exchange = sharding.DeviceSampleExchange(engine, dist, device, max(engine.config.max_games * 128, 1 << 16))
     steps = new_unique = 0
     done = False
     st = None
     while True:
-        mine = np.zeros(0, SAMPLE_DTYPE)
         if not done:
             st = engine.selfplay_step(waves_per_call)
-            if st.pending_samples:
-                mine = engine.selfplay_drain()
-            done = st.games_finished >= games_per_rank
-        got = sharding.gather_samples(mine, dist, device if flat.is_cuda else None)
-        if rank == 0 and len(got):
-            steps += len(got)
-            new_unique += replay.add(got)
-        if sharding.all_done(done, dist, device if flat.is_cuda else None):
+        if on_gpu:
+            for ptr, n in exchange.exchange():
+                if n:
+                    steps += n
+                    new_unique += replay.add_dev(ptr, n)
+        else:
+            mine = engine.selfplay_drain() if (st.pending_samples and not done) else np.zeros(0, SAMPLE_DTYPE)
+            got = sharding.allgather_samples(mine, dist)
+            if len(got):
+                steps += len(got)
+                new_unique += replay.add(got)
+        done = st.active_games == 0
+        if sharding.all_done(done, dist, device if on_gpu else None):
             break
-    sums, _ = sharding.reduce_metrics([float(st.simulations), float(st.evaluations)], [0.0], dist)
-    out = {"iteration": iteration, "n_ranks": world, "positions": steps, "new_unique_states": new_unique,
-           "replay_buffer_size": len(replay) if rank == 0 else 0, "simulations": int(sums[0]), "evaluations": int(sums[1]), "trained": False}
-    train = all_flag = False
-    if rank == 0:
-        train = len(replay) >= min_replay_size
-    t = torch.tensor([1 if train else 0], dtype=torch.int32, device=device if flat.is_cuda else None)
-    if world > 1:
-        dist.broadcast(t, src=0)
-    all_flag = bool(t.item())
-    if all_flag:
-        if rank == 0:
-            pl, vl = train_iteration(model, optimizer, replay, iteration, num_steps, batch_size)
-            out.update(trained=True, avg_policy_loss=pl, avg_value_loss=vl, learning_rate=get_cyclical_lr(iteration))
-        sync_weights()
+    sums, _ = sharding.reduce_metrics([float(st.simulations), float(st.evaluations), float(st.games_finished)], [0.0], dist)
+    out = {"iteration": iteration, "n_ranks": world, "games": int(sums[2]), "positions": steps, "new_unique_states": new_unique,
+           "replay_buffer_size": len(replay), "simulations": int(sums[0]), "evaluations": int(sums[1]), "trained": False,
+           "sample_gather": "device all-gather (NCCL)" if on_gpu else "host all-gather"}
+    if len(replay) >= min_replay_size:   # identical on every rank: the replicas hold the same entries
+        pl, vl = train_iteration(model, optimizer, replay, iteration, num_steps, batch_size, dist=dist if world > 1 else None)
+        out.update(trained=True, avg_policy_loss=pl, avg_value_loss=vl, learning_rate=get_cyclical_lr(iteration))
+        engine.load_weights(export_weights(model))
     return out

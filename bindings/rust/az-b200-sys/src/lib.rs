@@ -14,13 +14,13 @@ pub struct az_config { pub device: i32, pub max_games: i32, pub max_batch: i32, 
                        pub c_puct: f32, pub dirichlet_alpha: f32, pub dirichlet_epsilon: f32,
                        pub temperature_annealing: u32, pub num_halfmoves: u32, pub num_fullmoves: u32,
                        pub repetitions: u32, pub seed: u64, pub precision: i32, pub cache_log2: i32,
-                       pub edge_capacity_per_node: i32, pub reserved: i32 }
+                       pub edge_capacity_per_node: i32, pub temperature: f32 }
 #[repr(C)] pub struct az_sample { pub position: az_position, pub final_value: f32, pub search_depth: i32,
                                   pub game_id: u64, pub ply: u32, pub action: u16, pub n_visits: u16,
                                   pub index: [u16; 256], pub count: [u16; 256] }                          // 1120 bytes
 #[repr(C)] #[derive(Default)] pub struct az_selfplay_stats { pub simulations: u64, pub positions: u64, pub evaluations: u64,
     pub cache_hits: u64, pub terminal_leaves: u64, pub games_finished: u64, pub sum_leaf_depth: u64, pub sum_edges: u64,
-    pub waves: u64, pub pending_samples: u64 }
+    pub waves: u64, pub pending_samples: u64, pub active_games: u64, pub parked_games: u64, pub cache_evictions: u64 }
 pub enum az_engine {}
 
 extern "C" {
@@ -43,8 +43,10 @@ extern "C" {
                      hist_offsets: *const u32, num_simulations: c_int, noise_game_ids: *const u64, noise_plies: *const u32,
                      visits: *mut f32, scores: *mut f32, depth: *mut i32) -> c_int;
     pub fn az_selfplay_begin(eng: *mut az_engine, n_games: c_int, first_game_id: u64) -> c_int;
+    pub fn az_selfplay_begin_n(eng: *mut az_engine, n_concurrent: c_int, first_game_id: u64, total_games: u64) -> c_int;
     pub fn az_selfplay_step(eng: *mut az_engine, waves: c_int, stats: *mut az_selfplay_stats) -> c_int;
     pub fn az_selfplay_drain(eng: *mut az_engine, out: *mut az_sample, max_samples: c_int, n_out: *mut c_int) -> c_int;
+    pub fn az_selfplay_drain_dev(eng: *mut az_engine, out_dev: *mut az_sample, max_samples: c_int, n_out: *mut c_int) -> c_int;
     // callers beyond self-play (section 3)
     pub fn az_version() -> *const c_char;
     pub fn az_position_from_fen(fen: *const c_char, out: *mut az_position) -> c_int;
@@ -57,6 +59,7 @@ extern "C" {
     pub fn az_replay_destroy(rp: *mut az_replay);
     pub fn az_replay_add(rp: *mut az_replay, samples: *const az_sample, n: c_int, new_unique: *mut c_int) -> c_int;
     pub fn az_replay_add_pending(rp: *mut az_replay, n_added: *mut c_int, new_unique: *mut c_int) -> c_int;
+    pub fn az_replay_add_dev(rp: *mut az_replay, samples_dev: *const az_sample, n: c_int, new_unique: *mut c_int) -> c_int;
     pub fn az_replay_len(rp: *mut az_replay, len: *mut c_int) -> c_int;
     pub fn az_replay_sample(rp: *mut az_replay, batch: c_int, seed: u64, planes: *mut f32, policy: *mut f32, value: *mut f32, n_out: *mut c_int) -> c_int;
     pub fn az_replay_export(rp: *mut az_replay, first: c_int, n: c_int, pos: *mut az_position, policy: *mut f32, value: *mut f32,

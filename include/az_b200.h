@@ -70,7 +70,7 @@ typedef struct az_config {
     int32_t precision;              /* 0: bf16 tensor-core network (tcgen05), 1: fp32 network (parity mode) */
     int32_t cache_log2;             /* log2 slots of the GPU position->evaluation cache (0 disables; training.rs:342) */
     int32_t edge_capacity_per_node; /* average edge-pool budget per tree node (0: 96); overflow -> AZ_ERR_CAPACITY */
-    int32_t reserved;
+    float temperature;              /* TEMPERATURE (1.0): improved policy = visits^(1/T) / sum (tree.rs:173-177) */
 } az_config;
 
 typedef struct az_engine az_engine;
@@ -151,6 +151,9 @@ typedef struct az_selfplay_stats {
     uint64_t sum_edges;       /* edges visited by selection (bytes model of DESIGN.md) */
     uint64_t waves;
     uint64_t pending_samples; /* samples waiting for az_selfplay_drain */
+    uint64_t active_games;    /* slots still playing (az_selfplay_begin_n: 0 once every game of the generation has ended) */
+    uint64_t parked_games;    /* finished games waiting for room in the sample queue (drain to let them publish) */
+    uint64_t cache_evictions; /* cache entries replaced by newer ones (capacity management, parameters.rs:4) */
 } az_selfplay_stats;
 
 typedef struct az_sample {
@@ -166,8 +169,14 @@ typedef struct az_sample {
 } az_sample;
 
 int az_selfplay_begin(az_engine* eng, int n_games, uint64_t first_game_id);
+/* run_all_episodes (training.rs:340-378) plays exactly NUM_EPISODES games to completion: n_concurrent slots play the games
+ * first_game_id .. first_game_id + total_games - 1; a slot whose game ends takes the next unplayed id or goes idle, and
+ * stats.active_games reaches 0 when the generation is complete.  total_games = 0: games restart forever (az_selfplay_begin). */
+int az_selfplay_begin_n(az_engine* eng, int n_concurrent, uint64_t first_game_id, uint64_t total_games);
 int az_selfplay_step(az_engine* eng, int waves, az_selfplay_stats* stats_out);
 int az_selfplay_drain(az_engine* eng, az_sample* out, int max_samples, int* n_out);
+/* same, into DEVICE memory (e.g. the send buffer of an NCCL gather): no host hop between self-play and the replay buffer */
+int az_selfplay_drain_dev(az_engine* eng, az_sample* out_dev, int max_samples, int* n_out);
 
 /* ---- memory.rs: ReplayBuffer (the consumer of self-play output) ---------------------------
  * Device resident.  az_replay_add mirrors ReplayBuffer::add (memory.rs:41-76) for a batch of EpisodeSteps applied in
@@ -184,6 +193,8 @@ int az_replay_create(az_engine* eng, int capacity, int max_batch, az_replay** ou
 void az_replay_destroy(az_replay* rp);
 int az_replay_add(az_replay* rp, const az_sample* samples, int n, int* new_unique_out);
 int az_replay_add_pending(az_replay* rp, int* n_added_out, int* new_unique_out);
+/* az_replay_add for samples already in device memory (what an NCCL gather delivered) */
+int az_replay_add_dev(az_replay* rp, const az_sample* samples_dev, int n, int* new_unique_out);
 int az_replay_len(az_replay* rp, int* len_out);
 int az_replay_sample(az_replay* rp, int batch_size, uint64_t seed, float* planes_out, float* policy_out, float* value_out, int* n_out);
 int az_replay_export(az_replay* rp, int first, int n, az_position* pos_out, float* policy_out, float* value_out, uint32_t* visits_out,

@@ -199,7 +199,8 @@ struct EpisodeStep {            // training.rs:15-20
 inline std::pair<float, std::vector<EpisodeStep>> run_all_episodes(AlphaZero& model, int n_games, uint64_t first_game_id = 0,
                                                                    int waves_per_call = 64) {
     Engine& e = model.engine();
-    e.check(az_selfplay_begin(e.handle(), n_games, first_game_id), "az_selfplay_begin");
+    // exactly the games first_game_id .. first_game_id + n_games - 1, each played to completion (training.rs:352-361,376-377)
+    e.check(az_selfplay_begin_n(e.handle(), n_games, first_game_id, (uint64_t)n_games), "az_selfplay_begin_n");
     std::vector<EpisodeStep> steps;
     std::vector<az_sample> buf((std::size_t)std::max(n_games * 128, 1 << 16));
     const float sims = (float)e.config().num_simulations;
@@ -215,19 +216,18 @@ inline std::pair<float, std::vector<EpisodeStep>> run_all_episodes(AlphaZero& mo
             int n = 0;
             e.check(az_selfplay_drain(e.handle(), buf.data(), (int)buf.size(), &n), "az_selfplay_drain");
             for (int i = 0; i < n; i++) {
-                if (buf[i].game_id < first_game_id || buf[i].game_id >= first_game_id + (uint64_t)n_games) continue;  // restarted games
                 char& f = finished[(std::size_t)(buf[i].game_id - first_game_id)];
                 if (!f) { f = 1; n_finished++; }
                 EpisodeStep s;
                 s.state = buf[i].position;
                 s.improved_policy.fill(0.0f);
-                for (int k = 0; k < buf[i].n_visits; k++) s.improved_policy[buf[i].index[k]] = (float)buf[i].count[k] / sims;
+                for (int k = 0; k < buf[i].n_visits; k++) s.improved_policy[buf[i].index[k]] = (float)buf[i].count[k] / sims;  // T = 1
                 s.final_value = buf[i].final_value;
                 s.search_depth = (std::size_t)buf[i].search_depth;
                 steps.push_back(s);
             }
         }
-        if (n_finished >= n_games) break;  // a finished game's steps arrive together, so every episode is complete
+        if (st.active_games == 0 && st.pending_samples == 0) break;  // every slot is idle: all n_games episodes are complete
     }
     return {(float)(evals / batches), std::move(steps)};
 }
