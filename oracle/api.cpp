@@ -155,6 +155,65 @@ int orc_play_move(Pos* pos, const Pos* history, int n_hist, int action_index) {
     return r;
 }
 
+// ---- batched forms for the 65,536-position differential of BASELINE config 2 (one ctypes call instead of 65,536) ----------
+// Seeded random playouts: position i starts from roots[i % n_roots] and plays a uniformly random legal
+// move for a random number of plies in [0, max_plies] (stopping early at a finished game).  hist_out (nullable) receives
+// every position on the way INCLUDING the final one, hist_off[n + 1] delimits games; returns the total history length.
+int64_t orc_playout_corpus(uint64_t seed, int n, int max_plies, const Pos* roots, int n_roots, Pos* pos_out, Pos* hist_out,
+                           int64_t hist_cap, uint32_t* hist_off) {
+    int64_t total = 0;
+    for (int i = 0; i < n; i++) {
+        Pos p = roots[i % n_roots];
+        const int plies = (int)(rng_u64(seed, (uint64_t)i, 0, 7, 0) % (uint64_t)(max_plies + 1));
+        if (hist_off) hist_off[i] = (uint32_t)total;
+        if (hist_out && total < hist_cap) hist_out[total] = p;
+        total++;
+        for (int k = 0; k < plies; k++) {
+            MoveList ml; legal_moves(p, ml);
+            if (ml.n == 0 || outcome(p) != 0) break;
+            play_unchecked(p, ml.m[rng_u64(seed, (uint64_t)i, (uint64_t)k + 1, 7, 1) % (uint64_t)ml.n]);
+            if (hist_out && total < hist_cap) hist_out[total] = p;
+            total++;
+        }
+        pos_out[i] = p;
+    }
+    if (hist_off) hist_off[n] = (uint32_t)total;
+    return total;
+}
+
+// legal_moves + move_to_index for n positions: moves_out / index_out [n][256] (unused entries 0xFFFF / untouched), count_out [n]
+void orc_legal_moves_batch(const Pos* pos, int n, uint16_t* moves_out, uint16_t* index_out, int32_t* count_out) {
+    for (int i = 0; i < n; i++) {
+        MoveList ml; legal_moves(pos[i], ml);
+        count_out[i] = ml.n;
+        for (int k = 0; k < 256; k++) {
+            moves_out[(size_t)i * 256 + k] = k < ml.n ? encode_move(ml.m[k]) : (uint16_t)0xFFFF;
+            if (k < ml.n) index_out[(size_t)i * 256 + k] = (uint16_t)move_to_index(ml.m[k], pos[i].turn);
+        }
+    }
+}
+
+void orc_to_tensor_batch(const Pos* pos, int n, float* out) {
+    for (int i = 0; i < n; i++) to_tensor(pos[i], out + (size_t)i * 19 * 64);
+}
+
+// play_move (chess.rs:36-63) for n games: pos updated in place when legal, result_out [n]
+void orc_play_move_batch(Pos* pos, int n, const Pos* history, const uint32_t* hist_off, const uint16_t* action_index, int32_t* result_out) {
+    for (int i = 0; i < n; i++) {
+        const Pos* h = history ? history + hist_off[i] : nullptr;
+        const int nh = history ? (int)(hist_off[i + 1] - hist_off[i]) : 0;
+        result_out[i] = orc_play_move(&pos[i], h, nh, (int)action_index[i]);
+    }
+}
+
+// index_to_move for n (position, index) pairs: 0xFFFF where the reference returns None
+void orc_index_to_move_batch(const Pos* pos, int n, const uint16_t* index, uint16_t* moves_out) {
+    for (int i = 0; i < n; i++) {
+        Move m;
+        moves_out[i] = index_to_move((int)index[i], pos[i], &m) ? encode_move(m) : (uint16_t)0xFFFF;
+    }
+}
+
 void orc_stub_eval(uint64_t seed, const Pos* p, float* policy, float* value) { stub_evaluator(&seed, p, policy, value); }
 
 uint64_t orc_rng_u64(uint64_t seed, uint64_t game, uint64_t ply, uint64_t stream, uint64_t counter) {

@@ -145,6 +145,61 @@ def to_tensor(pos):
     return out.reshape(19, 8, 8)
 
 
+def playout_corpus(n, seed=42, max_plies=80, roots=None, with_history=True):
+    """Seeded random-playout positions generated inside the oracle library: (positions [n],
+    history [total] or None, hist_offsets [n + 1]); each game's history ends in its position."""
+    r = np.ascontiguousarray(roots if roots is not None else [startpos()], POSITION_DTYPE)
+    pos = np.zeros(n, POSITION_DTYPE)
+    offs = np.zeros(n + 1, np.uint32)
+    lib().orc_playout_corpus.restype = ctypes.c_int64
+    hist = None
+    if with_history:
+        cap = int(n) * (max_plies + 1)
+        hist = np.zeros(cap, POSITION_DTYPE)
+        total = lib().orc_playout_corpus(ctypes.c_uint64(seed), int(n), int(max_plies), _p(r), int(r.shape[0]), _p(pos), _p(hist),
+                                         ctypes.c_int64(cap), _p(offs))
+        hist = hist[:total]
+    else:
+        lib().orc_playout_corpus(ctypes.c_uint64(seed), int(n), int(max_plies), _p(r), int(r.shape[0]), _p(pos), ctypes.c_void_p(0),
+                                 ctypes.c_int64(0), _p(offs))
+    return pos, hist, offs
+
+
+def legal_moves_batch(positions):
+    p = np.ascontiguousarray(positions, POSITION_DTYPE)
+    n = p.shape[0]
+    moves = np.zeros((n, 256), np.uint16)
+    index = np.zeros((n, 256), np.uint16)
+    count = np.zeros(n, np.int32)
+    lib().orc_legal_moves_batch(_p(p), n, _p(moves), _p(index), _p(count))
+    return moves, index, count
+
+
+def to_tensor_batch(positions):
+    p = np.ascontiguousarray(positions, POSITION_DTYPE)
+    out = np.zeros((p.shape[0], 19, 8, 8), np.float32)
+    lib().orc_to_tensor_batch(_p(p), p.shape[0], _p(out))
+    return out
+
+
+def play_move_batch(positions, action_index, history=None, hist_offsets=None):
+    p = np.ascontiguousarray(positions, POSITION_DTYPE).copy()
+    a = np.ascontiguousarray(action_index, np.uint16)
+    res = np.zeros(p.shape[0], np.int32)
+    h = np.ascontiguousarray(history, POSITION_DTYPE) if history is not None else None
+    ho = np.ascontiguousarray(hist_offsets, np.uint32) if hist_offsets is not None else None
+    lib().orc_play_move_batch(_p(p), p.shape[0], _p(h), _p(ho), _p(a), _p(res))
+    return p, res
+
+
+def index_to_move_batch(positions, index):
+    p = np.ascontiguousarray(positions, POSITION_DTYPE)
+    ix = np.ascontiguousarray(index, np.uint16)
+    out = np.zeros(p.shape[0], np.uint16)
+    lib().orc_index_to_move_batch(_p(p), p.shape[0], _p(ix), _p(out))
+    return out
+
+
 def stub_eval(seed, pos):
     pol = np.zeros(ACTION_SPACE, np.float32)
     val = ctypes.c_float(0)
@@ -276,3 +331,41 @@ class Replay:
             lib().orc_replay_destroy(ctypes.c_void_p(self.h))
         except Exception:
             pass
+
+
+# ---- random-init weights without the product library (bench.py --impl reference must not load libaz_b200.so) ---------------
+def weight_catalogue():
+    """(name, size) of the 144 arrays of AlphaZero::new (agent.rs:69-110) in record order, restated independently of
+    include/az_b200.h's az_weight_name / az_weight_size (tests/test_abi_cpu.py checks that the two agree)."""
+    bn = ["gamma", "beta", "running_mean", "running_var"]
+    out = [("input_conv.weight", 128 * 19 * 9), ("input_conv.bias", 128)] + [(f"input_bn.{k}", 128) for k in bn]
+    for b in range(10):
+        for c, n in (("conv1", "bn1"), ("conv2", "bn2")):
+            out += [(f"res_blocks.{b}.{c}.weight", 128 * 128 * 9), (f"res_blocks.{b}.{c}.bias", 128)]
+            out += [(f"res_blocks.{b}.{n}.{k}", 128) for k in bn]
+    out += [("policy_conv_1.weight", 32 * 128), ("policy_conv_1.bias", 32)] + [(f"policy_bn.{k}", 32) for k in bn]
+    out += [("policy_conv_2.weight", 64 * 32), ("policy_conv_2.bias", 64)]
+    out += [("value_conv.weight", 8 * 128), ("value_conv.bias", 8)] + [(f"value_bn.{k}", 8) for k in bn]
+    out += [("value_linear_1.weight", 512 * 64), ("value_linear_1.bias", 64), ("value_linear_2.weight", 64), ("value_linear_2.bias", 1)]
+    return out
+
+
+_FAN_IN = {"input_conv": 19 * 9, "conv1": 128 * 9, "conv2": 128 * 9, "policy_conv_1": 128, "policy_conv_2": 32, "value_conv": 128,
+           "value_linear_1": 512, "value_linear_2": 64}
+
+
+def random_weights(seed=42):
+    """The same random-init network as the product's random_weights(seed) (conv / linear U(-k, k), k = 1/sqrt(fan_in);
+    BatchNorm gamma 1, beta 0, mean 0, var 1), generated without touching the CUDA library."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for name, size in weight_catalogue():
+        layer, field = name.split(".")[-2:]
+        if field in ("weight", "bias"):
+            k = 1.0 / np.sqrt(_FAN_IN[layer])
+            out.append(rng.uniform(-k, k, size).astype(np.float32))
+        elif field in ("gamma", "running_var"):
+            out.append(np.ones(size, np.float32))
+        else:
+            out.append(np.zeros(size, np.float32))
+    return out

@@ -3,6 +3,8 @@ import ctypes
 import os
 import re
 
+import numpy as np
+
 import alphazero_chess_b200 as az
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -57,3 +59,16 @@ def test_rust_bindings_list_every_header_function():
             declared = set(re.findall(r"pub fn (az_[a-z0-9_]+)\(", f.read()))
         assert names <= declared, (rel, sorted(names - declared))
         assert declared <= names, (rel, sorted(declared - names))
+
+
+def test_oracle_weight_catalogue_equals_the_abi():
+    """bench.py --impl reference builds its random-init network from the oracle's own catalogue (it must not load the CUDA
+    library); the catalogue and the generator have to agree with the product's."""
+    from oracle import pyoracle as orc
+
+    import alphazero_chess_b200 as az
+    cat = orc.weight_catalogue()
+    assert [n for n, _ in cat] == az.weight_names()
+    assert [s for _, s in cat] == az.weight_sizes()
+    a, b = orc.random_weights(seed=42), az.random_weights(seed=42)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
