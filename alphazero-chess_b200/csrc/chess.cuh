@@ -295,6 +295,11 @@ __device__ __forceinline__ u64 shfl_u64(u64 v, int src) {
     return ((u64)hi << 32) | lo;
 }
 
+__device__ __forceinline__ u64 shfl_xor_u64(u64 v, int mask) {
+    const unsigned lo = __shfl_xor_sync(0xffffffffu, (unsigned)v, mask), hi = __shfl_xor_sync(0xffffffffu, (unsigned)(v >> 32), mask);
+    return ((u64)hi << 32) | lo;
+}
+
 __device__ __forceinline__ GenInfo warp_gen_legal(const DPos& p, uint16_t* __restrict__ moves, int lane, int& n_out) {
     const int us = meta_turn(p.meta);
     const u64 occ = occupied(p);

@@ -111,6 +111,15 @@ int az_engine_create(const az_config* cfg, az_engine** out) {
     if (prop.major != 10) { e->err = "this library contains sm_100a code only (Blackwell B200 required)"; return AZ_ERR_NO_DEVICE; }
     e->sm_count = prop.multiProcessorCount;
     AZ_CUDA(e, cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    {
+        auto env_int = [](const char* name, int dflt) { const char* v = getenv(name); return v ? atoi(v) : dflt; };
+        e->knobs.tower_fused = env_int("AZ_TOWER_FUSED", 1);
+        e->knobs.tower_split = std::max(0, env_int("AZ_TOWER_SPLIT", 0));
+        e->knobs.tower_inkernel = env_int("AZ_TOWER_INKERNEL", 1);
+        e->knobs.tc_release_arrive = env_int("AZ_TC_RELEASE_ARRIVE", 0);
+        e->knobs.adv_minb = env_int("AZ_ADV_MINB", 7);
+        e->knobs.tower_grid = std::max(0, env_int("AZ_TOWER_GRID", 0));
+    }
     const size_t nb = (size_t)e->max_batch;
     AZ_CUDA(e, cudaMalloc(&e->d_wire, nb * sizeof(az_position)));
     AZ_CUDA(e, cudaMalloc(&e->d_hist_off, (nb + 1) * sizeof(uint32_t)));

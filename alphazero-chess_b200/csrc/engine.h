@@ -66,6 +66,17 @@ struct az_engine {
     double prof_ms = 0.0, prof_input_ms = 0.0, prof_heads_ms = 0.0, prof_adv_ms = 0.0;
     uint64_t prof_samples = 0, prof_boards = 0, prof_launches = 0;
 
+    // tuning switches: read from the environment ONCE, when the engine is created, and kept per engine
+    // (no process-wide statics shared by engines / devices)
+    struct Knobs {
+        int tower_fused = 1;       // AZ_TOWER_FUSED
+        int tower_split = 0;       // AZ_TOWER_SPLIT (0: automatic)
+        int tower_inkernel = 1;    // AZ_TOWER_INKERNEL
+        int tc_release_arrive = 0; // AZ_TC_RELEASE_ARRIVE
+        int adv_minb = 7;          // AZ_ADV_MINB
+        int tower_grid = 0;        // AZ_TOWER_GRID (0: every SM; the SM-partition experiment of profiles/)
+    } knobs;
+
     azb::NetWeights* net = nullptr;
     azb::SearchState* search = nullptr;
     int stub_kind = 0;

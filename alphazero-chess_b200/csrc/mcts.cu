@@ -119,6 +119,7 @@ struct Ctx {
     GameCtl c;
     // statistics accumulated by lane 0
     unsigned int st_sims, st_pos, st_evals, st_term, st_games, st_depth, st_edges, st_hits, st_evict;
+    unsigned long long new_link;   // edge_link value of the node create_node made last
 };
 
 // Expands `mv` from `parent` on lane 0: child position, its legal moves (into shared memory), mate / stalemate /
@@ -226,7 +227,7 @@ __device__ __forceinline__ int create_node(Ctx& x, int depth) {
             x.ptr.edge_N[e] = 0.0f;
             x.ptr.edge_W[e] = 0.0f;
             x.ptr.edge_P[e] = 0.0f;
-            x.ptr.edge_child[e] = -1;
+            x.ptr.edge_link[e] = EDGE_NO_CHILD;
         }
         written += __popc(bal);
     }
@@ -236,11 +237,11 @@ __device__ __forceinline__ int create_node(Ctx& x, int depth) {
         x.ptr.node_edge_off[ni] = eoff;
         x.ptr.node_nedges[ni] = (uint16_t)L;
         x.ptr.node_nmoves[ni] = (uint16_t)n;
-        x.ptr.node_total[ni] = 0.0f;
         x.ptr.node_depth[ni] = (uint16_t)depth;
     }
     x.c.n_nodes++;
     x.c.n_edges += L;
+    x.new_link = (unsigned long long)node | ((unsigned long long)L << 16) | ((unsigned long long)eoff << 24);
     __syncwarp();
     return node;
 }
@@ -270,66 +271,99 @@ __device__ __forceinline__ int submit_request(Ctx& x, int node) {
 }
 
 // W[a] += v ; N[a] += 1 along the stored path, leaf parent first (tree.rs:197-206).  `leaf_value` is what
-// expand() returned (the child's point of view).
-__device__ __forceinline__ void backup(Ctx& x, float leaf_value, int path_len) {
+// expand() returned (the child's point of view).  `spec` (nullable): this lane's path entry requested before the control block
+// was known (levels 0..31), which takes one dependent load out of the chain ctl -> path -> edge.
+__device__ __forceinline__ void backup(Ctx& x, float leaf_value, int path_len, const uint2* spec = nullptr) {
     for (int i0 = 0; i0 < path_len; i0 += 32) {
         const int i = i0 + x.lane;
         if (i < path_len) {
-            const uint2 pe = x.ptr.path[(size_t)x.g * x.prm.node_cap + i];
-            const int node = pe.x & 0xFFFF;
+            const uint2 pe = (spec && i0 == 0) ? *spec : x.ptr.path[(size_t)x.g * x.prm.node_cap + i];
             const size_t e = x.ebase + pe.y;
             // levels above the leaf's parent: the sign flips once per level
             const int up = path_len - 1 - i;
             const float v = (up & 1) ? leaf_value : -leaf_value;
             x.ptr.edge_W[e] = __fadd_rn(x.ptr.edge_W[e], v);
             x.ptr.edge_N[e] = __fadd_rn(x.ptr.edge_N[e], 1.0f);
-            x.ptr.node_total[x.nbase + node] = __fadd_rn(x.ptr.node_total[x.nbase + node], 1.0f);
         }
     }
     __syncwarp();
 }
 
-// One PUCT descent from the root (tree.rs:180-202).  Fills the path and returns (node, edge) of the leaf edge.
-__device__ __forceinline__ void select_leaf(Ctx& x, int& leaf_node, int& leaf_edge, int& depth) {
+// One PUCT descent from the root (tree.rs:180-202).  Fills the path and returns the leaf: its parent's node id, position and
+// depth, and the chosen edge (pool index, wire move).
+// The walk costs ONE dependent memory round trip per level: an edge carries its child's id together with the child's edge
+// range (edge_link), the root's range is in the control block, total_visits = sum of the edges' visit counts (tree.rs:184 --
+// integers in f32, exact in any order) is reduced from the very loads the scores need, and the chosen edge's move and every
+// visited node's position (the leaf's parent needs it) are requested in the same batch of loads.
+__device__ __forceinline__ void select_leaf(Ctx& x, int& leaf_node, size_t& leaf_pe, uint32_t& leaf_mv, int& depth, DPos& parent) {
     int node = 0;
     depth = 0;
+    uint32_t eoff = 0;
+    int L = (int)((x.c.flags >> 8) & 0xFF);
     for (;;) {
-        const size_t ni = x.nbase + node;
-        const size_t off = x.ebase + x.ptr.node_edge_off[ni];
-        const int L = x.ptr.node_nedges[ni];
-        const float total = __fadd_rn(x.ptr.node_total[ni], 1.0f);
+        const size_t off = x.ebase + eoff;
+        u64 here = 0;   // lanes 0..7: the eight words of this node's position
+        if (x.lane < 8) here = reinterpret_cast<const u64*>(&x.ptr.node_pos[x.nbase + node])[x.lane];
+        float P0 = 0.0f, N0 = 0.0f, W0 = 0.0f;
+        u64 K0 = EDGE_NO_CHILD;
+        uint32_t M0 = 0;
+        if (x.lane < L) {
+            P0 = x.ptr.edge_P[off + x.lane]; N0 = x.ptr.edge_N[off + x.lane]; W0 = x.ptr.edge_W[off + x.lane];
+            K0 = x.ptr.edge_link[off + x.lane]; M0 = x.ptr.edge_mv[off + x.lane];
+        }
+        float nsum = N0;
+        for (int e = x.lane + 32; e < L; e += 32) nsum = __fadd_rn(nsum, x.ptr.edge_N[off + e]);
+        for (int d = 16; d; d >>= 1) nsum = __fadd_rn(nsum, __shfl_xor_sync(0xffffffffu, nsum, d));
+        const float total = __fadd_rn(nsum, 1.0f);
         const float sq = __fsqrt_rn(total);
         float best = -INFINITY;
         int best_e = 0x7FFFFFFF;
-        // the child link travels with the score, so the walk does not wait for one more dependent load per level
-        int best_child = x.lane == 0 && L > 0 ? x.ptr.edge_child[off] : -1;
-        for (int e = x.lane; e < L; e += 32) {
+        u64 best_k = K0;        // the link and the move travel with the score through the argmax
+        uint32_t best_m = M0;
+        if (x.lane < L) {
+            const float u = __fdiv_rn(__fmul_rn(__fmul_rn(x.prm.c_puct, P0), sq), __fadd_rn(1.0f, N0));
+            const float q = N0 > 0.0f ? __fdiv_rn(W0, N0) : 0.0f;
+            const float v = __fadd_rn(q, u);
+            if (v > best) { best = v; best_e = x.lane; }
+        }
+        for (int e = x.lane + 32; e < L; e += 32) {
             const float P = x.ptr.edge_P[off + e], N = x.ptr.edge_N[off + e], W = x.ptr.edge_W[off + e];
-            const int ch = x.ptr.edge_child[off + e];
+            const u64 K = x.ptr.edge_link[off + e];
+            const uint32_t M = x.ptr.edge_mv[off + e];
             const float u = __fdiv_rn(__fmul_rn(__fmul_rn(x.prm.c_puct, P), sq), __fadd_rn(1.0f, N));
             const float q = N > 0.0f ? __fdiv_rn(W, N) : 0.0f;
             const float v = __fadd_rn(q, u);
-            if (v > best) { best = v; best_e = e; best_child = ch; }
+            if (v > best) { best = v; best_e = e; best_k = K; best_m = M; }
         }
         // warp argmax: larger value wins, ties go to the earlier move (strict '>' in list order)
         for (int d = 16; d; d >>= 1) {
             const float ov = __shfl_xor_sync(0xffffffffu, best, d);
             const int oe = __shfl_xor_sync(0xffffffffu, best_e, d);
-            const int oc = __shfl_xor_sync(0xffffffffu, best_child, d);
-            if (ov > best || (ov == best && oe < best_e)) { best = ov; best_e = oe; best_child = oc; }
+            const u64 ok = shfl_xor_u64(best_k, d);
+            const uint32_t om = __shfl_xor_sync(0xffffffffu, best_m, d);
+            if (ov > best || (ov == best && oe < best_e)) { best = ov; best_e = oe; best_k = ok; best_m = om; }
         }
         if (best_e == 0x7FFFFFFF) {  // every score was NaN / -inf: the reference keeps max_index = 0 (first move)
             best_e = 0;
-            best_child = __shfl_sync(0xffffffffu, best_child, 0);
+            best_k = shfl_u64(K0, 0);
+            best_m = __shfl_sync(0xffffffffu, M0, 0);
         }
         if (x.lane == 0) {
             x.ptr.path[(size_t)x.g * x.prm.node_cap + depth] =
-                make_uint2((uint32_t)node | ((uint32_t)best_e << 16), (uint32_t)(off - x.ebase) + (uint32_t)best_e);
+                make_uint2((uint32_t)node | ((uint32_t)best_e << 16), eoff + (uint32_t)best_e);
             x.st_edges += L;
         }
-        const int child = best_child;
-        if (child < 0) { leaf_node = node; leaf_edge = best_e; __syncwarp(); return; }
-        node = child;
+        if (best_k == EDGE_NO_CHILD) {
+            leaf_node = node; leaf_pe = off + best_e; leaf_mv = best_m;
+            parent.pawn = shfl_u64(here, 0); parent.knight = shfl_u64(here, 1); parent.bishop = shfl_u64(here, 2);
+            parent.rook = shfl_u64(here, 3); parent.queen = shfl_u64(here, 4); parent.king = shfl_u64(here, 5);
+            parent.white = shfl_u64(here, 6); parent.meta = shfl_u64(here, 7);
+            __syncwarp();
+            return;
+        }
+        node = (int)(best_k & 0xFFFF);
+        L = (int)((best_k >> 16) & 0xFF);
+        eoff = (uint32_t)(best_k >> 24);
         depth++;
     }
 }
@@ -415,6 +449,7 @@ __device__ __forceinline__ void setup_root_from_shared(Ctx& x) {
     // fresh tree whose root is sh->child / sh->moves (priors are written by the caller)
     x.c.n_nodes = 0; x.c.n_edges = 0; x.c.sims_done = 0; x.c.max_depth = 0; x.c.pending_node = -1;
     create_node(x, 0);
+    x.c.flags = (x.c.flags & 0xFFFF00FFu) | ((uint32_t)((x.new_link >> 16) & 0xFF) << 8);   // the root's edge count (its offset is 0)
 }
 
 // Start position, shared start-position priors, fresh noise (training.rs:352-361) -- or, when the generation's budget of
@@ -562,7 +597,8 @@ __device__ void move_step(Ctx& x) {
     }
     x.c.n_samples = min(x.c.n_samples + 1, (uint32_t)MAX_SAMPLE_PLIES);
     // ---- play it (chess.rs:36-63)
-    const int child_node = x.ptr.edge_child[off + action_edge];
+    const unsigned long long child_link = x.ptr.edge_link[off + action_edge];
+    const int child_node = child_link == EDGE_NO_CHILD ? -1 : (int)(child_link & 0xFFFF);
     lane0_make_child(x, root, (uint16_t)(amv & 0xFFFF));
     int term = x.sh->term;
     if (term == 0 && draw_by_rules(x, x.sh->child, 1)) term = 1;
@@ -596,6 +632,33 @@ __device__ void move_step(Ctx& x) {
     finish_game(x, __fmul_rn(result, decay));
 }
 
+// ------------------------------------------------------------------------------------------- cold paths of the wave kernel
+// A finished search (once per S waves and game), a parked game and root noise are rare; compiled inline they sit in the middle
+// of the hot instruction stream of a 20,000-instruction kernel whose warps stall on instruction fetch (ncu: "no instructions"
+// is the second stall reason, profiles/r2_advance_v1_full.md).  They are real calls instead.  The game's control block goes in
+// and out BY VALUE so that the hot path's copy stays in registers (a reference would pin it in local memory).
+struct ColdOut {
+    GameCtl c;
+    unsigned int st_pos, st_games;
+};
+__device__ __forceinline__ Ctx cold_ctx(const SearchParams* prm, const SearchPtrs* ptr, WarpShared* sh, int g, const GameCtl& c) {
+    return Ctx{*prm, *ptr, sh, g, (int)(threadIdx.x & 31), (size_t)g * prm->node_cap, (size_t)g * prm->edge_cap, c, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+}
+__device__ __noinline__ ColdOut move_step_cold(const SearchParams* prm, const SearchPtrs* ptr, WarpShared* sh, int g, GameCtl c) {
+    Ctx x = cold_ctx(prm, ptr, sh, g, c);
+    move_step(x);
+    return ColdOut{x.c, x.st_pos, x.st_games};
+}
+__device__ __noinline__ ColdOut finish_game_cold(const SearchParams* prm, const SearchPtrs* ptr, WarpShared* sh, int g, GameCtl c) {
+    Ctx x = cold_ctx(prm, ptr, sh, g, c);
+    finish_game(x, __uint_as_float(c.park_scale));
+    return ColdOut{x.c, x.st_pos, x.st_games};
+}
+__device__ __noinline__ void root_noise_cold(const SearchParams* prm, const SearchPtrs* ptr, WarpShared* sh, int g, GameCtl c) {
+    Ctx x = cold_ctx(prm, ptr, sh, g, c);
+    apply_noise(x, 0, c.game_id, c.noise_ply);
+}
+
 // ------------------------------------------------------------------------------------------- the wave kernel
 #ifdef AZ_ADV_TIMING
 #define ADV_T0() long long t_prev = clock64(), t_start = t_prev; unsigned long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
@@ -607,17 +670,22 @@ __device__ void move_step(Ctx& x) {
 // MINB = resident groups of four warps per SM the register allocation is bounded for: the kernel is a chain of dependent global loads
 // per game, so resident warps (latency hiding) are worth more than registers (AZ_ADV_MINB selects, see launch below)
 template <int MINB>
-__global__ void __launch_bounds__(WARPS * 32, MINB * 4 / WARPS) k_advance(SearchParams prm, SearchPtrs ptr) {
+__global__ void __launch_bounds__(WARPS * 32, MINB * 4 / WARPS) k_advance(const __grid_constant__ SearchParams prm, const __grid_constant__ SearchPtrs ptr) {
     __shared__ WarpShared shared[WARPS];
     const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (g >= prm.n_games) return;
+    // the path of the pending simulation is requested together with the control block (its address needs only g)
+    const uint2 path_spec = ptr.path[(size_t)g * prm.node_cap + min((int)(threadIdx.x & 31), prm.node_cap - 1)];
     Ctx x{prm, ptr, &shared[threadIdx.x >> 5], g, (int)(threadIdx.x & 31), (size_t)g * prm.node_cap, (size_t)g * prm.edge_cap,
-          ptr.ctl[g], 0, 0, 0, 0, 0, 0, 0, 0, 0};
+          ptr.ctl[g], 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (x.c.status != 0 && x.c.status != 4) return;
 
     ADV_T0();
     // ---- 0. game over, samples staged: publish now if the host has drained the queue, else stay parked
-    if (x.c.status == 4) finish_game(x, __uint_as_float(x.c.park_scale));
+    if (x.c.status == 4) {
+        const ColdOut o = finish_game_cold(&prm, &ptr, x.sh, g, x.c);
+        x.c = o.c; x.st_pos += o.st_pos; x.st_games += o.st_games;
+    }
     const bool runnable = x.c.status == 0;
     // ---- 1. the evaluation requested in the previous wave has arrived
     if (runnable && x.c.pending_node >= 0) {
@@ -635,9 +703,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB * 4 / WARPS) k_advance(Search
             cache_insert(x, fen_key_hash(x.sh->key), node, ptr.res_value[slot]);
         }
         if (node == 0) {  // MCTree::init (tree.rs:37-64): root priors, optional noise, no backup
-            if (x.c.flags & 1) apply_noise(x, 0, x.c.game_id, x.c.noise_ply);
+            if (x.c.flags & 1) root_noise_cold(&prm, &ptr, x.sh, g, x.c);
         } else {
-            backup(x, ptr.res_value[slot], (int)x.c.path_len);
+            backup(x, ptr.res_value[slot], (int)x.c.path_len, &path_spec);
             x.c.sims_done++;
             if (x.lane == 0) x.st_sims++;
         }
@@ -649,17 +717,19 @@ __global__ void __launch_bounds__(WARPS * 32, MINB * 4 / WARPS) k_advance(Search
     for (int iter = 0; runnable && iter < prm.max_iters; iter++) {
         if ((int)x.c.sims_done >= prm.S) {
             if (prm.mode == 0) { x.c.status = 1; break; }
-            move_step(x);
+            const ColdOut o = move_step_cold(&prm, &ptr, x.sh, g, x.c);
+            x.c = o.c; x.st_pos += o.st_pos; x.st_games += o.st_games;
             ADV_T(6);
             if (x.c.status != 0) break;   // idle (generation complete), parked (sample queue full) or an error
             continue;
         }
-        int node, edge, depth;
-        select_leaf(x, node, edge, depth);
+        int node, depth;
+        size_t pe;
+        uint32_t leaf_mv;
+        DPos parent;
+        select_leaf(x, node, pe, leaf_mv, depth, parent);
         ADV_T(1);
-        const size_t pe = x.ebase + ptr.node_edge_off[x.nbase + node] + edge;
-        const DPos parent = ptr.node_pos[x.nbase + node];
-        lane0_make_child(x, parent, (uint16_t)(ptr.edge_mv[pe] & 0xFFFF));
+        lane0_make_child(x, parent, (uint16_t)(leaf_mv & 0xFFFF));
         int term = x.sh->term;
         ADV_T(2);
         if (term == 0 && draw_by_rules(x, x.sh->child, depth + 1)) term = 1;
@@ -675,7 +745,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB * 4 / WARPS) k_advance(Search
         const int child = create_node(x, depth + 1);
         ADV_T(4);
         if (child < 0) { x.c.status = 2; if (x.lane == 0) atomicAdd(&ptr.counters->errors, 1ULL); break; }
-        if (x.lane == 0) ptr.edge_child[pe] = child;
+        if (x.lane == 0) ptr.edge_link[pe] = x.new_link;
         x.c.max_depth = max(x.c.max_depth, (uint32_t)(depth + 1));
         if (prm.cache_mask && prm.mode == 1) {  // cache.get (tree.rs:214-218): a hit needs no network evaluation
             if (x.lane == 0) x.sh->key = fen_key_of(x.sh->child);
@@ -734,7 +804,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_init_search(SearchParams prm, Se
     GameCtl c;
     memset(&c, 0, sizeof c);
     Ctx x{prm, ptr, &shared[threadIdx.x >> 5], g, (int)(threadIdx.x & 31), (size_t)g * prm.node_cap, (size_t)g * prm.edge_cap, c,
-          0, 0, 0, 0, 0, 0, 0, 0, 0};
+          0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     x.c.game_id = noise_ids ? noise_ids[g] : 0;
     x.c.noise_ply = noise_plies ? noise_plies[g] : 0;
     x.c.flags = noise_ids ? 1 : 0;
@@ -780,7 +850,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_init_selfplay(SearchParams prm, 
     GameCtl c;
     memset(&c, 0, sizeof c);
     Ctx x{prm, ptr, &shared[threadIdx.x >> 5], g, (int)(threadIdx.x & 31), (size_t)g * prm.node_cap, (size_t)g * prm.edge_cap, c,
-          0, 0, 0, 0, 0, 0, 0, 0, 0};
+          0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     x.c.game_id = first_game_id + g;
     x.c.hist_len = 1;
     if (x.lane == 0) {
@@ -895,9 +965,9 @@ int search_create(az_engine* e) {
     const size_t NN = (size_t)G * p.node_cap, NE = (size_t)G * p.edge_cap;
     int r = 0;
     r |= salloc(e, st, &q.node_pos, NN); r |= salloc(e, st, &q.node_edge_off, NN); r |= salloc(e, st, &q.node_nedges, NN);
-    r |= salloc(e, st, &q.node_nmoves, NN); r |= salloc(e, st, &q.node_total, NN); r |= salloc(e, st, &q.node_depth, NN);
+    r |= salloc(e, st, &q.node_nmoves, NN); r |= salloc(e, st, &q.node_depth, NN);
     r |= salloc(e, st, &q.edge_P, NE); r |= salloc(e, st, &q.edge_N, NE); r |= salloc(e, st, &q.edge_W, NE);
-    r |= salloc(e, st, &q.edge_child, NE); r |= salloc(e, st, &q.edge_mv, NE);
+    r |= salloc(e, st, &q.edge_link, NE); r |= salloc(e, st, &q.edge_mv, NE);
     r |= salloc(e, st, &q.ctl, (size_t)G); r |= salloc(e, st, &q.path, NN); r |= salloc(e, st, &q.hist, (size_t)G * HIST_CAP);
     r |= salloc(e, st, &q.batch_count, 8); r |= salloc(e, st, &q.req_pos, (size_t)e->max_batch);
     r |= salloc(e, st, &q.req_f32, (size_t)e->max_batch * AZ_NUM_PLANES * 64);
@@ -974,8 +1044,7 @@ static int run_wave(az_engine* e, SearchState* st) {
         cudaEventRecord(e->prof_adv_event, e->stream);
     }
     e->n_launches++;
-    static int minb = -1;
-    if (minb < 0) { const char* v = getenv("AZ_ADV_MINB"); minb = v ? atoi(v) : 7; }
+    const int minb = e->knobs.adv_minb;
     // groups of four warps per SM (register bound): 3 -> 162 registers, 4 -> 128, 5 -> 96, 6 -> 80, 7 -> 72 with 216 bytes of
     // spills.  With 7, all 4096 games of a wave are resident at once (148 SMs x 28 warps) and the kernel is one round of
     // latency chains instead of two: measured per wave 4 -> 67.6 us, 5 -> 68.5, 6 -> 69.6, 7 -> 54.7.

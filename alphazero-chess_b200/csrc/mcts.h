@@ -20,7 +20,7 @@ struct __align__(16) GameCtl {
     uint32_t status;        // 0 active, 1 search finished / slot idle, 2 capacity error, 3 illegal state, 4 parked: the game is over
                             //   and its samples wait for room in the sample queue (park_scale = result x decay)
     uint32_t noise_ply;
-    uint32_t flags;         // bit0: Dirichlet noise at the root
+    uint32_t flags;         // bit0: Dirichlet noise at the root; bits 8-15: number of edges of the root (its offset is 0)
     uint32_t n_samples;
     uint32_t park_scale;    // f32 bits
 };
@@ -69,6 +69,7 @@ struct Counters {
         next_game_id, samples_out, errors;
 };
 
+constexpr unsigned long long EDGE_NO_CHILD = ~0ULL;
 constexpr int STAT_STRIPES = 64;
 constexpr int STAT_WIDTH = 24;    // per stripe: 0..7 the statistics fields of Counters, 8..15 AZ_ADV_TIMING phase clocks, 16 cache evictions
 
@@ -78,13 +79,13 @@ struct SearchPtrs {
     uint32_t* node_edge_off;
     uint16_t* node_nedges;
     uint16_t* node_nmoves;
-    float* node_total;
     uint16_t* node_depth;
     // edges [G * edge_cap]
     float* edge_P;
     float* edge_N;
     float* edge_W;
-    int32_t* edge_child;
+    unsigned long long* edge_link;   // child node id | its edge count << 16 | its edge offset << 24 (EDGE_NO_CHILD: none): selection
+                                     // walks from edges to edges without a dependent load of the child's node record
     uint32_t* edge_mv;   // wire move | policy index << 16
     // per game
     GameCtl* ctl;

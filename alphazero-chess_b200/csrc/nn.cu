@@ -336,6 +336,8 @@ int net_forward_bf16(az_engine* e, const int* n_dev, int n_static, float* policy
     NetWeights* w = e->net;
     if (!w->loaded) return set_err(e, AZ_ERR_NO_WEIGHTS, "az_load_weights has not been called");
     const int grid = e->sm_count & ~1;
+    const int tgrid = e->knobs.tower_grid > 0 ? std::min(grid, e->knobs.tower_grid & ~1) : grid;   // CTAs of the tower launch
+    const int rel = e->knobs.tc_release_arrive;
     e->n_launches += 1;  // heads; the input convolution and the tower add 1 (one fused launch), 2 or 21 below
     const bool sample = e->prof_every > 0 && (e->prof_counter++ % (uint64_t)e->prof_every) == 0 && e->prof_pending.size() < 4000;
     az_engine::ProfSample ps{nullptr, nullptr, nullptr, nullptr, nullptr, 0};
@@ -346,12 +348,11 @@ int net_forward_bf16(az_engine* e, const int* n_dev, int n_static, float* policy
     // AZ_TOWER_FUSED: 1 (default) = input convolution + one launch for the 20 tower layers, 2 = the input convolution runs as
     // an extra first layer of that launch (measured: 48 us inside vs 60 us alone per 4096 boards, epilogue-bound either
     // way, so the wave gains 0.2 % -- kept as an option), 0 = 21 launches
-    static int fused = -1;
-    if (fused < 0) { const char* v = getenv("AZ_TOWER_FUSED"); fused = v ? atoi(v) : 1; }
+    const int fused = e->knobs.tower_fused;
     int r = 0;
     if (fused < 2) {
         e->n_launches += 1;
-        r = tc_conv3x3_launch(e->stream, &w->map_a_in, &w->map_w_in, 64, w->f_b_in, nullptr, w->a_buf[0], n_dev, n_static, 1, grid);
+        r = tc_conv3x3_launch(e->stream, &w->map_a_in, &w->map_w_in, 64, w->f_b_in, nullptr, w->a_buf[0], n_dev, n_static, 1, grid, rel ? 32 : 0);
         if (r) return set_err(e, AZ_ERR_CUDA, "tc conv (input) launch failed");
     }
     if (sample) {
@@ -367,22 +368,20 @@ int net_forward_bf16(az_engine* e, const int* n_dev, int n_static, float* policy
         // are 7 rounds, the same 98.8 % fill as the whole batch.  At 4096 boards two launches take 1148 us against
         // 1250 us for one launch whose 134 MB stream through HBM in every layer (and the clocks under the power cap
         // are higher).  AZ_TOWER_SPLIT overrides the number of ranges.
-        static int split = -1;
-        if (split < 0) { const char* v = getenv("AZ_TOWER_SPLIT"); split = v ? std::max(1, atoi(v)) : 0; }
+        const int split = e->knobs.tower_split;
         const int cap_tiles = ((n_dev ? w->max_boards : n_static) + 3) / 4;
-        const int pairs = grid / 2;
+        const int pairs = tgrid / 2;
         int n_ranges = split > 0 ? split : (cap_tiles + 7 * pairs - 1) / (7 * pairs);   // at most 7 rounds (2072 boards) per range
         if (split == 0 && cap_tiles < 6 * pairs * n_ranges) n_ranges = std::max(1, cap_tiles / (6 * pairs));  // >= 6 tiles per pair (lazy publication)
         const int per = (cap_tiles + n_ranges - 1) / n_ranges;
         // One launch walks all ranges (all 20 layers of a range, then the next range: the weight pipeline simply continues),
         // which saves a launch fill/drain per extra range; AZ_TOWER_INKERNEL=0 launches once per range instead.
-        static int inkernel = -1;
-        if (inkernel < 0) { const char* v = getenv("AZ_TOWER_INKERNEL"); inkernel = v ? atoi(v) : 1; }
+        const int inkernel = e->knobs.tower_inkernel;
         for (int lo = 0; lo < cap_tiles; lo += inkernel ? cap_tiles : per) {
             e->n_launches += 1;
             if (sample) e->prof_launches += 1;
-            r = inkernel ? tc_tower_launch(e->stream, w->d_maps, w->f_b_tower, act, n_dev, n_static, 20, fused >= 2, grid, 0, 0x7FFFFFFF, per)
-                         : tc_tower_launch(e->stream, w->d_maps, w->f_b_tower, act, n_dev, n_static, 20, fused >= 2, grid, lo, lo + per);
+            r = inkernel ? tc_tower_launch(e->stream, w->d_maps, w->f_b_tower, act, n_dev, n_static, 20, fused >= 2, tgrid, 0, 0x7FFFFFFF, per, rel)
+                         : tc_tower_launch(e->stream, w->d_maps, w->f_b_tower, act, n_dev, n_static, 20, fused >= 2, tgrid, lo, lo + per, 0, rel);
             if (r) return set_err(e, AZ_ERR_CUDA, "tower launch failed");
         }
         x = 0;  // the fused tower works in place: block input and block output share a_buf[0], a_buf[1] holds conv1's output
@@ -392,10 +391,10 @@ int net_forward_bf16(az_engine* e, const int* n_dev, int n_static, float* policy
         if (sample) e->prof_launches += 2;
         const int y = (x + 1) % 3, z = (x + 2) % 3;
         r = tc_conv3x3_launch(e->stream, &w->map_a[x], &w->map_w_tower[2 * blk], 128, w->f_b_tower + (2 * blk) * 128, nullptr, w->a_buf[y],
-                              n_dev, n_static, 1, grid);
+                              n_dev, n_static, 1, grid, rel ? 32 : 0);
         if (r) return set_err(e, AZ_ERR_CUDA, "tc conv launch failed");
         r = tc_conv3x3_launch(e->stream, &w->map_a[y], &w->map_w_tower[2 * blk + 1], 128, w->f_b_tower + (2 * blk + 1) * 128, w->a_buf[x],
-                              w->a_buf[z], n_dev, n_static, 1, grid);
+                              w->a_buf[z], n_dev, n_static, 1, grid, rel ? 32 : 0);
         if (r) return set_err(e, AZ_ERR_CUDA, "tc conv launch failed");
         x = z;
     }

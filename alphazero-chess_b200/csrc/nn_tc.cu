@@ -504,7 +504,7 @@ conv_tower_kernel(const TowerParams prm) {
 }
 
 int tc_tower_launch(cudaStream_t stream, const CUtensorMap* maps_dev, const float* bias, void* const* act, const int* n_boards_dev,
-                    int n_boards_static, int n_layers, int stem, int grid, int tile_lo, int tile_hi, int range_tiles) {
+                    int n_boards_static, int n_layers, int stem, int grid, int tile_lo, int tile_hi, int range_tiles, int release_arrive) {
     static PerDeviceOnce once;
     if (once.first() &&
         cudaFuncSetAttribute(conv_tower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<2>::kTotal) != cudaSuccess)
@@ -516,9 +516,7 @@ int tc_tower_launch(cudaStream_t stream, const CUtensorMap* maps_dev, const floa
     for (int i = 0; i < 3; i++) p.act[i] = (__nv_bfloat16*)act[i];
     p.n_boards_ptr = n_boards_dev; p.n_boards_static = n_boards_static; p.n_layers = n_layers; p.stem = stem ? 1 : 0;
     p.tile_lo = tile_lo; p.tile_hi = tile_hi; p.range_tiles = range_tiles > 0 ? range_tiles : (1 << 30);
-    static int rel = -1;
-    if (rel < 0) { const char* v = getenv("AZ_TC_RELEASE_ARRIVE"); rel = v ? atoi(v) : 0; }
-    p.release_arrive = rel;
+    p.release_arrive = release_arrive;
     conv_tower_kernel<<<grid, kThreads2, ConvSmem<2>::kTotal, stream>>>(p);
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
@@ -576,9 +574,6 @@ int tc_conv3x3_launch(cudaStream_t stream, const CUtensorMap* in_map, const CUte
     }
     if (grid <= 0) grid = 148;
     grid &= ~1;  // CTA pairs
-    static int rel = -1;
-    if (rel < 0) { const char* v = getenv("AZ_TC_RELEASE_ARRIVE"); rel = v ? atoi(v) : 0; }
-    if (rel) dbg |= 32;
     if (cin == 64)
         conv3x3_tc2_kernel<1><<<grid, kThreads2, ConvSmem<1>::kTotal, stream>>>(*in_map, *w_map, bias, (const __nv_bfloat16*)residual,
                                                                                (__nv_bfloat16*)out, n_boards_dev, n_boards_static, relu, dbg);

@@ -10,8 +10,9 @@ int tc_make_act_map(CUtensorMap* map, const void* base, int channels, int max_bo
 int tc_make_weight_map(CUtensorMap* map, const void* base, int cin);
 // out = act( conv3x3(in) + bias (+ residual) ); the board count is read from n_boards_dev when non-null
 int tc_conv3x3_launch(cudaStream_t stream, const CUtensorMap* in_map, const CUtensorMap* w_map, int cin, const float* bias,
-                      const void* residual, void* out, const int* n_boards_dev, int n_boards_static, int relu, int grid, int dbg = 0);
+                      const void* residual, void* out, const int* n_boards_dev, int n_boards_static, int relu, int grid, int dbg = 0);   // dbg bit 5 (32): hand accumulators back with a release arrive
 // the 20-layer residual tower in one persistent launch; maps_dev = device array {act0, act1, act2, w[0..19]}
 int tc_tower_launch(cudaStream_t stream, const CUtensorMap* maps_dev, const float* bias, void* const* act, const int* n_boards_dev,
-                    int n_boards_static, int n_layers, int stem, int grid, int tile_lo = 0, int tile_hi = 0x7FFFFFFF, int range_tiles = 0);
+                    int n_boards_static, int n_layers, int stem, int grid, int tile_lo = 0, int tile_hi = 0x7FFFFFFF, int range_tiles = 0,
+                    int release_arrive = 0);
 }  // namespace azb

@@ -28,8 +28,9 @@ def test_two_devices_one_process():
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
 def test_sharded_generation_loop_two_ranks():
-    """BASELINE config 5 over NCCL: games sharded over two ranks, samples gathered into rank 0's replay buffer, training on
-    rank 0, weights broadcast back (tools/run_generations.py under torch.distributed.run)."""
+    """BASELINE config 5 over NCCL: games sharded over two ranks (exactly 128 complete games each), samples all-gathered device
+    to device into both replicas of the replay buffer, data-parallel training with a gradient all-reduce
+    (tools/run_generations.py under torch.distributed.run).  The replicas (weights + replay entries) must stay identical."""
     import json
     import os
     import subprocess
@@ -37,9 +38,16 @@ def test_sharded_generation_loop_two_ranks():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", str(29700 + os.getpid() % 200), os.path.join(root, "tools", "run_generations.py"),
-           "--games", "128", "--sims", "32", "--iterations", "2", "--min-replay", "1000", "--eval-games", "0"]
+           "--games", "128", "--sims", "32", "--iterations", "2", "--min-replay", "1000", "--eval-games", "0", "--all-ranks"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-3000:]
     lines = [json.loads(l) for l in out.stdout.splitlines() if l.startswith("{")]
-    assert len(lines) == 2 and all(m["n_ranks"] == 2 and m["trained"] for m in lines)
-    assert lines[0]["positions"] > 2 * 128 * 20 and lines[0]["replay_buffer_size"] == lines[0]["new_unique_states"]
+    assert len(lines) == 4 and all(m["n_ranks"] == 2 and m["trained"] and m["games"] == 256 for m in lines)
+    for it in (0, 1):
+        a, b = [m for m in lines if m["iteration"] == it]
+        assert {a["rank"], b["rank"]} == {0, 1}
+        assert a["replica_digest"] == b["replica_digest"], (it, a, b)
+        assert a["positions"] == b["positions"] > 2 * 128 * 20 and a["replay_buffer_size"] == b["replay_buffer_size"]
+        assert a["sample_gather"].startswith("device")
+    first = [m for m in lines if m["iteration"] == 0][0]
+    assert first["replay_buffer_size"] == first["new_unique_states"]
