@@ -2,7 +2,10 @@
 //   stage 1  [64 squares x 128 ch] x [128 x 40]   policy_conv_1 (32) and value_conv (8), BatchNorm folded, ReLU
 //   stage 2  [64 co x 32] x [32 x 64 squares]     policy_conv_2, kept transposed so that logits land as [co][square]
 //   softmax over the 4096 logits in registers (two warps share a board, 32 squares each), probabilities written as 32-byte sectors
-//   value    [8 boards x 512] x [512 x 64] -> ReLU -> 64 -> 1 -> tanh, one board group per block
+//   value    [32 boards x 512] x [512 x 64] -> ReLU -> 64 -> 1 -> tanh, once per group of four rounds of a block
+// The policy part of a board needs only its own pair of warps (named barrier of 64 threads), so the pairs of a block run
+// through the rounds of a group without block-wide barriers; only the value head, which batches the boards of the whole group
+// into two M = 16 MMA tiles, synchronises the block (ncu of the first version: "barrier" was the top stall reason).
 // The heads are 0.3 % of the network's FLOPs; they use mma.sync (a warp reads its rows straight from global memory, no shared-memory staging of
 // the activations) while the 99 % in the tower runs on tcgen05 (nn_tc.cu).
 #include "nn.h"
@@ -14,8 +17,10 @@ namespace azb {
 constexpr int HW40_PITCH = 136;  // bf16 elements per row of W40 in shared memory (128 + 8: conflict-free fragment loads)
 constexpr int HW2_PITCH = 40;    // 32 + 8
 constexpr int HV1_PITCH = 520;   // 512 + 8
-constexpr int HEXP_PITCH = 68;   // floats per output-channel row of the per-warp softmax tile (64 + 4)
-constexpr int HEADS_DYN_SMEM = 8 * 64 * HEXP_PITCH * 4;
+constexpr int HEXP_PITCH = 72;   // floats per output-channel row of the per-board softmax tile: 64 + 8, so that the float2 stores of
+                                 // a half-warp (rows g = 0..3, columns 2 tig) hit 16 distinct bank pairs (68 gave two-way conflicts)
+constexpr int HEADS_GROUP = 4;   // rounds of boards whose value heads are evaluated together (32 board rows = two M = 16 tiles)
+constexpr int HEADS_DYN_SMEM = 8 * 64 * HEXP_PITCH * 4 + HEADS_GROUP * 8 * HV1_PITCH * 2;
 
 __device__ __forceinline__ void mma_bf16_16816(float* d, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
     asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -37,11 +42,11 @@ k_heads_mma(const __nv_bfloat16* __restrict__ tower, const __nv_bfloat16* __rest
             const __nv_bfloat16* __restrict__ wp2, const float* __restrict__ bp2, const __nv_bfloat16* __restrict__ wl1t,
             const float* __restrict__ bl1, const float* __restrict__ wl2, const float* __restrict__ bl2, float* __restrict__ policy_out,
             float* __restrict__ value_out, const int* __restrict__ n_dev, int n_static, HeadScatter sc, int bpi) {
-    extern __shared__ float s_exp_all[];  // [8 boards][64 co][HEXP_PITCH]: exp(logit - max) of the board in flight
+    extern __shared__ float s_exp_all[];  // [8 boards][64 co][HEXP_PITCH]: exp(logit - max) of the board in flight, then s_v1
     __shared__ __align__(16) __nv_bfloat16 s_w40[40 * HW40_PITCH];
     __shared__ __align__(16) __nv_bfloat16 s_w2[64 * HW2_PITCH];
-    __shared__ __align__(16) __nv_bfloat16 s_v1[8 * HV1_PITCH];
-    __shared__ float s_b40[40], s_b2[64], s_red[2][8][2], s_hid[2][8][64], s_vsum[16];
+    __nv_bfloat16* s_v1 = reinterpret_cast<__nv_bfloat16*>(s_exp_all + 8 * 64 * HEXP_PITCH);   // [HEADS_GROUP * 8 board rows][HV1_PITCH]
+    __shared__ float s_b40[40], s_b2[64], s_red[2][8][2], s_hid[2][HEADS_GROUP * 8][64], s_vsum[HEADS_GROUP][16];
     const int n = n_dev ? *n_dev : n_static;
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31, g = lane >> 2, tig = lane & 3;
     const int bs = warp >> 1, h = warp & 1;  // board slot in the block, square half
@@ -56,9 +61,13 @@ k_heads_mma(const __nv_bfloat16* __restrict__ tower, const __nv_bfloat16* __rest
 
     // bpi = boards per block and round (<= 8): the host picks it so that the last round is full (4096 boards on 148 blocks:
     // 4 rounds of 7 instead of 3.46 -> 4 rounds of 8)
-    for (int base = blockIdx.x * bpi; base < n; base += gridDim.x * bpi) {
+    const int round_stride = gridDim.x * bpi;
+    for (int base0 = blockIdx.x * bpi; base0 < n; base0 += round_stride * HEADS_GROUP) {
+      for (int r = 0; r < HEADS_GROUP; r++) {
+        const int base = base0 + r * round_stride;
         const int b = base + bs;
         const bool active = bs < bpi && b < n;
+        __nv_bfloat16* vr = s_v1 + (r * 8 + bs) * HV1_PITCH;   // this board's row of the value head's input
         if (active) {
             // ---------------- stage 1: D1[square][40] for this warp's 32 squares
             float d1[2][5][4];
@@ -111,7 +120,6 @@ k_heads_mma(const __nv_bfloat16* __restrict__ tower, const __nv_bfloat16* __rest
                     d1[mt][nt][2] = fmaxf(d1[mt][nt][2] + bb0, 0.0f);
                     d1[mt][nt][3] = fmaxf(d1[mt][nt][3] + bb1, 0.0f);
                 }
-                __nv_bfloat16* vr = s_v1 + bs * HV1_PITCH;
                 const int sq = h * 32 + mt * 16 + g, c = tig * 2;
                 vr[c * 64 + sq] = __float2bfloat16_rn(d1[mt][4][0]);
                 vr[(c + 1) * 64 + sq] = __float2bfloat16_rn(d1[mt][4][1]);
@@ -201,38 +209,52 @@ k_heads_mma(const __nv_bfloat16* __restrict__ tower, const __nv_bfloat16* __rest
                     }
             }
         } else {
-            for (int i = h * 32 + lane; i < 512; i += 64) s_v1[bs * HV1_PITCH + i] = __float2bfloat16_rn(0.0f);
+            for (int i = h * 32 + lane; i < 512; i += 64) vr[i] = __float2bfloat16_rn(0.0f);
         }
-        // ---------------- value head: warp w sums K half (w >> 3) of hidden[board][8(w&7) .. +7] (rows 8..15 of the M=16 tile unused)
+      }
+        // ---------------- value head of the group's 32 board rows (row = round * 8 + slot): warp w sums K half (w >> 3) of
+        // hidden[row][8(w&7) .. +7]; M tile m holds rows 16m .. 16m + 15 (rounds 2m and 2m + 1)
         {
-            float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            float acc[2][4] = {{0.0f, 0.0f, 0.0f, 0.0f}, {0.0f, 0.0f, 0.0f, 0.0f}};
             const int hw = warp & 7, kh = warp >> 3;
             const uint32_t* W = reinterpret_cast<const uint32_t*>(wl1t + (size_t)(hw * 8 + g) * 512) + kh * 128;
-            const uint32_t* V = reinterpret_cast<const uint32_t*>(s_v1 + g * HV1_PITCH) + kh * 128;
             // the weight fragments do not depend on the boards: requested before the barrier (the policy accumulators are
-            // dead by now), so their L2 latency hides behind the wait for the slowest warp
+            // dead by now), so their L2 latency hides behind the wait for the slowest pair
             uint32_t wf[16][2];
 #pragma unroll
             for (int ks = 0; ks < 16; ks++) { wf[ks][0] = __ldg(W + ks * 8 + tig); wf[ks][1] = __ldg(W + ks * 8 + tig + 4); }
             __syncthreads();
 #pragma unroll
-            for (int ks = 0; ks < 16; ks++) {
-                const uint32_t a0 = V[ks * 8 + tig], a2 = V[ks * 8 + tig + 4];
-                mma_bf16_16816(acc, a0, 0u, a2, 0u, wf[ks][0], wf[ks][1]);
+            for (int m = 0; m < 2; m++) {
+                const uint32_t* V0 = reinterpret_cast<const uint32_t*>(s_v1 + (16 * m + g) * HV1_PITCH) + kh * 128;
+                const uint32_t* V1 = reinterpret_cast<const uint32_t*>(s_v1 + (16 * m + g + 8) * HV1_PITCH) + kh * 128;
+#pragma unroll
+                for (int ks = 0; ks < 16; ks++)
+                    mma_bf16_16816(acc[m], V0[ks * 8 + tig], V1[ks * 8 + tig], V0[ks * 8 + tig + 4], V1[ks * 8 + tig + 4], wf[ks][0], wf[ks][1]);
+                const int hn = hw * 8 + tig * 2;   // acc[0], acc[1]: row 16m + g; acc[2], acc[3]: row 16m + g + 8; hidden units hn, hn + 1
+                s_hid[kh][16 * m + g][hn] = acc[m][0];
+                s_hid[kh][16 * m + g][hn + 1] = acc[m][1];
+                s_hid[kh][16 * m + g + 8][hn] = acc[m][2];
+                s_hid[kh][16 * m + g + 8][hn + 1] = acc[m][3];
             }
-            const int hn = hw * 8 + tig * 2;   // acc[0], acc[1]: board g, hidden units hn, hn + 1
-            s_hid[kh][g][hn] = acc[0];
-            s_hid[kh][g][hn + 1] = acc[1];
         }
         __syncthreads();
-        {   // 8 boards x 64 hidden units on 512 threads: ReLU(sum of the two K halves + bias) * w2, reduced per board
-            const int vb = t >> 6, hn = t & 63;
-            float part = fmaxf(s_hid[0][vb][hn] + s_hid[1][vb][hn] + bl1[hn], 0.0f) * wl2[hn];
-            for (int d = 16; d; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
-            if (lane == 0) s_vsum[warp] = part;
+        {   // 32 rows x 64 hidden units on 512 threads: ReLU(sum of the two K halves + bias) * w2, reduced per row
+            const int hn = t & 63;
+            const float b1 = bl1[hn], w2 = wl2[hn];
+#pragma unroll
+            for (int r = 0; r < HEADS_GROUP; r++) {
+                const int row = r * 8 + (t >> 6);
+                float part = fmaxf(s_hid[0][row][hn] + s_hid[1][row][hn] + b1, 0.0f) * w2;
+                for (int d = 16; d; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+                if (lane == 0) s_vsum[r][warp] = part;
+            }
         }
         __syncthreads();
-        if (t < bpi && base + t < n) value_out[base + t] = tanhf(bl2[0] + s_vsum[2 * t] + s_vsum[2 * t + 1]);
+        if (t < HEADS_GROUP * 8) {
+            const int r = t >> 3, slot = t & 7, board = base0 + r * round_stride + slot;
+            if (slot < bpi && board < n) value_out[board] = tanhf(bl2[0] + s_vsum[r][2 * slot] + s_vsum[r][2 * slot + 1]);
+        }
     }
 }
 
