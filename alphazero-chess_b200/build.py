@@ -55,6 +55,8 @@ def _stamp(target, digest):
 
 
 def build(verbose=False, force=False):
+    # AZ_NVCC_DEFINES="-DAZ_ADV_TIMING" builds the instrumented search kernel (tools/adv_timing.sh); part of the content hash
+    extra_defs = os.environ.get("AZ_NVCC_DEFINES", "").split()
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     inc = os.path.join(HERE, "..", "include")
     headers += [os.path.join(inc, f) for f in os.listdir(inc) if f.endswith((".h", ".hpp"))]
@@ -64,8 +66,8 @@ def build(verbose=False, force=False):
         s = os.path.join(CSRC, src)
         o = os.path.join(CSRC, src.rsplit(".", 1)[0] + ".o")
         objs.append(o)
-        cmd = ["nvcc"] + ARCH + COMMON + extra + ["-c", s, "-o", o]
-        d = _digest([s] + headers, ARCH + COMMON[:4] + extra)
+        cmd = ["nvcc"] + ARCH + COMMON + extra + extra_defs + ["-c", s, "-o", o]
+        d = _digest([s] + headers, ARCH + COMMON[:4] + extra + extra_defs)
         digests.append(d)
         if force or not _up_to_date(o, d):
             if verbose:

@@ -789,6 +789,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB * 4 / WARPS) k_advance(const 
 #ifdef AZ_ADV_TIMING
         t_acc[7] = (unsigned long long)(clock64() - t_start);
         for (int k = 0; k < 8; k++) atomicAdd(&ct[8 + k], t_acc[k]);
+        atomicAdd(&ct[24 + min(15, (int)(t_acc[7] >> 12))], 1ULL);
 #endif
     }
 }
@@ -1247,6 +1248,11 @@ int az_selfplay_step(az_engine* e, int waves, az_selfplay_stats* out) {
 #ifdef AZ_ADV_TIMING
         unsigned long long tc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (int i = 0; i < STAT_STRIPES * STAT_WIDTH; i++) if (i % STAT_WIDTH >= 8 && i % STAT_WIDTH < 16) tc[i % STAT_WIDTH - 8] += stripes[i];
+        unsigned long long hist[16] = {0};
+        for (int i = 0; i < STAT_STRIPES * STAT_WIDTH; i++) if (i % STAT_WIDTH >= 24) hist[i % STAT_WIDTH - 24] += stripes[i];
+        fprintf(stderr, "azb: k_advance warp-time histogram (buckets of 4096 clocks):");
+        for (int k = 0; k < 16; k++) fprintf(stderr, " %llu", hist[k]);
+        fprintf(stderr, "\n");
         fprintf(stderr, "azb: k_advance phase clocks per warp-wave: consume %.0f select %.0f child %.0f rules %.0f create %.0f submit %.0f move %.0f total %.0f\n",
                 (double)tc[0] / ((double)st->prm.n_games * waves), (double)tc[1] / ((double)st->prm.n_games * waves), (double)tc[2] / ((double)st->prm.n_games * waves),
                 (double)tc[3] / ((double)st->prm.n_games * waves), (double)tc[4] / ((double)st->prm.n_games * waves), (double)tc[5] / ((double)st->prm.n_games * waves),

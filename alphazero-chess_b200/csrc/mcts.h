@@ -71,7 +71,8 @@ struct Counters {
 
 constexpr unsigned long long EDGE_NO_CHILD = ~0ULL;
 constexpr int STAT_STRIPES = 64;
-constexpr int STAT_WIDTH = 24;    // per stripe: 0..7 the statistics fields of Counters, 8..15 AZ_ADV_TIMING phase clocks, 16 cache evictions
+constexpr int STAT_WIDTH = 40;    // per stripe: 0..7 the statistics fields of Counters, 8..15 AZ_ADV_TIMING phase clocks, 16 cache evictions,
+                                  // 24..39 AZ_ADV_TIMING histogram of a warp's time in k_advance (buckets of 4096 clocks)
 
 struct SearchPtrs {
     // nodes [G * node_cap]
