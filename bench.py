@@ -367,10 +367,17 @@ def peaked_weights(az, local_rank, seconds_budget=40.0):
 
 
 def eval_avoidance_leg(az, local_rank, G, S, peak_tf):
-    w, how = peaked_weights(az, local_rank)
-    out = {"network": how}
-    for label, log2 in (("cache_off", 0), ("cache_on", 24)):
-        eng = az.Engine(device=local_rank, max_games=G, num_simulations=S, seed=42, cache_log2=log2)
+    """Self-play as in the timed region but with the evaluation cache on (2^24 entries, 17 GB), for three networks: the
+    random-init one of the headline, a briefly trained one, and the trained one with its policy logits x 4 (a stand-in for the
+    peaked priors of a strong network).  sims/s, evals/s and the avoided fraction are reported separately; the headline
+    `value` keeps the cache off (every simulation pays a network evaluation)."""
+    w_trained, how = peaked_weights(az, local_rank)
+    names = az.weight_names()
+    w_sharp = [a * np.float32(4.0) if n.startswith("policy_conv_2.") else a for a, n in zip(w_trained, names)]
+    out = {"network": how, "cache_log2_slots": 24,
+           "note": "3 timed plies after 2 warm-up plies, same games / sims as the headline; profiles/r2_avoidance.md has the longer sweep"}
+    for label, w in (("random_init", az.random_weights(seed=42)), ("trained", w_trained), ("trained_policy_logits_x4", w_sharp)):
+        eng = az.Engine(device=local_rank, max_games=G, num_simulations=S, seed=42, cache_log2=24)
         eng.load_weights(w)
         eng.selfplay_begin(G, first_game_id=0)
         eng.selfplay_step(2 * S)
@@ -383,7 +390,7 @@ def eval_avoidance_leg(az, local_rank, G, S, peak_tf):
         out[label] = {"sims_per_sec": d["simulations"] / (ms * 1e-3), "nn_evals_per_sec": d["evaluations"] / (ms * 1e-3),
                       "eval_avoidance_ratio": 1.0 - d["evaluations"] / max(d["simulations"], 1),
                       "cache_hits": int(d["cache_hits"]), "cache_evictions": int(d["cache_evictions"]), "terminal_leaves": int(d["terminal_leaves"]),
-                      "mean_leaf_depth": d["sum_leaf_depth"] / max(d["simulations"], 1), "cache_log2_slots": log2,
+                      "mean_leaf_depth": d["sum_leaf_depth"] / max(d["simulations"], 1),
                       "nn_tensor_frac": d["evaluations"] * az.FLOPS_PER_EVAL / (ms * 1e-3) / 1e12 / peak_tf, "waves": 3 * S}
         eng.close()
     return out
