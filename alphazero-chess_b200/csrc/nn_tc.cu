@@ -43,7 +43,18 @@ struct ConvSmem {
 // and the shared-memory operand bandwidth of the single-CTA kernel and doubles the work per issued instruction
 // (the single-CTA kernel was bound by the issue rate of its N=64 MMAs: profiles/r1_conv_ablation.md).
 constexpr int kTmemCols2 = 256;  // 2 accumulator stages x 128 fp32 columns
-constexpr int kThreads2 = 320;   // warp 0 TMA, warp 1 MMA/TMEM, warps 2-9 epilogue (two per TMEM lane quarter)
+// Epilogue warps per CTA: kEpiWarps / 4 per TMEM lane quarter, each owning 128 / (kEpiWarps / 4) accumulator columns of its 32 rows.
+// Measured (profiles/r2_ab.md): 16 warps (32 columns = one tcgen05.ld each) make the tower 3.4 % SLOWER than 8 warps (64 columns) and leave
+// the input convolution unchanged, so 8 is the default; -DAZ_EPI_WARPS=16 rebuilds the experiment.
+#ifndef AZ_EPI_WARPS
+#define AZ_EPI_WARPS 8
+#endif
+constexpr int kEpiWarps = AZ_EPI_WARPS;
+constexpr int kEpiCols = 128 / (kEpiWarps / 4);   // accumulator columns per epilogue warp
+constexpr int kEpiChunks = kEpiCols / 32;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads2 = 64 + kEpiThreads;   // warp 0 TMA, warp 1 MMA/TMEM, then the epilogue warps
+static_assert(kEpiWarps == 8 || kEpiWarps == 16, "epilogue warps: 8 or 16");
 
 template <int HALVES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
@@ -76,7 +87,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
         tma_prefetch_desc(&w_map);
         for (int i = 0; i < NS; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
         for (int i = 0; i < S::kWTiles; i++) mbar_init(&wfull_bar[i], 1);
-        for (int i = 0; i < 2; i++) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 16); }
+        for (int i = 0; i < 2; i++) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 2 * kEpiWarps); }
         fence_barrier_init();
     }
     if (threadIdx.x >= 64 && threadIdx.x < 192) bias_s[threadIdx.x - 64] = bias[threadIdx.x - 64];
@@ -153,9 +164,9 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
             }
         }
     } else {
-        // ------------------------------------------------ epilogue (8 warps: TMEM lane quarter q, column half ch)
+        // ------------------------------------------------ epilogue (TMEM lane quarter q, column group cg of kEpiCols columns)
         const int q = warp & 3;
-        const int ch = (warp - 2) >> 2;
+        const int cg = (warp - 2) >> 2;
         const int row = q * 32 + lane;
         const int h = row >> 4, b = (row >> 3) & 1, w = row & 7;
         int lt = 0;
@@ -163,7 +174,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
             const int acc = lt & 1; const uint32_t accphase = (lt >> 1) & 1;
             const int board = t * 4 + (int)rank * 2 + b;
             const bool valid = board < n_boards;
-            const size_t off = ((size_t)board * 64 + h * 8 + w) * 128 + ch * 64;
+            const size_t off = ((size_t)board * 64 + h * 8 + w) * 128 + cg * kEpiCols;
             if (dbg & 4) {
                 mbar_wait(&tfull_bar[acc], accphase, 15);
                 tc_fence_before();
@@ -172,21 +183,21 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
                 continue;
             }
             const bool has_res = residual != nullptr && valid && !(dbg & 8);
-            // the 128-byte residual half-row is requested before waiting for the accumulator (4 x 32-byte loads in flight)
-            uint32_t res[32];
+            // the residual part of the row is requested before waiting for the accumulator (32-byte loads in flight)
+            uint32_t res[kEpiCols / 2];
             if (has_res) {
 #pragma unroll
-                for (int i = 0; i < 4; i++) ld_global_v8(residual + off + i * 16, &res[i * 8]);
+                for (int i = 0; i < kEpiCols / 16; i++) ld_global_v8(residual + off + i * 16, &res[i * 8]);
             }
             mbar_wait(&tfull_bar[acc], accphase, 15);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 128 + ch * 64;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 128 + cg * kEpiCols;
 #pragma unroll
-            for (int chunk = 0; chunk < 2; chunk++) {
+            for (int chunk = 0; chunk < kEpiChunks; chunk++) {
                 uint32_t r[32];
                 tmem_ld32(taddr + chunk * 32, r);
                 tmem_ld_wait();
-                if (chunk == 1) {
+                if (chunk == kEpiChunks - 1) {
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) { if (dbg & 32) mbar_arrive_cluster(&tempty_bar[acc], 0); else mbar_arrive_cluster_relaxed(&tempty_bar[acc], 0); }
@@ -198,7 +209,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
 #pragma unroll
                         for (int j = 0; j < 8; j++) {
                             const int c = v * 16 + j * 2;
-                            const float2 bb = *reinterpret_cast<const float2*>(&bias_s[ch * 64 + chunk * 32 + c]);
+                            const float2 bb = *reinterpret_cast<const float2*>(&bias_s[cg * kEpiCols + chunk * 32 + c]);
                             float x0 = __uint_as_float(r[c]) + bb.x;
                             float x1 = __uint_as_float(r[c + 1]) + bb.y;
                             if (has_res) {
@@ -264,7 +275,7 @@ conv_tower_kernel(const TowerParams prm) {
     uint64_t* tfull_bar = wempty_bar + 6;                               // 2    (per CTA)
     uint64_t* tempty_bar = tfull_bar + 2;                               // 2    (leader)
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-    volatile uint32_t* epi_done = reinterpret_cast<volatile uint32_t*>(tmem_ptr_s + 4);  // 8 per-warp tile counters
+    volatile uint32_t* epi_done = reinterpret_cast<volatile uint32_t*>(tmem_ptr_s + 4);  // kEpiWarps per-warp tile counters
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -287,10 +298,10 @@ conv_tower_kernel(const TowerParams prm) {
     if (threadIdx.x == 0) {
         for (int i = 0; i < NS; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
         for (int i = 0; i < 6; i++) { mbar_init(&wfull_bar[i], 1); mbar_init(&wempty_bar[i], 1); }
-        for (int i = 0; i < 2; i++) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 16); }
+        for (int i = 0; i < 2; i++) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 2 * kEpiWarps); }
         fence_barrier_init();
     }
-    if (threadIdx.x < 8) epi_done[threadIdx.x] = 0;
+    if (threadIdx.x < kEpiWarps) epi_done[threadIdx.x] = 0;
     float* bias_s = reinterpret_cast<float*>(misc + 512);  // [2][128]: bias of the current layer, double buffered by layer parity
     if (warp == 1) tmem2_alloc(tmem_ptr_s, kTmemCols2);
     tc_fence_before();
@@ -319,7 +330,7 @@ conv_tower_kernel(const TowerParams prm) {
                     const uint32_t need = cum + (uint32_t)((L - 1) * T + i + 1);
                     long long t0 = clock64();
                     for (;;) {
-                        bool ok = lane >= 8 || epi_done[lane & 7] >= need;
+                        bool ok = lane >= kEpiWarps || epi_done[lane & (kEpiWarps - 1)] >= need;
                         if (__all_sync(0xffffffffu, ok)) break;
                         if (clock64() - t0 > 4000000000LL) { if (lane == 0) printf("azb: tower epilogue wait timeout\n"); __trap(); }
                     }
@@ -404,9 +415,9 @@ conv_tower_kernel(const TowerParams prm) {
             }
         }
     } else {
-        // ------------------------------------------------ epilogue (8 warps: TMEM lane quarter q, column half ch)
+        // ------------------------------------------------ epilogue (TMEM lane quarter q, column group cg of kEpiCols columns)
         const int q = warp & 3;
-        const int ch = (warp - 2) >> 2;
+        const int cg = (warp - 2) >> 2;
         const int row = q * 32 + lane;
         const int h = row >> 4, b = (row >> 3) & 1, w = row & 7;
         int lt = 0, g = 0;
@@ -425,22 +436,22 @@ conv_tower_kernel(const TowerParams prm) {
             // tile t, and no other tile's convolution reads these boards: the block output can replace the block input in place,
             // which keeps the tower's footprint at two activation buffers (L2 residency)
             const __nv_bfloat16* residual = blk_second ? prm.act[0] : nullptr;
-            // the 8 epilogue warps switch layers together: whoever arrives refills the buffer last used two layers ago
+            // the epilogue warps switch layers together: whoever arrives refills the buffer last used two layers ago
             if (threadIdx.x - 64 < 128)
                 bias_s[(g & 1) * 128 + threadIdx.x - 64] = prm.bias[(layer >= 0 ? layer : prm.n_layers) * 128 + threadIdx.x - 64];
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            const float* bias = bias_s + (g & 1) * 128 + ch * 64;
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+            const float* bias = bias_s + (g & 1) * 128 + cg * kEpiCols;
             for (int i = 0; i < T; i++, lt++) {
                 const int t = first_tile + i * tile_step;
                 const int acc = lt & 1; const uint32_t accphase = (lt >> 1) & 1;
                 const int board = t * 4 + (int)rank * 2 + b;
                 const bool valid = board < n_boards;
-                const size_t off = ((size_t)board * 64 + h * 8 + w) * 128 + ch * 64;
+                const size_t off = ((size_t)board * 64 + h * 8 + w) * 128 + cg * kEpiCols;
                 const bool has_res = residual != nullptr && valid;
-                uint32_t res[32];
+                uint32_t res[kEpiCols / 2];
                 if (has_res) {
 #pragma unroll
-                    for (int k = 0; k < 4; k++) ld_global_v8(residual + off + k * 16, &res[k * 8]);
+                    for (int k = 0; k < kEpiCols / 16; k++) ld_global_v8(residual + off + k * 16, &res[k * 8]);
                 }
                 mbar_wait(&tfull_bar[acc], accphase, 26);
                 tc_fence_after();
@@ -449,13 +460,13 @@ conv_tower_kernel(const TowerParams prm) {
                     __syncwarp();
                     if (lane == 0) { __threadfence(); epi_done[warp - 2] = done; }
                 }
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 128 + ch * 64;
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 128 + cg * kEpiCols;
 #pragma unroll
-                for (int chunk = 0; chunk < 2; chunk++) {
+                for (int chunk = 0; chunk < kEpiChunks; chunk++) {
                     uint32_t r[32];
                     tmem_ld32(taddr + chunk * 32, r);
                     tmem_ld_wait();
-                    if (chunk == 1) {
+                    if (chunk == kEpiChunks - 1) {
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) { if (prm.release_arrive) mbar_arrive_cluster(&tempty_bar[acc], 0); else mbar_arrive_cluster_relaxed(&tempty_bar[acc], 0); }
