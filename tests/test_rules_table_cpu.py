@@ -33,3 +33,14 @@ def test_ep_plane():
         if case["plane16"]:
             want[case["plane16"][0], case["plane16"][1]] = 1.0
         assert np.array_equal(planes[16], want), (case["fen"], case["why"])
+
+
+def _uci(mv):
+    f, t, promo = mv & 63, (mv >> 6) & 63, (mv >> 12) & 7
+    return "abcdefgh"[f & 7] + str((f >> 3) + 1) + "abcdefgh"[t & 7] + str((t >> 3) + 1) + ["", "n", "b", "r", "q"][promo]
+
+
+def test_move_order():
+    for case in RULES["move_order"]:
+        mv, _ = orc.legal_moves(orc.from_fen(case["fen"]))
+        assert [_uci(int(m)) for m in mv] == case["moves"], (case["fen"], case["why"])

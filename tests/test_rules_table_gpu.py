@@ -66,3 +66,15 @@ def test_ep_plane(eng):
         if case["plane16"]:
             want[case["plane16"][0], case["plane16"][1]] = 1.0
         assert np.array_equal(planes[16], want), (case["fen"], case["why"])
+
+
+def test_move_order(eng):
+    def uci(mv):
+        f, t, promo = mv & 63, (mv >> 6) & 63, (mv >> 12) & 7
+        return "abcdefgh"[f & 7] + str((f >> 3) + 1) + "abcdefgh"[t & 7] + str((t >> 3) + 1) + ["", "n", "b", "r", "q"][promo]
+
+    cases = RULES["move_order"]
+    pos = np.array([az.position_from_fen(c["fen"]) for c in cases], az.POSITION_DTYPE)
+    moves, _, count = eng.movegen(pos)
+    for i, c in enumerate(cases):
+        assert [uci(int(m)) for m in moves[i, : count[i]]] == c["moves"], (c["fen"], c["why"])
