@@ -679,6 +679,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB * 4 / WARPS) k_advance(const 
     Ctx x{prm, ptr, &shared[threadIdx.x >> 5], g, (int)(threadIdx.x & 31), (size_t)g * prm.node_cap, (size_t)g * prm.edge_cap,
           ptr.ctl[g], 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (x.c.status != 0 && x.c.status != 4) return;
+    if (!prm.consume && x.c.pending_node >= 0) return;   // extra pass: this game already waits for the network
 
     ADV_T0();
     // ---- 0. game over, samples staged: publish now if the host has drained the queue, else stay parked
@@ -954,7 +955,8 @@ int search_create(az_engine* e) {
     // With the evaluation cache a hit completes a simulation without the network, so games may go further per wave.
     p.mode = 0; p.max_iters = c.cache_log2 > 0 ? 4 : 2;
     if (const char* v = getenv("AZ_ADV_MAX_ITERS")) p.max_iters = std::max(1, atoi(v));
-    p.last_game_id = 0; p.cache_epoch = 0;
+    p.last_game_id = 0; p.cache_epoch = 0; p.consume = 1;
+    if (const char* v = getenv("AZ_ADV_PASSES")) { st->adv_passes = std::max(1, std::min(4, atoi(v))); st->adv_passes_fixed = 1; }
     if (!(c.temperature > 0.0f)) return set_err(e, AZ_ERR_INVALID_ARGUMENT, "temperature must be positive");
     p.inv_temperature = 1.0f / c.temperature;
     p.fp32_planes = c.precision == 1 ? 1 : 0;
@@ -1044,6 +1046,13 @@ static int run_wave(az_engine* e, SearchState* st) {
         cudaEventCreate(&e->prof_adv_event);
         cudaEventRecord(e->prof_adv_event, e->stream);
     }
+    // With a high cache hit rate many games complete their max_iters network-free simulations without needing the network;
+    // extra passes let exactly those games go on (everybody else returns at once), so the batch of the wave fills up and the
+    // marginal simulations cost a 40 us kernel instead of a share of the 1.1 ms network wave.  az_selfplay_step adapts the
+    // number of passes to the avoided fraction it measured in its previous call.
+    const int passes = st->prm.mode == 1 && st->prm.cache_mask ? st->adv_passes : 1;
+    for (int pass = 0; pass < passes; pass++) {
+    st->prm.consume = pass == 0 ? 1 : 0;
     e->n_launches++;
     const int minb = e->knobs.adv_minb;
     // groups of four warps per SM (register bound): 3 -> 162 registers, 4 -> 128, 5 -> 96, 6 -> 80, 7 -> 72 with 216 bytes of
@@ -1056,6 +1065,8 @@ static int run_wave(az_engine* e, SearchState* st) {
         case 7: k_advance<7><<<blocks, WARPS * 32, 0, e->stream>>>(st->prm, st->ptr); break;
         default: k_advance<3><<<blocks, WARPS * 32, 0, e->stream>>>(st->prm, st->ptr); break;
     }
+    }
+    st->prm.consume = 1;
     AZ_CUDA(e, cudaGetLastError());
     return evaluate_batch(e, st);
 }
@@ -1182,6 +1193,8 @@ int az_selfplay_begin_n(az_engine* e, int n_games, uint64_t first_game_id, uint6
     st->prm.n_games = n_games; st->prm.mode = 1; st->prm.S = e->cfg.num_simulations;
     st->prm.last_game_id = total_games ? first_game_id + total_games : 0;
     st->wave_counter = 0; st->prm.cache_epoch = 0;
+    st->last_sims = 0; st->last_evals = 0;
+    if (!st->adv_passes_fixed) st->adv_passes = 1;
     if (st->prm.cache_mask)  // a new cache per generation (training.rs:342)
         AZ_CUDA(e, cudaMemsetAsync(q.cache_state, 0, ((size_t)st->prm.cache_mask + 1) * sizeof(uint32_t), e->stream));
     Counters zero;
@@ -1261,6 +1274,14 @@ int az_selfplay_step(az_engine* e, int waves, az_selfplay_stats* out) {
         c.simulations = sum[0]; c.positions = sum[1]; c.evaluations = sum[2]; c.cache_hits = sum[3];
         c.terminal_leaves = sum[4]; c.games_finished = sum[5]; c.sum_leaf_depth = sum[6]; c.sum_edges = sum[7];
     }
+    if (!st->adv_passes_fixed && st->prm.cache_mask && waves > 0) {   // passes for the NEXT call from this call's avoided fraction
+        const double ds = (double)(c.simulations - st->last_sims), de = (double)(c.evaluations - st->last_evals);
+        if (ds > 0) {
+            const double avoided = 1.0 - de / ds;
+            st->adv_passes = avoided > 0.5 ? 3 : avoided > 0.25 ? 2 : 1;
+        }
+    }
+    st->last_sims = c.simulations; st->last_evals = c.evaluations;
     if (out) {
         out->simulations = c.simulations; out->positions = c.positions; out->evaluations = c.evaluations; out->cache_hits = c.cache_hits;
         out->terminal_leaves = c.terminal_leaves; out->games_finished = c.games_finished; out->sum_leaf_depth = c.sum_leaf_depth;

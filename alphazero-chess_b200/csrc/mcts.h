@@ -42,6 +42,8 @@ struct SearchParams {
     unsigned long long last_game_id;  // self-play: game ids >= this are not started (0: games restart forever)
     float inv_temperature;            // 1 / TEMPERATURE as f32 (tree.rs:174)
     uint32_t cache_epoch;             // coarse clock (one tick per ply of self-play) used to age cache entries, 6 bits
+    int consume;                      // 1: first k_advance pass of a wave (evaluations of the previous wave are consumed);
+                                      // 0: an extra pass -- only games that still have no request in flight run
 };
 
 // Position -> (legal-move priors, value) cache: the moka Cache<Fen, CacheEntry> of training.rs:342 / tree.rs:214-218.
@@ -117,6 +119,9 @@ struct SearchState {
     int G = 0;
     bool selfplay_active = false;
     unsigned long long cache_evictions = 0;
+    int adv_passes = 1;                    // k_advance launches per wave (see run_wave)
+    int adv_passes_fixed = 0;              // AZ_ADV_PASSES: no adaptation
+    unsigned long long last_sims = 0, last_evals = 0;   // counters at the end of the previous az_selfplay_step (adaptation)
     unsigned long long wave_counter = 0;   // self-play waves since az_selfplay_begin (cache epoch = wave_counter / S)
     unsigned long long* d_noise_ids = nullptr;  // [max_games] az_search staging (no allocation per call)
     uint32_t* d_noise_plies = nullptr;
