@@ -956,7 +956,7 @@ int search_create(az_engine* e) {
     p.mode = 0; p.max_iters = c.cache_log2 > 0 ? 4 : 2;
     if (const char* v = getenv("AZ_ADV_MAX_ITERS")) p.max_iters = std::max(1, atoi(v));
     p.last_game_id = 0; p.cache_epoch = 0; p.consume = 1;
-    if (const char* v = getenv("AZ_ADV_PASSES")) { st->adv_passes = std::max(1, std::min(4, atoi(v))); st->adv_passes_fixed = 1; }
+    if (const char* v = getenv("AZ_ADV_PASSES")) st->adv_passes = std::max(1, std::min(4, atoi(v)));
     if (!(c.temperature > 0.0f)) return set_err(e, AZ_ERR_INVALID_ARGUMENT, "temperature must be positive");
     p.inv_temperature = 1.0f / c.temperature;
     p.fp32_planes = c.precision == 1 ? 1 : 0;
@@ -1046,10 +1046,10 @@ static int run_wave(az_engine* e, SearchState* st) {
         cudaEventCreate(&e->prof_adv_event);
         cudaEventRecord(e->prof_adv_event, e->stream);
     }
-    // With a high cache hit rate many games complete their max_iters network-free simulations without needing the network;
-    // extra passes let exactly those games go on (everybody else returns at once), so the batch of the wave fills up and the
-    // marginal simulations cost a 40 us kernel instead of a share of the 1.1 ms network wave.  az_selfplay_step adapts the
-    // number of passes to the avoided fraction it measured in its previous call.
+    // AZ_ADV_PASSES > 1 (experiment, default 1): extra k_advance passes per wave in which only the games that completed their
+    // max_iters network-free simulations without needing the network go on.  Measured at 14 % / 45 % / 63 % cache hits
+    // (profiles/r2_passes_raw.jsonl): always slower -- the fuller batch costs tower time in proportion, and more simulations
+    // per wave mean more games evaluating the same position in the same wave before anybody's result reaches the cache.
     const int passes = st->prm.mode == 1 && st->prm.cache_mask ? st->adv_passes : 1;
     for (int pass = 0; pass < passes; pass++) {
     st->prm.consume = pass == 0 ? 1 : 0;
@@ -1193,8 +1193,6 @@ int az_selfplay_begin_n(az_engine* e, int n_games, uint64_t first_game_id, uint6
     st->prm.n_games = n_games; st->prm.mode = 1; st->prm.S = e->cfg.num_simulations;
     st->prm.last_game_id = total_games ? first_game_id + total_games : 0;
     st->wave_counter = 0; st->prm.cache_epoch = 0;
-    st->last_sims = 0; st->last_evals = 0;
-    if (!st->adv_passes_fixed) st->adv_passes = 1;
     if (st->prm.cache_mask)  // a new cache per generation (training.rs:342)
         AZ_CUDA(e, cudaMemsetAsync(q.cache_state, 0, ((size_t)st->prm.cache_mask + 1) * sizeof(uint32_t), e->stream));
     Counters zero;
@@ -1274,14 +1272,6 @@ int az_selfplay_step(az_engine* e, int waves, az_selfplay_stats* out) {
         c.simulations = sum[0]; c.positions = sum[1]; c.evaluations = sum[2]; c.cache_hits = sum[3];
         c.terminal_leaves = sum[4]; c.games_finished = sum[5]; c.sum_leaf_depth = sum[6]; c.sum_edges = sum[7];
     }
-    if (!st->adv_passes_fixed && st->prm.cache_mask && waves > 0) {   // passes for the NEXT call from this call's avoided fraction
-        const double ds = (double)(c.simulations - st->last_sims), de = (double)(c.evaluations - st->last_evals);
-        if (ds > 0) {
-            const double avoided = 1.0 - de / ds;
-            st->adv_passes = avoided > 0.5 ? 3 : avoided > 0.25 ? 2 : 1;
-        }
-    }
-    st->last_sims = c.simulations; st->last_evals = c.evaluations;
     if (out) {
         out->simulations = c.simulations; out->positions = c.positions; out->evaluations = c.evaluations; out->cache_hits = c.cache_hits;
         out->terminal_leaves = c.terminal_leaves; out->games_finished = c.games_finished; out->sum_leaf_depth = c.sum_leaf_depth;

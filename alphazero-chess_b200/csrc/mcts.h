@@ -119,9 +119,7 @@ struct SearchState {
     int G = 0;
     bool selfplay_active = false;
     unsigned long long cache_evictions = 0;
-    int adv_passes = 1;                    // k_advance launches per wave (see run_wave)
-    int adv_passes_fixed = 0;              // AZ_ADV_PASSES: no adaptation
-    unsigned long long last_sims = 0, last_evals = 0;   // counters at the end of the previous az_selfplay_step (adaptation)
+    int adv_passes = 1;                    // k_advance launches per wave (AZ_ADV_PASSES, see run_wave)
     unsigned long long wave_counter = 0;   // self-play waves since az_selfplay_begin (cache epoch = wave_counter / S)
     unsigned long long* d_noise_ids = nullptr;  // [max_games] az_search staging (no allocation per call)
     uint32_t* d_noise_plies = nullptr;

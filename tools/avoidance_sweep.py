@@ -25,21 +25,22 @@ from alphazero_chess_b200 import training as tr  # noqa: E402
 G, S = 4096, 800
 
 
-def measure(weights, label, cache_log2=24, max_iters=None):
+def measure(weights, label, cache_log2=24, max_iters=None, warm_plies=2):
     if max_iters:
         os.environ["AZ_ADV_MAX_ITERS"] = str(max_iters)
     eng = az.Engine(max_games=G, num_simulations=S, seed=42, cache_log2=cache_log2)
     os.environ.pop("AZ_ADV_MAX_ITERS", None)
     eng.load_weights(weights)
     eng.selfplay_begin(G)
-    eng.selfplay_step(2 * S)
+    for _ in range(warm_plies):
+        eng.selfplay_step(S)
     st0 = eng.selfplay_step(0)
     eng.timer_start()
     st1 = eng.selfplay_step(3 * S)
     ms = eng.timer_stop()
     d = {k: getattr(st1, k) - getattr(st0, k) for k in ("simulations", "evaluations", "cache_hits", "cache_evictions", "terminal_leaves", "sum_leaf_depth")}
     eng.close()
-    out = {"label": label, "cache_log2": cache_log2, "max_iters": max_iters, "sims_per_sec": d["simulations"] / ms * 1e3,
+    out = {"label": label, "warm_plies": warm_plies, "cache_log2": cache_log2, "max_iters": max_iters, "sims_per_sec": d["simulations"] / ms * 1e3,
            "evals_per_sec": d["evaluations"] / ms * 1e3, "avoidance": 1 - d["evaluations"] / d["simulations"],
            "hits": d["cache_hits"], "evictions": d["cache_evictions"], "terminal": d["terminal_leaves"],
            "mean_leaf_depth": d["sum_leaf_depth"] / d["simulations"], "us_per_wave": ms * 1e3 / (3 * S)}
@@ -84,6 +85,10 @@ def main():
         measure(sharpen(w, k), f"trained {gens} generations, policy logits x {k:g}")
     measure(sharpen(w, 4.0), "policy logits x 4, max_iters 8", max_iters=8)
     measure(sharpen(w, 4.0), "policy logits x 4, cache off", cache_log2=0)
+    # the same after 12 plies of warm-up: the games have left the shared opening, so hits on OTHER games' evaluations are gone
+    for k in (1.0, 4.0, 8.0):
+        measure(sharpen(w, k) if k != 1.0 else w, f"trained {gens} generations, policy logits x {k:g}, 12 warm-up plies", warm_plies=12)
+    measure(w0, "random-init, 12 warm-up plies", warm_plies=12)
 
 
 if __name__ == "__main__":
