@@ -222,17 +222,24 @@ def run_generation_sharded(engine, replay, model, optimizer, iteration, games_pe
     engine.selfplay_begin(slots, first_game_id=sharding.first_game_id(rank) + iteration * (1 << 24), total_games=games_per_rank)
     if on_gpu and exchange is None:
         exchange = sharding.DeviceSampleExchange(engine, dist, device, max(engine.config.max_games * 128, 1 << 16))
+    import time
+
     steps = new_unique = 0
     done = False
     st = None
+    t_play = t_xchg = 0.0
     while True:
+        t0 = time.perf_counter()
         if not done:
             st = engine.selfplay_step(waves_per_call)
+        t1 = time.perf_counter()
+        t_play += t1 - t0
         if on_gpu:
             for ptr, n in exchange.exchange():
                 if n:
                     steps += n
                     new_unique += replay.add_dev(ptr, n)
+            t_xchg += time.perf_counter() - t1
         else:
             mine = engine.selfplay_drain() if (st.pending_samples and not done) else np.zeros(0, SAMPLE_DTYPE)
             got = sharding.allgather_samples(mine, dist)
@@ -245,9 +252,12 @@ def run_generation_sharded(engine, replay, model, optimizer, iteration, games_pe
     sums, _ = sharding.reduce_metrics([float(st.simulations), float(st.evaluations), float(st.games_finished)], [0.0], dist)
     out = {"iteration": iteration, "n_ranks": world, "games": int(sums[2]), "positions": steps, "new_unique_states": new_unique,
            "replay_buffer_size": len(replay), "simulations": int(sums[0]), "evaluations": int(sums[1]), "trained": False,
-           "sample_gather": "device all-gather (NCCL)" if on_gpu else "host all-gather"}
+           "sample_gather": "device all-gather (NCCL)" if on_gpu else "host all-gather",
+           "seconds_selfplay": t_play, "seconds_sample_exchange_and_replay_add": t_xchg}
     if len(replay) >= min_replay_size:   # identical on every rank: the replicas hold the same entries
+        t0 = time.perf_counter()
         pl, vl = train_iteration(model, optimizer, replay, iteration, num_steps, batch_size, dist=dist if world > 1 else None)
         out.update(trained=True, avg_policy_loss=pl, avg_value_loss=vl, learning_rate=get_cyclical_lr(iteration))
         engine.load_weights(export_weights(model))
+        out["seconds_training"] = time.perf_counter() - t0
     return out

@@ -181,7 +181,7 @@ def run_reference(args, rank, world):
 
     cores = os.cpu_count() or 1
     weights = orc.random_weights(seed=42)
-    warm, steps = min(args.warmup, 2), max(1, min(args.steps, 12))   # bounded: about 7 s of host work per step
+    warm, steps = args.warmup, max(1, args.steps)   # about 7.5 s of host work per step on 16 threads (20 + 5 steps: 3 minutes)
     cpu_shared_sample(weights, args.sims, cores, warm, first_step=0)
     r = cpu_shared_sample(weights, args.sims, cores, steps, first_step=warm)
     value = r["simulations"] / r["seconds"] if r["seconds"] > 0 else 0.0
@@ -638,7 +638,8 @@ def run_generation_mode(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
     G, S = args.games, args.sims
     torch.manual_seed(42)
-    eng = az.Engine(device=local_rank, max_games=min(G, 4096), num_simulations=S, seed=42, cache_log2=args.cache_log2)
+    slots = min(args.slots or G, G, 4096)
+    eng = az.Engine(device=local_rank, max_games=max(slots, 256), num_simulations=S, seed=42, cache_log2=args.cache_log2)
     model = tr.import_weights(tr.AlphaZeroNet(), az.random_weights(seed=42)).to(dev)
     if world > 1:
         model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)   # BatchNorm statistics over the global batch, as the reference's
@@ -654,7 +655,8 @@ def run_generation_mode(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        m = tr.run_generation_sharded(eng, replay, model, opt, it, G, dist, dev, min_replay_size=args.min_replay, exchange=exchange)
+        m = tr.run_generation_sharded(eng, replay, model, opt, it, G, dist, dev, min_replay_size=args.min_replay, exchange=exchange,
+                                      concurrent=slots)
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
@@ -674,7 +676,7 @@ def run_generation_mode(args, rank, world, local_rank):
                 "vs_baseline": None, "dtype": "bf16", "mode": "generation",
                 "data": "synthetic start (random-init 10x128 net, seed 42), then the loop's own self-play data",
                 "config": {"workload": f"BASELINE configs[4]: per generation {G} complete self-play games per GPU x {S} sims/move -> replay buffer "
-                                       f"(100,000) -> 40 x 512 AdamW steps (data parallel) -> 256-game BaseModel match", "games_per_gpu": G,
+                                       f"(100,000) -> 40 x 512 AdamW steps (data parallel) -> 256-game BaseModel match", "games_per_gpu": G, "concurrent_games_per_gpu": slots,
                            "sims_per_move": S, "parallelism": f"games sharded {world} x {G}; NCCL: sample all-gather (device to device), gradient all-reduce"},
                 "mcts_simulations_per_sec": sims / secs, "sample_bytes_gathered": exchange.bytes_moved, "generations": rows}
         print(json.dumps(line), flush=True)
@@ -700,6 +702,7 @@ def main():
     ap.add_argument("--quick", action="store_true", help="timed region and e2e only (no parity / config-2 / eval-avoidance / fp32 legs)")
     ap.add_argument("--cache-log2", type=int, default=0, help="log2 slots of the GPU evaluation cache (0 = off)")
     ap.add_argument("--min-replay", type=int, default=20_000, help="generation mode: MIN_REPLAY_SIZE (parameters.rs:11)")
+    ap.add_argument("--slots", type=int, default=0, help="generation mode: concurrent games per GPU (0 = all games of the generation at once, like the reference's NUM_EPISODES tasks)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
