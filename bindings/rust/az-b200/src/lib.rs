@@ -80,10 +80,11 @@ impl Engine {
         Ok((visits, depth))
     }
 
-    /// run_all_episodes (training.rs:340-378): `n_games` self-play games; the callback receives the finished games' steps
-    /// (values already back-filled) as they become available.  Returns the average batch size (= evaluations per wave).
+    /// run_all_episodes (training.rs:340-378): EXACTLY `n_games` self-play games (ids first_game_id ..), each played to
+    /// completion; the callback receives the finished games' steps (values already back-filled) as they become available.
+    /// Returns the average batch size (= evaluations per wave).
     pub fn run_all_episodes<F: FnMut(&[sys::az_sample])>(&mut self, n_games: i32, first_game_id: u64, mut sink: F) -> Result<f32> {
-        self.check(unsafe { sys::az_selfplay_begin(self.raw, n_games, first_game_id) })?;
+        self.check(unsafe { sys::az_selfplay_begin_n(self.raw, n_games, first_game_id, n_games as u64) })?;
         let mut buf: Vec<sys::az_sample> = Vec::with_capacity((n_games as usize * 128).max(1 << 16));
         let mut stats = sys::az_selfplay_stats::default();
         let mut waves = 0u64;
@@ -96,7 +97,7 @@ impl Engine {
                 unsafe { buf.set_len(n as usize) };
                 sink(&buf);
             }
-            if stats.games_finished >= n_games as u64 { break; }
+            if stats.active_games == 0 && stats.pending_samples == 0 { break; }   // every game of the generation has ended
         }
         Ok(stats.evaluations as f32 / waves as f32)
     }
