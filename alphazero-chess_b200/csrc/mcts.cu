@@ -292,62 +292,51 @@ __device__ __forceinline__ void backup(Ctx& x, float leaf_value, int path_len, c
 // One PUCT descent from the root (tree.rs:180-202).  Fills the path and returns the leaf: its parent's node id, position and
 // depth, and the chosen edge (pool index, wire move).
 // The walk costs ONE dependent memory round trip per level: an edge carries its child's id together with the child's edge
-// range (edge_link), the root's range is in the control block, total_visits = sum of the edges' visit counts (tree.rs:184 --
-// integers in f32, exact in any order) is reduced from the very loads the scores need, and the chosen edge's move and every
-// visited node's position (the leaf's parent needs it) are requested in the same batch of loads.
+// range (edge_link), the root's range is in the control block, and the chosen edge's move and every visited node's position
+// (the leaf's parent needs it) are requested in the same batch of loads.
+// total_visits (tree.rs:184: the sum of the node's visit counts) needs no loads at all: every simulation that passes through
+// a node increments exactly one of its edges, and the simulations passing through a node are the visits of the edge leading
+// into it minus the one that created it -- so total_visits + 1 is exactly that edge's N (at the root: simulations done + 1),
+// the same integer in f32 the reference obtains by summing.
 __device__ __forceinline__ void select_leaf(Ctx& x, int& leaf_node, size_t& leaf_pe, uint32_t& leaf_mv, int& depth, DPos& parent) {
     int node = 0;
     depth = 0;
     uint32_t eoff = 0;
     int L = (int)((x.c.flags >> 8) & 0xFF);
+    float total = __fadd_rn((float)x.c.sims_done, 1.0f);
     for (;;) {
         const size_t off = x.ebase + eoff;
         u64 here = 0;   // lanes 0..7: the eight words of this node's position
         if (x.lane < 8) here = reinterpret_cast<const u64*>(&x.ptr.node_pos[x.nbase + node])[x.lane];
-        float P0 = 0.0f, N0 = 0.0f, W0 = 0.0f;
-        u64 K0 = EDGE_NO_CHILD;
-        uint32_t M0 = 0;
-        if (x.lane < L) {
-            P0 = x.ptr.edge_P[off + x.lane]; N0 = x.ptr.edge_N[off + x.lane]; W0 = x.ptr.edge_W[off + x.lane];
-            K0 = x.ptr.edge_link[off + x.lane]; M0 = x.ptr.edge_mv[off + x.lane];
-        }
-        float nsum = N0;
-        for (int e = x.lane + 32; e < L; e += 32) nsum = __fadd_rn(nsum, x.ptr.edge_N[off + e]);
-        for (int d = 16; d; d >>= 1) nsum = __fadd_rn(nsum, __shfl_xor_sync(0xffffffffu, nsum, d));
-        const float total = __fadd_rn(nsum, 1.0f);
         const float sq = __fsqrt_rn(total);
         float best = -INFINITY;
         int best_e = 0x7FFFFFFF;
-        u64 best_k = K0;        // the link and the move travel with the score through the argmax
-        uint32_t best_m = M0;
-        if (x.lane < L) {
-            const float u = __fdiv_rn(__fmul_rn(__fmul_rn(x.prm.c_puct, P0), sq), __fadd_rn(1.0f, N0));
-            const float q = N0 > 0.0f ? __fdiv_rn(W0, N0) : 0.0f;
-            const float v = __fadd_rn(q, u);
-            if (v > best) { best = v; best_e = x.lane; }
-        }
-        for (int e = x.lane + 32; e < L; e += 32) {
+        // this lane's candidate: link, move and visit count of its best edge (lane 0 starts with edge 0 for the NaN fallback)
+        u64 my_k = EDGE_NO_CHILD;
+        uint32_t my_m = 0;
+        float my_n = 0.0f;
+        for (int e = x.lane; e < L; e += 32) {
             const float P = x.ptr.edge_P[off + e], N = x.ptr.edge_N[off + e], W = x.ptr.edge_W[off + e];
             const u64 K = x.ptr.edge_link[off + e];
             const uint32_t M = x.ptr.edge_mv[off + e];
             const float u = __fdiv_rn(__fmul_rn(__fmul_rn(x.prm.c_puct, P), sq), __fadd_rn(1.0f, N));
             const float q = N > 0.0f ? __fdiv_rn(W, N) : 0.0f;
             const float v = __fadd_rn(q, u);
-            if (v > best) { best = v; best_e = e; best_k = K; best_m = M; }
+            if (v > best) { best = v; best_e = e; my_k = K; my_m = M; my_n = N; }
+            else if (e == x.lane) { my_k = K; my_m = M; my_n = N; }   // seed: lane 0 must hold edge 0 for the NaN fallback
         }
-        // warp argmax: larger value wins, ties go to the earlier move (strict '>' in list order)
+        // warp argmax over (score, edge): larger value wins, ties go to the earlier move (strict '>' in list order)
         for (int d = 16; d; d >>= 1) {
             const float ov = __shfl_xor_sync(0xffffffffu, best, d);
             const int oe = __shfl_xor_sync(0xffffffffu, best_e, d);
-            const u64 ok = shfl_xor_u64(best_k, d);
-            const uint32_t om = __shfl_xor_sync(0xffffffffu, best_m, d);
-            if (ov > best || (ov == best && oe < best_e)) { best = ov; best_e = oe; best_k = ok; best_m = om; }
+            if (ov > best || (ov == best && oe < best_e)) { best = ov; best_e = oe; }
         }
-        if (best_e == 0x7FFFFFFF) {  // every score was NaN / -inf: the reference keeps max_index = 0 (first move)
-            best_e = 0;
-            best_k = shfl_u64(K0, 0);
-            best_m = __shfl_sync(0xffffffffu, M0, 0);
-        }
+        if (best_e == 0x7FFFFFFF) best_e = 0;  // every score was NaN / -inf: the reference keeps max_index = 0 (first move)
+        // the winning edge belongs to lane best_e % 32, whose candidate it is
+        const int owner = best_e & 31;
+        const u64 best_k = shfl_u64(my_k, owner);
+        const uint32_t best_m = __shfl_sync(0xffffffffu, my_m, owner);
+        const float best_n = __shfl_sync(0xffffffffu, my_n, owner);
         if (x.lane == 0) {
             x.ptr.path[(size_t)x.g * x.prm.node_cap + depth] =
                 make_uint2((uint32_t)node | ((uint32_t)best_e << 16), eoff + (uint32_t)best_e);
@@ -364,6 +353,7 @@ __device__ __forceinline__ void select_leaf(Ctx& x, int& leaf_node, size_t& leaf
         node = (int)(best_k & 0xFFFF);
         L = (int)((best_k >> 16) & 0xFF);
         eoff = (uint32_t)(best_k >> 24);
+        total = best_n;   // = (visits through this child) + 1
         depth++;
     }
 }
@@ -1261,6 +1251,12 @@ int az_selfplay_step(az_engine* e, int waves, az_selfplay_stats* out) {
         for (int i = 0; i < STAT_STRIPES * STAT_WIDTH; i++) if (i % STAT_WIDTH >= 8 && i % STAT_WIDTH < 16) tc[i % STAT_WIDTH - 8] += stripes[i];
         unsigned long long hist[16] = {0};
         for (int i = 0; i < STAT_STRIPES * STAT_WIDTH; i++) if (i % STAT_WIDTH >= 24) hist[i % STAT_WIDTH - 24] += stripes[i];
+        {   // the device counters are cumulative since az_selfplay_begin: report this call's share
+            static unsigned long long prev_tc[8], prev_hist[16];
+            for (int k = 0; k < 8; k++) { const unsigned long long c = tc[k]; tc[k] = c >= prev_tc[k] ? c - prev_tc[k] : c; prev_tc[k] = c; }
+            for (int k = 0; k < 16; k++) { const unsigned long long c = hist[k]; hist[k] = c >= prev_hist[k] ? c - prev_hist[k] : c; prev_hist[k] = c; }
+        }
+        if (waves > 0) {
         fprintf(stderr, "azb: k_advance warp-time histogram (buckets of 4096 clocks):");
         for (int k = 0; k < 16; k++) fprintf(stderr, " %llu", hist[k]);
         fprintf(stderr, "\n");
@@ -1268,6 +1264,7 @@ int az_selfplay_step(az_engine* e, int waves, az_selfplay_stats* out) {
                 (double)tc[0] / ((double)st->prm.n_games * waves), (double)tc[1] / ((double)st->prm.n_games * waves), (double)tc[2] / ((double)st->prm.n_games * waves),
                 (double)tc[3] / ((double)st->prm.n_games * waves), (double)tc[4] / ((double)st->prm.n_games * waves), (double)tc[5] / ((double)st->prm.n_games * waves),
                 (double)tc[6] / ((double)st->prm.n_games * waves), (double)tc[7] / ((double)st->prm.n_games * waves));
+        }
 #endif
         c.simulations = sum[0]; c.positions = sum[1]; c.evaluations = sum[2]; c.cache_hits = sum[3];
         c.terminal_leaves = sum[4]; c.games_finished = sum[5]; c.sum_leaf_depth = sum[6]; c.sum_edges = sum[7];
