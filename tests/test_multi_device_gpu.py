@@ -41,7 +41,15 @@ def test_sharded_generation_loop_two_ranks():
            "--games", "128", "--sims", "32", "--iterations", "2", "--min-replay", "1000", "--eval-games", "0", "--all-ranks"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-3000:]
-    lines = [json.loads(l) for l in out.stdout.splitlines() if l.startswith("{")]
+    # both ranks write to one pipe: parse every JSON object, wherever the line breaks fell
+    lines, dec, text, pos = [], json.JSONDecoder(), out.stdout, 0
+    while True:
+        pos = text.find('{"iteration"', pos)
+        if pos < 0:
+            break
+        obj, end = dec.raw_decode(text, pos)
+        lines.append(obj)
+        pos = end
     assert len(lines) == 4 and all(m["n_ranks"] == 2 and m["trained"] and m["games"] == 256 for m in lines)
     for it in (0, 1):
         a, b = [m for m in lines if m["iteration"] == it]

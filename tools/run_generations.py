@@ -82,7 +82,8 @@ def main():
         if world > 1:
             dist.barrier()
         if rank == 0 or args.all_ranks:
-            print(json.dumps(m), flush=True)
+            sys.stdout.write(json.dumps(m) + "\n")   # one write per line: the ranks share a pipe
+            sys.stdout.flush()
     replay.close()
     if old is not None:
         old.close()
