@@ -48,7 +48,7 @@ class Config(ctypes.Structure):
 class SelfplayStats(ctypes.Structure):
     _fields_ = [(n, ctypes.c_uint64) for n in ("simulations", "positions", "evaluations", "cache_hits", "terminal_leaves",
                                                "games_finished", "sum_leaf_depth", "sum_edges", "waves", "pending_samples",
-                                               "active_games", "parked_games", "cache_evictions")]
+                                               "active_games", "parked_games", "cache_evictions", "sum_search_depth")]
 
 
 class EngineError(RuntimeError):

@@ -119,6 +119,7 @@ struct Ctx {
     GameCtl c;
     // statistics accumulated by lane 0
     unsigned int st_sims, st_pos, st_evals, st_term, st_games, st_depth, st_edges, st_hits, st_evict;
+    unsigned int st_sdepth;        // sum of EpisodeStep::search_depth over the steps recorded (avg_search_depth, training.rs:91-97)
     unsigned long long new_link;   // edge_link value of the node create_node made last
 };
 
@@ -584,6 +585,7 @@ __device__ void move_step(Ctx& x) {
         smp->action = (uint16_t)(amv >> 16);
         smp->n_visits = (uint16_t)nv;
         x.st_pos++;
+        x.st_sdepth += x.c.max_depth;
     }
     x.c.n_samples = min(x.c.n_samples + 1, (uint32_t)MAX_SAMPLE_PLIES);
     // ---- play it (chess.rs:36-63)
@@ -629,20 +631,20 @@ __device__ void move_step(Ctx& x) {
 // and out BY VALUE so that the hot path's copy stays in registers (a reference would pin it in local memory).
 struct ColdOut {
     GameCtl c;
-    unsigned int st_pos, st_games;
+    unsigned int st_pos, st_games, st_sdepth;
 };
 __device__ __forceinline__ Ctx cold_ctx(const SearchParams* prm, const SearchPtrs* ptr, WarpShared* sh, int g, const GameCtl& c) {
-    return Ctx{*prm, *ptr, sh, g, (int)(threadIdx.x & 31), (size_t)g * prm->node_cap, (size_t)g * prm->edge_cap, c, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    return Ctx{*prm, *ptr, sh, g, (int)(threadIdx.x & 31), (size_t)g * prm->node_cap, (size_t)g * prm->edge_cap, c, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 }
 __device__ __noinline__ ColdOut move_step_cold(const SearchParams* prm, const SearchPtrs* ptr, WarpShared* sh, int g, GameCtl c) {
     Ctx x = cold_ctx(prm, ptr, sh, g, c);
     move_step(x);
-    return ColdOut{x.c, x.st_pos, x.st_games};
+    return ColdOut{x.c, x.st_pos, x.st_games, x.st_sdepth};
 }
 __device__ __noinline__ ColdOut finish_game_cold(const SearchParams* prm, const SearchPtrs* ptr, WarpShared* sh, int g, GameCtl c) {
     Ctx x = cold_ctx(prm, ptr, sh, g, c);
     finish_game(x, __uint_as_float(c.park_scale));
-    return ColdOut{x.c, x.st_pos, x.st_games};
+    return ColdOut{x.c, x.st_pos, x.st_games, x.st_sdepth};
 }
 __device__ __noinline__ void root_noise_cold(const SearchParams* prm, const SearchPtrs* ptr, WarpShared* sh, int g, GameCtl c) {
     Ctx x = cold_ctx(prm, ptr, sh, g, c);
@@ -667,7 +669,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB * 4 / WARPS) k_advance(const 
     // the path of the pending simulation is requested together with the control block (its address needs only g)
     const uint2 path_spec = ptr.path[(size_t)g * prm.node_cap + min((int)(threadIdx.x & 31), prm.node_cap - 1)];
     Ctx x{prm, ptr, &shared[threadIdx.x >> 5], g, (int)(threadIdx.x & 31), (size_t)g * prm.node_cap, (size_t)g * prm.edge_cap,
-          ptr.ctl[g], 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+          ptr.ctl[g], 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (x.c.status != 0 && x.c.status != 4) return;
     if (!prm.consume && x.c.pending_node >= 0) return;   // extra pass: this game already waits for the network
 
@@ -675,7 +677,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB * 4 / WARPS) k_advance(const 
     // ---- 0. game over, samples staged: publish now if the host has drained the queue, else stay parked
     if (x.c.status == 4) {
         const ColdOut o = finish_game_cold(&prm, &ptr, x.sh, g, x.c);
-        x.c = o.c; x.st_pos += o.st_pos; x.st_games += o.st_games;
+        x.c = o.c; x.st_pos += o.st_pos; x.st_games += o.st_games; x.st_sdepth += o.st_sdepth;
     }
     const bool runnable = x.c.status == 0;
     // ---- 1. the evaluation requested in the previous wave has arrived
@@ -709,7 +711,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB * 4 / WARPS) k_advance(const 
         if ((int)x.c.sims_done >= prm.S) {
             if (prm.mode == 0) { x.c.status = 1; break; }
             const ColdOut o = move_step_cold(&prm, &ptr, x.sh, g, x.c);
-            x.c = o.c; x.st_pos += o.st_pos; x.st_games += o.st_games;
+            x.c = o.c; x.st_pos += o.st_pos; x.st_games += o.st_games; x.st_sdepth += o.st_sdepth;
             ADV_T(6);
             if (x.c.status != 0) break;   // idle (generation complete), parked (sample queue full) or an error
             continue;
@@ -777,6 +779,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB * 4 / WARPS) k_advance(const 
         if (x.st_depth) atomicAdd(&ct[6], (unsigned long long)x.st_depth);
         if (x.st_edges) atomicAdd(&ct[7], (unsigned long long)x.st_edges);
         if (x.st_evict) atomicAdd(&ct[16], (unsigned long long)x.st_evict);
+        if (x.st_sdepth) atomicAdd(&ct[17], (unsigned long long)x.st_sdepth);
 #ifdef AZ_ADV_TIMING
         t_acc[7] = (unsigned long long)(clock64() - t_start);
         for (int k = 0; k < 8; k++) atomicAdd(&ct[8 + k], t_acc[k]);
@@ -796,7 +799,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_init_search(SearchParams prm, Se
     GameCtl c;
     memset(&c, 0, sizeof c);
     Ctx x{prm, ptr, &shared[threadIdx.x >> 5], g, (int)(threadIdx.x & 31), (size_t)g * prm.node_cap, (size_t)g * prm.edge_cap, c,
-          0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+          0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     x.c.game_id = noise_ids ? noise_ids[g] : 0;
     x.c.noise_ply = noise_plies ? noise_plies[g] : 0;
     x.c.flags = noise_ids ? 1 : 0;
@@ -842,7 +845,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_init_selfplay(SearchParams prm, 
     GameCtl c;
     memset(&c, 0, sizeof c);
     Ctx x{prm, ptr, &shared[threadIdx.x >> 5], g, (int)(threadIdx.x & 31), (size_t)g * prm.node_cap, (size_t)g * prm.edge_cap, c,
-          0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+          0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     x.c.game_id = first_game_id + g;
     x.c.hist_len = 1;
     if (x.lane == 0) {
@@ -1239,13 +1242,15 @@ int az_selfplay_step(az_engine* e, int waves, az_selfplay_stats* out) {
     AZ_CUDA(e, cudaStreamSynchronize(e->stream));
     {
         unsigned long long sum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        unsigned long long evictions = 0;
+        unsigned long long evictions = 0, sdepth = 0;
         for (int i = 0; i < STAT_STRIPES * STAT_WIDTH; i++) {
             const int f = i % STAT_WIDTH;
             if (f < 8) sum[f] += stripes[i];
             if (f == 16) evictions += stripes[i];
+            if (f == 17) sdepth += stripes[i];
         }
         st->cache_evictions = evictions;
+        st->sum_search_depth = sdepth;
 #ifdef AZ_ADV_TIMING
         unsigned long long tc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (int i = 0; i < STAT_STRIPES * STAT_WIDTH; i++) if (i % STAT_WIDTH >= 8 && i % STAT_WIDTH < 16) tc[i % STAT_WIDTH - 8] += stripes[i];
@@ -1274,6 +1279,7 @@ int az_selfplay_step(az_engine* e, int waves, az_selfplay_stats* out) {
         out->terminal_leaves = c.terminal_leaves; out->games_finished = c.games_finished; out->sum_leaf_depth = c.sum_leaf_depth;
         out->sum_edges = c.sum_edges; out->waves = (uint64_t)waves; out->pending_samples = std::min<unsigned long long>(c.samples_out, st->prm.sample_cap);
         out->active_games = (uint64_t)(flags[0] + flags[2]); out->parked_games = (uint64_t)flags[2]; out->cache_evictions = st->cache_evictions;
+        out->sum_search_depth = st->sum_search_depth;
     }
     if (c.errors || flags[1]) return set_err(e, AZ_ERR_CAPACITY, "a per-game node/edge pool overflowed during self-play (raise edge_capacity_per_node)");
     return AZ_OK;

@@ -73,7 +73,7 @@ struct Counters {
 
 constexpr unsigned long long EDGE_NO_CHILD = ~0ULL;
 constexpr int STAT_STRIPES = 64;
-constexpr int STAT_WIDTH = 40;    // per stripe: 0..7 the statistics fields of Counters, 8..15 AZ_ADV_TIMING phase clocks, 16 cache evictions,
+constexpr int STAT_WIDTH = 40;    // per stripe: 0..7 the statistics fields of Counters, 8..15 AZ_ADV_TIMING phase clocks, 16 cache evictions, 17 sum of search depths,
                                   // 24..39 AZ_ADV_TIMING histogram of a warp's time in k_advance (buckets of 4096 clocks)
 
 struct SearchPtrs {
@@ -119,6 +119,7 @@ struct SearchState {
     int G = 0;
     bool selfplay_active = false;
     unsigned long long cache_evictions = 0;
+    unsigned long long sum_search_depth = 0;
     int adv_passes = 1;                    // k_advance launches per wave (AZ_ADV_PASSES, see run_wave)
     unsigned long long wave_counter = 0;   // self-play waves since az_selfplay_begin (cache epoch = wave_counter / S)
     unsigned long long* d_noise_ids = nullptr;  // [max_games] az_search staging (no allocation per call)

@@ -181,9 +181,10 @@ def run_generation(engine, replay, model, optimizer, iteration, n_games, min_rep
     engine.load_weights(export_weights(model))
     slots = min(n_games, concurrent or engine.config.max_games, engine.config.max_games)
     engine.selfplay_begin(slots, first_game_id=iteration * (1 << 24), total_games=n_games)
-    new_unique = steps = 0
+    new_unique = steps = waves = 0
     while True:
         st = engine.selfplay_step(waves_per_call)
+        waves += waves_per_call
         if st.pending_samples:
             n, nu = replay.add_pending()
             steps += n
@@ -193,7 +194,9 @@ def run_generation(engine, replay, model, optimizer, iteration, n_games, min_rep
     assert st.games_finished == n_games, (st.games_finished, n_games)
     out = {"iteration": iteration, "games": int(st.games_finished), "positions": steps, "new_unique_states": new_unique,
            "replay_buffer_size": len(replay), "simulations": int(st.simulations), "evaluations": int(st.evaluations),
-           "cache_hits": int(st.cache_hits), "trained": False}
+           "cache_hits": int(st.cache_hits), "trained": False,
+           # what MetricUpdate::SelfPlayFinished logs (training.rs:107-129): mean search depth per step, mean batch per wave
+           "avg_search_depth": st.sum_search_depth / max(int(st.positions), 1), "avg_batch_size": st.evaluations / max(waves, 1)}
     if len(replay) >= min_replay_size:
         pl, vl = train_iteration(model, optimizer, replay, iteration, num_steps, batch_size)
         out.update(trained=True, avg_policy_loss=pl, avg_value_loss=vl, learning_rate=get_cyclical_lr(iteration))
@@ -249,8 +252,10 @@ def run_generation_sharded(engine, replay, model, optimizer, iteration, games_pe
         done = st.active_games == 0
         if sharding.all_done(done, dist, device if on_gpu else None):
             break
-    sums, _ = sharding.reduce_metrics([float(st.simulations), float(st.evaluations), float(st.games_finished)], [0.0], dist)
+    sums, _ = sharding.reduce_metrics([float(st.simulations), float(st.evaluations), float(st.games_finished), float(st.sum_search_depth),
+                                       float(st.positions)], [0.0], dist)
     out = {"iteration": iteration, "n_ranks": world, "games": int(sums[2]), "positions": steps, "new_unique_states": new_unique,
+           "avg_search_depth": float(sums[3]) / max(float(sums[4]), 1.0),
            "replay_buffer_size": len(replay), "simulations": int(sums[0]), "evaluations": int(sums[1]), "trained": False,
            "sample_gather": "device all-gather (NCCL)" if on_gpu else "host all-gather",
            "seconds_selfplay": t_play, "seconds_sample_exchange_and_replay_add": t_xchg}

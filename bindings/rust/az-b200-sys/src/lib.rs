@@ -20,7 +20,8 @@ pub struct az_config { pub device: i32, pub max_games: i32, pub max_batch: i32, 
                                   pub index: [u16; 256], pub count: [u16; 256] }                          // 1120 bytes
 #[repr(C)] #[derive(Default)] pub struct az_selfplay_stats { pub simulations: u64, pub positions: u64, pub evaluations: u64,
     pub cache_hits: u64, pub terminal_leaves: u64, pub games_finished: u64, pub sum_leaf_depth: u64, pub sum_edges: u64,
-    pub waves: u64, pub pending_samples: u64, pub active_games: u64, pub parked_games: u64, pub cache_evictions: u64 }
+    pub waves: u64, pub pending_samples: u64, pub active_games: u64, pub parked_games: u64, pub cache_evictions: u64,
+    pub sum_search_depth: u64 }
 pub enum az_engine {}
 
 extern "C" {

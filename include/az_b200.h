@@ -154,6 +154,7 @@ typedef struct az_selfplay_stats {
     uint64_t active_games;    /* slots still playing (az_selfplay_begin_n: 0 once every game of the generation has ended) */
     uint64_t parked_games;    /* finished games waiting for room in the sample queue (drain to let them publish) */
     uint64_t cache_evictions; /* cache entries replaced by newer ones (capacity management, parameters.rs:4) */
+    uint64_t sum_search_depth; /* sum of EpisodeStep::search_depth over `positions`: avg_search_depth of training.rs:91-97 */
 } az_selfplay_stats;
 
 typedef struct az_sample {

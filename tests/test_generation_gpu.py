@@ -56,6 +56,7 @@ def test_exactly_n_games_are_played_to_completion():
         samples, st = _play_generation(e, 8, first, 20)
         assert st.games_finished == 20 and st.parked_games == 0
         assert st.positions == len(samples)
+        assert st.sum_search_depth == int(samples["search_depth"].sum())   # avg_search_depth of training.rs:91-97
         # a further step changes nothing: every slot is idle
         st2 = e.selfplay_step(32)
         assert st2.simulations == st.simulations and st2.active_games == 0
