@@ -386,6 +386,21 @@ class ReplayBuffer:
                                                 ctypes.byref(n)), "az_replay_sample")
         return planes[: n.value], policy[: n.value], value[: n.value]
 
+    def sample_torch(self, batch_size, seed=0):
+        """ReplayBuffer::sample straight into CUDA tensors on the engine's device (az_replay_sample_dev): the same batch as
+        sample(batch_size, seed), without the device -> host -> device round trip of the numpy path."""
+        import torch
+
+        dev = torch.device("cuda", int(self._e.config.device))
+        planes = torch.empty((batch_size, NUM_PLANES, 8, 8), dtype=torch.float32, device=dev)
+        policy = torch.empty((batch_size, ACTION_SPACE), dtype=torch.float32, device=dev)
+        value = torch.empty(batch_size, dtype=torch.float32, device=dev)
+        n = ctypes.c_int(0)
+        self._e._check(self._L.az_replay_sample_dev(self._h, int(batch_size), ctypes.c_uint64(seed), ctypes.c_void_p(planes.data_ptr()),
+                                                    ctypes.c_void_p(policy.data_ptr()), ctypes.c_void_p(value.data_ptr()), ctypes.byref(n)),
+                       "az_replay_sample_dev")
+        return planes[: n.value], policy[: n.value], value[: n.value]
+
     def export(self, first, n):
         """Entries [first, first + n) in FIFO order (oldest first): (positions, policy [k,4096], value [k], visit_count [k])."""
         pos = np.zeros(n, POSITION_DTYPE)

@@ -496,7 +496,9 @@ int az_replay_len(az_replay* rp, int* len_out) {
     return AZ_OK;
 }
 
-int az_replay_sample(az_replay* rp, int batch_size, uint64_t seed, float* planes_out, float* policy_out, float* value_out, int* n_out) {
+// ReplayBuffer::sample (memory.rs:78-97); `to_device`: the three outputs are device pointers (no host hop on the way to the trainer)
+static int replay_sample(az_replay* rp, int batch_size, uint64_t seed, float* planes_out, float* policy_out, float* value_out, int* n_out,
+                         bool to_device) {
     if (!rp || !n_out || batch_size < 0) return AZ_ERR_INVALID_ARGUMENT;
     az_engine* e = rp->eng;
     cudaSetDevice(e->cfg.device);
@@ -520,11 +522,20 @@ int az_replay_sample(az_replay* rp, int batch_size, uint64_t seed, float* planes
     e->n_launches++;
     k_replay_gather<<<n, 256, 0, e->stream>>>(rp->p, rp->d_idx, n, rp->d_planes, rp->d_pol, rp->d_val);
     AZ_CUDA(e, cudaGetLastError());
-    if (planes_out) AZ_CUDA(e, cudaMemcpyAsync(planes_out, rp->d_planes, (size_t)n * AZ_NUM_PLANES * 64 * 4, cudaMemcpyDeviceToHost, e->stream));
-    if (policy_out) AZ_CUDA(e, cudaMemcpyAsync(policy_out, rp->d_pol, (size_t)n * AZ_ACTION_SPACE * 4, cudaMemcpyDeviceToHost, e->stream));
-    if (value_out) AZ_CUDA(e, cudaMemcpyAsync(value_out, rp->d_val, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
+    const cudaMemcpyKind kind = to_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (planes_out) AZ_CUDA(e, cudaMemcpyAsync(planes_out, rp->d_planes, (size_t)n * AZ_NUM_PLANES * 64 * 4, kind, e->stream));
+    if (policy_out) AZ_CUDA(e, cudaMemcpyAsync(policy_out, rp->d_pol, (size_t)n * AZ_ACTION_SPACE * 4, kind, e->stream));
+    if (value_out) AZ_CUDA(e, cudaMemcpyAsync(value_out, rp->d_val, (size_t)n * 4, kind, e->stream));
     AZ_CUDA(e, cudaStreamSynchronize(e->stream));
     return AZ_OK;
+}
+
+int az_replay_sample(az_replay* rp, int batch_size, uint64_t seed, float* planes_out, float* policy_out, float* value_out, int* n_out) {
+    return replay_sample(rp, batch_size, seed, planes_out, policy_out, value_out, n_out, false);
+}
+
+int az_replay_sample_dev(az_replay* rp, int batch_size, uint64_t seed, float* planes_dev, float* policy_dev, float* value_dev, int* n_out) {
+    return replay_sample(rp, batch_size, seed, planes_dev, policy_dev, value_dev, n_out, true);
 }
 
 int az_replay_export(az_replay* rp, int first, int n, az_position* pos_out, float* policy_out, float* value_out, uint32_t* visits_out,

@@ -146,13 +146,21 @@ def train_iteration(model, optimizer, replay, iteration, num_steps=NUM_TRAIN_STE
     tot = torch.zeros(2, dtype=torch.float64, device=device)
     done = 0
     for step in range(num_steps):
-        planes, policy, value = replay.sample(batch_size, seed=(seed * 1_000_003 + iteration) * 65_537 + step)
-        n = planes.shape[0]
-        if n == 0:
-            break
-        x = torch.from_numpy(planes[rank::world]).to(device)
-        pi = torch.from_numpy(policy[rank::world]).to(device)
-        z = torch.from_numpy(value[rank::world]).to(device)
+        batch_seed = (seed * 1_000_003 + iteration) * 65_537 + step
+        if device.type == "cuda" and hasattr(replay, "sample_torch"):   # device-resident: replay buffer -> trainer without a host hop
+            planes, policy, value = replay.sample_torch(batch_size, seed=batch_seed)
+            n = planes.shape[0]
+            if n == 0:
+                break
+            x, pi, z = planes[rank::world], policy[rank::world], value[rank::world]
+        else:
+            planes, policy, value = replay.sample(batch_size, seed=batch_seed)
+            n = planes.shape[0]
+            if n == 0:
+                break
+            x = torch.from_numpy(planes[rank::world]).to(device)
+            pi = torch.from_numpy(policy[rank::world]).to(device)
+            z = torch.from_numpy(value[rank::world]).to(device)
         p, v = model(x)
         # compute_gradients (training.rs:277-292) over the GLOBAL batch of n rows: this rank contributes its rows' terms
         difference = v - z

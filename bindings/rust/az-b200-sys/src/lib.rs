@@ -63,6 +63,7 @@ extern "C" {
     pub fn az_replay_add_dev(rp: *mut az_replay, samples_dev: *const az_sample, n: c_int, new_unique: *mut c_int) -> c_int;
     pub fn az_replay_len(rp: *mut az_replay, len: *mut c_int) -> c_int;
     pub fn az_replay_sample(rp: *mut az_replay, batch: c_int, seed: u64, planes: *mut f32, policy: *mut f32, value: *mut f32, n_out: *mut c_int) -> c_int;
+    pub fn az_replay_sample_dev(rp: *mut az_replay, batch: c_int, seed: u64, planes_dev: *mut f32, policy_dev: *mut f32, value_dev: *mut f32, n_out: *mut c_int) -> c_int;
     pub fn az_replay_export(rp: *mut az_replay, first: c_int, n: c_int, pos: *mut az_position, policy: *mut f32, value: *mut f32,
                             visits: *mut u32, n_out: *mut c_int) -> c_int;
     pub fn az_replay_import(rp: *mut az_replay, n: c_int, pos: *const az_position, policy: *const f32, value: *const f32, visits: *const u32) -> c_int;

@@ -198,6 +198,8 @@ int az_replay_add_pending(az_replay* rp, int* n_added_out, int* new_unique_out);
 int az_replay_add_dev(az_replay* rp, const az_sample* samples_dev, int n, int* new_unique_out);
 int az_replay_len(az_replay* rp, int* len_out);
 int az_replay_sample(az_replay* rp, int batch_size, uint64_t seed, float* planes_out, float* policy_out, float* value_out, int* n_out);
+/* the same batch into DEVICE memory (the trainer's input tensors): no host hop between the replay buffer and the training step */
+int az_replay_sample_dev(az_replay* rp, int batch_size, uint64_t seed, float* planes_dev, float* policy_dev, float* value_dev, int* n_out);
 int az_replay_export(az_replay* rp, int first, int n, az_position* pos_out, float* policy_out, float* value_out, uint32_t* visits_out,
                      int* n_out);
 int az_replay_import(az_replay* rp, int n, const az_position* pos, const float* policy, const float* value, const uint32_t* visits);

@@ -116,6 +116,10 @@ def test_sample_contract(played):
         assert gn >= 1 and np.array_equal(gp, policy[k]) and gv == value[k]
     p2, _, _ = gpu.sample(512, seed=3)
     assert p2.tobytes() != planes.tobytes()
+    # the device-resident path (az_replay_sample_dev into CUDA tensors) returns the very same batch
+    tp, tpi, tv = gpu.sample_torch(512, seed=2)
+    assert tp.is_cuda and np.array_equal(tp.cpu().numpy(), planes) and np.array_equal(tpi.cpu().numpy(), policy)
+    assert np.array_equal(tv.cpu().numpy(), value)
     gpu.close()
 
 
