@@ -72,3 +72,32 @@ def test_oracle_weight_catalogue_equals_the_abi():
     assert [s for _, s in cat] == az.weight_sizes()
     a, b = orc.random_weights(seed=42), az.random_weights(seed=42)
     assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/az_b200.h is a C header (the boundary a cgo / Rust-sys / ctypes binding consumes): a C99 program compiled
+    with gcc links against libaz_b200.so, reads the defaults of parameters.rs and the struct sizes the bindings assume."""
+    import subprocess
+
+    src = tmp_path / "abi.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "az_b200.h"
+int main(void) {
+    az_config c;
+    az_position p;
+    az_config_default(&c);
+    az_position_start(&p);
+    printf("%s|%d|%g|%g|%u|%zu|%zu|%zu|%zu|%d|%lld\n", az_version(), c.num_simulations, (double)c.c_puct, (double)c.temperature,
+           c.temperature_annealing, sizeof(az_config), sizeof(az_position), sizeof(az_sample), sizeof(az_selfplay_stats),
+           (int)p.castling, (long long)az_weight_size(0));
+    return 0;
+}
+''')
+    exe = tmp_path / "abi"
+    libdir = os.path.dirname(az.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", libdir, "-l:libaz_b200.so", f"-Wl,-rpath,{libdir}"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.strip().split("|")
+    assert out[1:] == ["256", "3", "1", "15", "72", "72", "1120", str(8 * 14), "15", str(128 * 19 * 9)], out
+    assert ctypes.sizeof(az.SelfplayStats) == 8 * 14 and ctypes.sizeof(az.Config) == 72
