@@ -247,7 +247,8 @@ __device__ __forceinline__ int create_node(Ctx& x, int depth) {
     return node;
 }
 
-// Queues the position in sh->child for evaluation; returns the batch slot.
+// Queues the position in sh->child (the node create_node made last: its edge range is in x.new_link) for evaluation;
+// returns the batch slot.
 __device__ __forceinline__ int submit_request(Ctx& x, int node) {
     int slot = 0;
     if (x.lane == 0) slot = atomicAdd(x.ptr.batch_count, 1);
@@ -255,8 +256,9 @@ __device__ __forceinline__ int submit_request(Ctx& x, int node) {
     const DPos child = x.sh->child;
     if (x.lane == 0) {
         x.ptr.req_pos[slot] = child;
-        x.ptr.req_edge_off[slot] = (unsigned long long)(x.ebase + x.ptr.node_edge_off[x.nbase + node]);
-        x.ptr.req_nedges[slot] = (int)x.ptr.node_nedges[x.nbase + node];
+        (void)node;
+        x.ptr.req_edge_off[slot] = (unsigned long long)(x.ebase + (size_t)(x.new_link >> 24));
+        x.ptr.req_nedges[slot] = (int)((x.new_link >> 16) & 0xFF);
     }
     if (x.prm.fp32_planes) {
         const u64 occ = occupied(child);
