@@ -267,7 +267,7 @@ __device__ __forceinline__ int submit_request(Ctx& x, int node) {
         float* out = x.ptr.req_f32 + (size_t)slot * (AZ_NUM_PLANES * 64);
         for (int e = x.lane; e < AZ_NUM_PLANES * 64; e += 32) out[e] = plane_value(child, e >> 6, e & 63, pep, ours, occ ^ ours);
     } else {
-        encode_bf16_warp(child, x.ptr.req_bf16 + (size_t)slot * 4096, x.lane);
+        encode_bf16_warp(child, x.ptr.req_bf16 + (size_t)slot * 64 * x.prm.plane_ch, x.lane, x.prm.plane_ch);
     }
     if (x.lane == 0) x.st_evals++;
     return slot;
@@ -955,6 +955,7 @@ int search_create(az_engine* e) {
     if (!(c.temperature > 0.0f)) return set_err(e, AZ_ERR_INVALID_ARGUMENT, "temperature must be positive");
     p.inv_temperature = 1.0f / c.temperature;
     p.fp32_planes = c.precision == 1 ? 1 : 0;
+    p.plane_ch = e->net->in_ch;
     // finished games' samples wait here for az_selfplay_drain / az_replay_add_pending; a game that does not fit parks until
     // the host has drained (finish_game), so the only hard requirement is room for one whole game
     p.sample_cap = std::max(G * 128, 1 << 16);
@@ -1209,7 +1210,7 @@ int az_selfplay_begin_n(az_engine* e, int n_games, uint64_t first_game_id, uint6
         launch_encode_f32(e->stream, e->d_wire, e->d_planes, 1);
         r = net_forward_fp32(e, e->d_planes, nullptr, 1, e->d_policy, e->d_value);
     } else {
-        launch_encode_bf16_wire(e->stream, e->d_wire, e->net->a_in, 1);
+        launch_encode_bf16_wire(e->stream, e->d_wire, e->net->a_in, 1, e->net->in_ch);
         r = net_forward_bf16(e, nullptr, 1, e->d_policy, e->d_value);
     }
     if (r) return r;

@@ -36,6 +36,7 @@ struct SearchParams {
     int mode;        // 0: az_search (stop after S simulations), 1: self-play
     int max_iters;   // simulations a game may complete per wave without needing the network
     int fp32_planes; // 1: requests are written as f32 NCHW planes, 0: bf16 NHWC
+    int plane_ch;    // channel pitch of the bf16 plane buffer (32; 64 with AZ_INPUT_K32=0)
     int sample_cap;
     uint32_t cache_mask;  // slots - 1 (0: cache disabled)
     int priors_scattered; // 1: the evaluator already wrote the legal-move priors into edge_P (fused heads)
@@ -97,7 +98,7 @@ struct SearchPtrs {
     // evaluation requests / results
     int* batch_count;
     DPos* req_pos;             // [max_batch]
-    __nv_bfloat16* req_bf16;   // [max_batch][64][64]
+    __nv_bfloat16* req_bf16;   // [max_batch][64][plane_ch]
     float* req_f32;            // [max_batch][19][64]
     unsigned long long* req_edge_off;  // [max_batch] first edge (global index) of the node each request will fill
     int* req_nedges;           // [max_batch]

@@ -64,16 +64,18 @@ int net_create(az_engine* e) {
     r |= dmalloc(e, &w->f_wp2t, 32 * 64); r |= dmalloc(e, &w->f_bp2, 64);
     r |= dmalloc(e, &w->f_wl1, 512 * 64); r |= dmalloc(e, &w->f_bl1, 64);
     r |= dmalloc(e, &w->f_wl2, 64); r |= dmalloc(e, &w->f_bl2, 1);
-    r |= dmalloc(e, &w->h_w_in, 9 * 128 * 64); r |= dmalloc(e, &w->h_w_tower, (size_t)20 * 9 * 128 * 128);
+    w->in_ch = e->knobs.input_k32 ? 32 : 64;
+    const int ic = w->in_ch;
+    r |= dmalloc(e, &w->h_w_in, (size_t)9 * 128 * ic); r |= dmalloc(e, &w->h_w_tower, (size_t)20 * 9 * 128 * 128);
     r |= dmalloc(e, &w->h_w40, 40 * 128); r |= dmalloc(e, &w->h_wp2, 64 * 32); r |= dmalloc(e, &w->h_wl1t, 64 * 512);
-    r |= dmalloc(e, &w->a_in, nb * 64 * 64);
+    r |= dmalloc(e, &w->a_in, nb * 64 * ic);
     for (int i = 0; i < 3; i++) r |= dmalloc(e, &w->a_buf[i], nb * 64 * 128);
     if (r) return AZ_ERR_OUT_OF_MEMORY;
-    cudaMemset(w->a_in, 0, nb * 64 * 64 * 2);
-    if (tc_make_act_map(&w->map_a_in, w->a_in, 64, e->max_batch)) return set_err(e, AZ_ERR_CUDA, "cuTensorMapEncodeTiled(a_in)");
+    cudaMemset(w->a_in, 0, nb * 64 * ic * 2);
+    if (tc_make_act_map(&w->map_a_in, w->a_in, ic, e->max_batch)) return set_err(e, AZ_ERR_CUDA, "cuTensorMapEncodeTiled(a_in)");
     for (int i = 0; i < 3; i++)
         if (tc_make_act_map(&w->map_a[i], w->a_buf[i], 128, e->max_batch)) return set_err(e, AZ_ERR_CUDA, "cuTensorMapEncodeTiled(act)");
-    if (tc_make_weight_map(&w->map_w_in, w->h_w_in, 64)) return set_err(e, AZ_ERR_CUDA, "cuTensorMapEncodeTiled(w_in)");
+    if (tc_make_weight_map(&w->map_w_in, w->h_w_in, ic)) return set_err(e, AZ_ERR_CUDA, "cuTensorMapEncodeTiled(w_in)");
     for (int l = 0; l < 20; l++)
         if (tc_make_weight_map(&w->map_w_tower[l], w->h_w_tower + (size_t)l * 9 * 128 * 128, 128))
             return set_err(e, AZ_ERR_CUDA, "cuTensorMapEncodeTiled(w_tower)");
@@ -123,11 +125,12 @@ static int load_from_host(az_engine* e, const float* const* a) {
     r |= upload(e, w->f_w_in, fw.data(), 128 * 19 * 9 * 4);
     r |= upload(e, w->f_b_in, fb.data(), 128 * 4);
     r |= upload(e, w->f_b_tower + 20 * 128, fb.data(), 128 * 4);
+    const int ic = w->in_ch;
     for (int tap = 0; tap < 9; tap++)
         for (int co = 0; co < 128; co++)
-            for (int ci = 0; ci < 64; ci++)
-                hw[((size_t)tap * 128 + co) * 64 + ci] = __float2bfloat16_rn(ci < 19 ? fw[((size_t)co * 19 + ci) * 9 + tap] : 0.0f);
-    r |= upload(e, w->h_w_in, hw.data(), 9 * 128 * 64 * 2);
+            for (int ci = 0; ci < ic; ci++)
+                hw[((size_t)tap * 128 + co) * ic + ci] = __float2bfloat16_rn(ci < 19 ? fw[((size_t)co * 19 + ci) * 9 + tap] : 0.0f);
+    r |= upload(e, w->h_w_in, hw.data(), (size_t)9 * 128 * ic * 2);
     AZ_CUDA(e, cudaStreamSynchronize(e->stream));
     for (int l = 0; l < 20; l++) {
         const int o = 6 + (l / 2) * 12 + (l % 2) * 6;
@@ -164,11 +167,11 @@ static int load_from_host(az_engine* e, const float* const* a) {
 }
 
 // ---------------------------------------------------------------------------------------------- plane converters
-__global__ void k_planes_to_bf16(const float* __restrict__ planes, __nv_bfloat16* __restrict__ out, int n) {
-    // out [n][64 sq][64 ch]; one thread per (board, square, 8-channel chunk)
+__global__ void k_planes_to_bf16(const float* __restrict__ planes, __nv_bfloat16* __restrict__ out, int n, int chunks) {
+    // out [n][64 sq][ch]; one thread per (board, square, 8-channel chunk); chunks = ch / 8 (8 or 4)
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (size_t)n * 512) return;
-    const int b = (int)(i >> 9), sq = (int)((i >> 3) & 63), chunk = (int)(i & 7);
+    if (i >= (size_t)n * 64 * chunks) return;
+    const int b = (int)(i / (size_t)(64 * chunks)), sq = (int)((i / chunks) & 63), chunk = (int)(i % chunks);
     uint32_t packed[4] = {0, 0, 0, 0};
     if (chunk < 3) {
         for (int j = 0; j < 8; j++) {
@@ -180,17 +183,17 @@ __global__ void k_planes_to_bf16(const float* __restrict__ planes, __nv_bfloat16
     }
     reinterpret_cast<uint4*>(out)[i] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
 }
-void launch_planes_to_bf16(cudaStream_t s, const float* planes, __nv_bfloat16* out, int n) {
-    if (n > 0) k_planes_to_bf16<<<(unsigned)(((size_t)n * 512 + 255) / 256), 256, 0, s>>>(planes, out, n);
+void launch_planes_to_bf16(cudaStream_t s, const float* planes, __nv_bfloat16* out, int n, int ch) {
+    if (n > 0) k_planes_to_bf16<<<(unsigned)(((size_t)n * 8 * ch + 255) / 256), 256, 0, s>>>(planes, out, n, ch / 8);
 }
-__global__ void k_encode_bf16_wire(const az_position* __restrict__ wire, __nv_bfloat16* __restrict__ out, int n) {
+__global__ void k_encode_bf16_wire(const az_position* __restrict__ wire, __nv_bfloat16* __restrict__ out, int n, int ch) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= n) return;
     DPos p = dpos_from_wire(wire[warp]);
-    encode_bf16_warp(p, out + (size_t)warp * 4096, lane);
+    encode_bf16_warp(p, out + (size_t)warp * 64 * ch, lane, ch);
 }
-void launch_encode_bf16_wire(cudaStream_t s, const az_position* wire, __nv_bfloat16* out, int n) {
-    if (n > 0) k_encode_bf16_wire<<<(n + 3) / 4, 128, 0, s>>>(wire, out, n);
+void launch_encode_bf16_wire(cudaStream_t s, const az_position* wire, __nv_bfloat16* out, int n, int ch) {
+    if (n > 0) k_encode_bf16_wire<<<(n + 3) / 4, 128, 0, s>>>(wire, out, n, ch);
 }
 
 // ---------------------------------------------------------------------------------------------- fp32 convolution
@@ -348,11 +351,12 @@ int net_forward_bf16(az_engine* e, const int* n_dev, int n_static, float* policy
     // AZ_TOWER_FUSED: 1 (default) = input convolution + one launch for the 20 tower layers, 2 = the input convolution runs as
     // an extra first layer of that launch (measured: 48 us inside vs 60 us alone per 4096 boards, epilogue-bound either
     // way, so the wave gains 0.2 % -- kept as an option), 0 = 21 launches
-    const int fused = e->knobs.tower_fused;
+    // the input convolution can only run inside the tower launch (mode 2) with the 64-channel plane layout
+    const int fused = (e->knobs.tower_fused >= 2 && w->in_ch != 64) ? 1 : e->knobs.tower_fused;
     int r = 0;
     if (fused < 2) {
         e->n_launches += 1;
-        r = tc_conv3x3_launch(e->stream, &w->map_a_in, &w->map_w_in, 64, w->f_b_in, nullptr, w->a_buf[0], n_dev, n_static, 1, grid, rel ? 32 : 0);
+        r = tc_conv3x3_launch(e->stream, &w->map_a_in, &w->map_w_in, w->in_ch, w->f_b_in, nullptr, w->a_buf[0], n_dev, n_static, 1, grid, rel ? 32 : 0);
         if (r) return set_err(e, AZ_ERR_CUDA, "tc conv (input) launch failed");
     }
     if (sample) {
@@ -489,7 +493,7 @@ int az_forward_planes(az_engine* e, int n, const float* planes, float* policy_ou
     if (e->cfg.precision == 1) {
         r = net_forward_fp32(e, e->d_planes, nullptr, n, e->d_policy, e->d_value);
     } else {
-        launch_planes_to_bf16(e->stream, e->d_planes, e->net->a_in, n);
+        launch_planes_to_bf16(e->stream, e->d_planes, e->net->a_in, n, e->net->in_ch);
         r = net_forward_bf16(e, nullptr, n, e->d_policy, e->d_value);
     }
     if (r) return r;
@@ -508,7 +512,7 @@ int az_forward(az_engine* e, int n, const az_position* pos, float* policy_out, f
         launch_encode_f32(e->stream, e->d_wire, e->d_planes, n);
         r = net_forward_fp32(e, e->d_planes, nullptr, n, e->d_policy, e->d_value);
     } else {
-        launch_encode_bf16_wire(e->stream, e->d_wire, e->net->a_in, n);
+        launch_encode_bf16_wire(e->stream, e->d_wire, e->net->a_in, n, e->net->in_ch);
         r = net_forward_bf16(e, nullptr, n, e->d_policy, e->d_value);
     }
     if (r) return r;

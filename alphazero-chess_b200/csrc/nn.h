@@ -18,6 +18,7 @@ struct HeadScatter {
 struct NetWeights {
     bool loaded = false;
     int max_boards = 0;
+    int in_ch = 32;   // channel pitch of the bf16 plane buffer a_in: 32 (default: half the TMA bytes and MMAs of the input convolution) or 64 (AZ_INPUT_K32=0)
     // ---- fp32 parameters, BatchNorm folded: conv weights [co][ci][3][3], head matrices as documented in nn.cu
     float* f_w_in = nullptr;     // [128][19][9]
     float* f_b_in = nullptr;     // [128]
@@ -32,7 +33,7 @@ struct NetWeights {
     float* f_wl2 = nullptr;      // [64]
     float* f_bl2 = nullptr;      // [1]
     // ---- bf16 tensor-core operands: [tap][co][ci]
-    __nv_bfloat16* h_w_in = nullptr;     // [9][128][64]  (19 channels zero-padded to 64)
+    __nv_bfloat16* h_w_in = nullptr;     // [9][128][in_ch]  (19 channels zero-padded to in_ch)
     __nv_bfloat16* h_w_tower = nullptr;  // [20][9][128][128]
     __nv_bfloat16* h_w40 = nullptr;      // [40][128]  heads stage 1 (policy_conv_1 | value_conv), BN folded
     __nv_bfloat16* h_wp2 = nullptr;      // [64][32]   policy_conv_2
@@ -40,7 +41,7 @@ struct NetWeights {
     CUtensorMap map_w_in;
     CUtensorMap map_w_tower[20];
     // ---- activations
-    __nv_bfloat16* a_in = nullptr;       // [max_boards][64 squares][64 ch]
+    __nv_bfloat16* a_in = nullptr;       // [max_boards][64 squares][in_ch]
     __nv_bfloat16* a_buf[3] = {nullptr, nullptr, nullptr};  // [max_boards][64][128]
     CUtensorMap map_a_in;
     CUtensorMap map_a[3];
@@ -59,17 +60,17 @@ int net_forward_fp32(az_engine* e, const float* planes, const int* n_dev, int n_
 // fused heads on warp-level tensor-core MMAs (nn_heads.cu); tower = NHWC bf16 [n][64][128]
 int launch_heads_mma(az_engine* e, const __nv_bfloat16* tower, const int* n_dev, int n_static, float* policy_out, float* value_out,
                      const HeadScatter* scatter);
-// f32 NCHW planes -> bf16 NHWC (64 channels) into net->a_in
-void launch_planes_to_bf16(cudaStream_t s, const float* planes, __nv_bfloat16* out, int n);
+// f32 NCHW planes -> bf16 NHWC (`ch` = 64 or 32 channels per square) into net->a_in
+void launch_planes_to_bf16(cudaStream_t s, const float* planes, __nv_bfloat16* out, int n, int ch);
 // positions -> bf16 NHWC planes (to_tensor fused with the layout the first convolution wants)
-void launch_encode_bf16_wire(cudaStream_t s, const az_position* wire, __nv_bfloat16* out, int n);
+void launch_encode_bf16_wire(cudaStream_t s, const az_position* wire, __nv_bfloat16* out, int n, int ch);
 
 // device helper used by the search kernels: writes the 64x64 bf16 plane tile of one position (one warp)
 #ifdef __CUDACC__
-__device__ __forceinline__ void encode_bf16_warp(const DPos& p, __nv_bfloat16* out /*[64][64]*/, int lane) {
-    // to_tensor (chess.rs:191-245) in the layout the first convolution reads: [square][64 channels] bf16, 19 channels used.
+__device__ __forceinline__ void encode_bf16_warp(const DPos& p, __nv_bfloat16* out /*[64][ch]*/, int lane, int ch = 64) {
+    // to_tensor (chess.rs:191-245) in the layout the first convolution reads: [square][ch channels] bf16 (ch = 64 or 32), 19 used.
     // Each lane builds two squares: one piece plane at most, four constant castling planes, ep, two constant counters.
-    // Channels 24..63 of every square stay zero (zero-filled at allocation, never written).
+    // Channels 24..ch-1 of every square stay zero (zero-filled at allocation, never written).
     const int turn = meta_turn(p.meta);
     const u64 occ = occupied(p);
     const u64 ours = turn == 0 ? p.white : occ ^ p.white;
@@ -101,7 +102,7 @@ __device__ __forceinline__ void encode_bf16_warp(const DPos& p, __nv_bfloat16* o
         w[7] = castle_hi;
         w[8] = (sq == pep ? ONE : 0u) | (hm_bits << 16);                    // planes 16, 17
         w[9] = fm_bits;                                                    // plane 18 (19 is padding)
-        uint4* o = reinterpret_cast<uint4*>(out) + sqc * 8;
+        uint4* o = reinterpret_cast<uint4*>(out) + sqc * (ch >> 3);
         o[0] = make_uint4(w[0], w[1], w[2], w[3]);
         o[1] = make_uint4(w[4], w[5], w[6], w[7]);
         o[2] = make_uint4(w[8], w[9], 0u, 0u);

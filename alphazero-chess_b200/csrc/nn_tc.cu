@@ -26,12 +26,16 @@ namespace azb {
 constexpr int kStageBytes = 160 * 128;   // {10 ranks x 2 boards x 8 files} rows x 64 channels bf16
 constexpr int kWTileBytes = 64 * 128;    // 64 output channels x 64 input channels bf16
 
-template <int HALVES>
+// KROW = bytes per operand row in shared memory = input channels per K block x 2: 128 (64 channels, 128-byte swizzle) for the
+// tower and the 64-channel plane layout, 64 (32 channels, 64-byte swizzle) for the 32-channel plane layout of the input convolution
+template <int HALVES, int KROW = 128>
 struct ConvSmem {
     static constexpr int kStages = HALVES == 2 ? 4 : 6;
     static constexpr int kWTiles = HALVES * 9;
-    static constexpr int kWBytes = kWTiles * kWTileBytes;
-    static constexpr int kABytes = kStages * kStageBytes;
+    static constexpr int kStageB = 160 * KROW;
+    static constexpr int kWTileB = 64 * KROW;
+    static constexpr int kWBytes = kWTiles * kWTileB;
+    static constexpr int kABytes = kStages * kStageB;
     static constexpr int kMisc = 2048;
     static constexpr int kTotal = kWBytes + kABytes + kMisc + 1024;  // + alignment slack
 };
@@ -56,12 +60,14 @@ constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreads2 = 64 + kEpiThreads;   // warp 0 TMA, warp 1 MMA/TMEM, then the epilogue warps
 static_assert(kEpiWarps == 8 || kEpiWarps == 16, "epilogue warps: 8 or 16");
 
-template <int HALVES>
+template <int HALVES, int KROW>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap w_map,
                    const float* __restrict__ bias, const __nv_bfloat16* __restrict__ residual,
                    __nv_bfloat16* __restrict__ out, const int* __restrict__ n_boards_ptr, int n_boards_static, int relu, int dbg) {
-    using S = ConvSmem<HALVES>;
+    using S = ConvSmem<HALVES, KROW>;
+    constexpr int kStageBytes = S::kStageB, kWTileBytes = S::kWTileB;   // shadow the 128-byte-row constants of the tower
+    constexpr int KSTEPS = KROW / 32;                                   // K = 16 elements = 32 bytes per MMA
     constexpr int NS = S::kStages;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -128,7 +134,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
         if (rank == 0) {
             // ------------------------------------------------------------ MMA issuer (leader CTA, warp-uniform loop)
             constexpr uint32_t idesc = umma_idesc_bf16(256, 128);
-            const uint64_t dbase = umma_desc_base_sw128();
+            const uint64_t dbase = KROW == 128 ? umma_desc_base_sw128() : umma_desc_base_sw64();
             const uint32_t w_lo = (smem_u32(w_sm) & 0x3FFFF) >> 4;
             int stage = 0; uint32_t phase = 0; int lt = 0;
             for (int t = first_tile; t < n_tiles; t += tile_step, lt++) {
@@ -148,8 +154,8 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
 #pragma unroll
                             for (int dyi = 0; dyi < 3; dyi++) {
 #pragma unroll
-                                for (int k = 0; k < 4; k++) {
-                                    const uint64_t ad = dbase | (uint64_t)(a_lo + dyi * (2048 >> 4) + k * 2);
+                                for (int k = 0; k < KSTEPS; k++) {
+                                    const uint64_t ad = dbase | (uint64_t)(a_lo + dyi * ((16 * KROW) >> 4) + k * 2);
                                     const uint64_t bd = dbase | (uint64_t)(b_lo + dyi * (kWTileBytes >> 4) + k * 2);
                                     if (!(dbg & 2)) umma2_bf16(d_tmem, ad, bd, idesc, (half | dxi | dyi | k) != 0 ? 1u : 0u);
                                 }
@@ -554,10 +560,11 @@ int tc_make_act_map(CUtensorMap* map, const void* base, int channels, int max_bo
     // dims fastest-first: channel, file, board, rank  (SMEM box order becomes [rank][board][file][channel])
     cuuint64_t dims[4] = {(cuuint64_t)channels, 8, (cuuint64_t)max_boards, 8};
     cuuint64_t strides[3] = {(cuuint64_t)channels * 2, (cuuint64_t)channels * 2 * 64, (cuuint64_t)channels * 2 * 8};
-    cuuint32_t box[4] = {64, 8, 2, 10};
+    // 64 channels (128-byte rows, 128-byte swizzle) per box, or the whole row of the 32-channel plane layout (64-byte swizzle)
+    cuuint32_t box[4] = {(cuuint32_t)(channels == 32 ? 32 : 64), 8, 2, 10};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, channels == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : -(int)r - 1000;
 }
@@ -567,10 +574,10 @@ int tc_make_weight_map(CUtensorMap* map, const void* base, int cin) {
     if (!enc) return -1;
     cuuint64_t dims[2] = {(cuuint64_t)cin, 9 * 128};
     cuuint64_t strides[1] = {(cuuint64_t)cin * 2};
-    cuuint32_t box[2] = {64, 64};
+    cuuint32_t box[2] = {(cuuint32_t)(cin == 32 ? 32 : 64), 64};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, cin == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : -(int)r - 1000;
 }
@@ -579,18 +586,22 @@ int tc_conv3x3_launch(cudaStream_t stream, const CUtensorMap* in_map, const CUte
                       const void* residual, void* out, const int* n_boards_dev, int n_boards_static, int relu, int grid, int dbg) {
     static PerDeviceOnce once;
     if (once.first()) {
-        cudaError_t e1 = cudaFuncSetAttribute(conv3x3_tc2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<1>::kTotal);
-        cudaError_t e2 = cudaFuncSetAttribute(conv3x3_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<2>::kTotal);
-        if (e1 != cudaSuccess || e2 != cudaSuccess) return -2;
+        cudaError_t e1 = cudaFuncSetAttribute(conv3x3_tc2_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<1>::kTotal);
+        cudaError_t e2 = cudaFuncSetAttribute(conv3x3_tc2_kernel<2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<2>::kTotal);
+        cudaError_t e3 = cudaFuncSetAttribute(conv3x3_tc2_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<1, 64>::kTotal);
+        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) return -2;
     }
     if (grid <= 0) grid = 148;
     grid &= ~1;  // CTA pairs
-    if (cin == 64)
-        conv3x3_tc2_kernel<1><<<grid, kThreads2, ConvSmem<1>::kTotal, stream>>>(*in_map, *w_map, bias, (const __nv_bfloat16*)residual,
-                                                                               (__nv_bfloat16*)out, n_boards_dev, n_boards_static, relu, dbg);
+    if (cin == 32)
+        conv3x3_tc2_kernel<1, 64><<<grid, kThreads2, ConvSmem<1, 64>::kTotal, stream>>>(*in_map, *w_map, bias, (const __nv_bfloat16*)residual,
+                                                                                       (__nv_bfloat16*)out, n_boards_dev, n_boards_static, relu, dbg);
+    else if (cin == 64)
+        conv3x3_tc2_kernel<1, 128><<<grid, kThreads2, ConvSmem<1>::kTotal, stream>>>(*in_map, *w_map, bias, (const __nv_bfloat16*)residual,
+                                                                                    (__nv_bfloat16*)out, n_boards_dev, n_boards_static, relu, dbg);
     else if (cin == 128)
-        conv3x3_tc2_kernel<2><<<grid, kThreads2, ConvSmem<2>::kTotal, stream>>>(*in_map, *w_map, bias, (const __nv_bfloat16*)residual,
-                                                                               (__nv_bfloat16*)out, n_boards_dev, n_boards_static, relu, dbg);
+        conv3x3_tc2_kernel<2, 128><<<grid, kThreads2, ConvSmem<2>::kTotal, stream>>>(*in_map, *w_map, bias, (const __nv_bfloat16*)residual,
+                                                                                    (__nv_bfloat16*)out, n_boards_dev, n_boards_static, relu, dbg);
     else
         return -3;
     return cudaGetLastError() == cudaSuccess ? 0 : -4;

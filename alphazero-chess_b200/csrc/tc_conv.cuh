@@ -145,6 +145,10 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ uint64_t umma_desc_base_sw128() {
     return ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
+// The same for 64-byte rows (32 bf16 channels): SWIZZLE_64B (layout type 4), 8-row groups 512 B apart.
+__device__ __forceinline__ uint64_t umma_desc_base_sw64() {
+    return ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
+}
 // instruction descriptor: bf16 x bf16 -> fp32, both operands K-major
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);

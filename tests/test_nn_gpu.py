@@ -92,12 +92,14 @@ import sys, hashlib
 sys.path.insert(0, {tests!r})
 import _pkg  # noqa: F401
 import alphazero_chess_b200 as az
-from helpers import random_playouts
+from helpers import orc, random_playouts
 p, _ = random_playouts(150, seed=8, max_plies=100)
+live = p[[i for i in range(len(p)) if orc.outcome(p[i]) == 0][:40]]
 with az.Engine(max_games=256, precision=0) as e:
     e.load_weights(az.random_weights(seed=3, randomize_bn=True))
     pol, val = e.forward(p)
-print("DIGEST", hashlib.sha256(pol.tobytes() + val.tobytes()).hexdigest())
+    visits = e.search(live, num_simulations=24)[0]   # the search kernel writes its own planes (encode_bf16_warp)
+print("DIGEST", hashlib.sha256(pol.tobytes() + val.tobytes() + visits.tobytes()).hexdigest())
 """
 
 
@@ -110,8 +112,10 @@ def test_launch_modes_give_identical_bits():
     here = os.path.dirname(os.path.abspath(__file__))
     digests = []
     # the last two also force three board ranges inside the tower launch (ranges with and without tiles for a CTA pair)
-    for mode, split in (("0", None), ("1", None), ("2", None), ("1", "3"), ("2", "3")):
-        env = dict(os.environ, AZ_TOWER_FUSED=mode)
+    # and AZ_INPUT_K32=1 (32-channel plane layout: the two K blocks it drops per tap only ever added exact zeros)
+    for mode, split, k32 in (("0", None, "0"), ("1", None, "0"), ("2", None, "0"), ("1", "3", "0"), ("2", "3", "0"), ("1", None, "1"), ("0", None, "1"),
+                             ("2", "3", "1")):
+        env = dict(os.environ, AZ_TOWER_FUSED=mode, AZ_INPUT_K32=k32)
         if split:
             env["AZ_TOWER_SPLIT"] = split
         out = subprocess.run([sys.executable, "-c", _MODE_SCRIPT.format(tests=here)], env=env, capture_output=True, text=True, timeout=300)
