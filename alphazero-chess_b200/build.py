@@ -24,6 +24,7 @@ UNITS = [
     ("nn.cu", []),
     ("nn_tc.cu", []),
     ("nn_heads.cu", []),
+    ("nn_heads_tc.cu", []),
     ("replay.cu", ["-fmad=false"]),
     ("dbg.cu", []),
 ]

@@ -75,6 +75,8 @@ int net_create(az_engine* e) {
     if (tc_make_act_map(&w->map_a_in, w->a_in, ic, e->max_batch)) return set_err(e, AZ_ERR_CUDA, "cuTensorMapEncodeTiled(a_in)");
     for (int i = 0; i < 3; i++)
         if (tc_make_act_map(&w->map_a[i], w->a_buf[i], 128, e->max_batch)) return set_err(e, AZ_ERR_CUDA, "cuTensorMapEncodeTiled(act)");
+    for (int i = 0; i < 3; i++)
+        if (tc_make_rows_map(&w->map_rows[i], w->a_buf[i], e->max_batch)) return set_err(e, AZ_ERR_CUDA, "cuTensorMapEncodeTiled(rows)");
     if (tc_make_weight_map(&w->map_w_in, w->h_w_in, ic)) return set_err(e, AZ_ERR_CUDA, "cuTensorMapEncodeTiled(w_in)");
     for (int l = 0; l < 20; l++)
         if (tc_make_weight_map(&w->map_w_tower[l], w->h_w_tower + (size_t)l * 9 * 128 * 128, 128))
@@ -403,7 +405,8 @@ int net_forward_bf16(az_engine* e, const int* n_dev, int n_static, float* policy
         x = z;
     }
     if (sample) cudaEventRecord(ps.b, e->stream);
-    const int hr = launch_heads_mma(e, w->a_buf[x], n_dev, n_static, policy_out, value_out, scatter);
+    const int hr = e->knobs.heads_tc ? launch_heads_tc(e, &w->map_rows[x], n_dev, n_static, policy_out, value_out, scatter)
+                                     : launch_heads_mma(e, w->a_buf[x], n_dev, n_static, policy_out, value_out, scatter);
     if (sample) {
         cudaEventCreate(&ps.h1); cudaEventRecord(ps.h1, e->stream);
         // the batch size of this wave, copied after the last bracketed phase so that the copy is not timed as part of one

@@ -45,6 +45,7 @@ struct NetWeights {
     __nv_bfloat16* a_buf[3] = {nullptr, nullptr, nullptr};  // [max_boards][64][128]
     CUtensorMap map_a_in;
     CUtensorMap map_a[3];
+    CUtensorMap map_rows[3];             // a_buf[i] as [max_boards * 64][128] (heads on tcgen05)
     CUtensorMap* d_maps = nullptr;       // device copy {map_a[0..2], map_w_tower[0..19]} for the fused tower kernel
     float* g_buf[3] = {nullptr, nullptr, nullptr};          // fp32 path, NCHW [max_boards][128][64] (allocated lazily)
 };
@@ -60,6 +61,9 @@ int net_forward_fp32(az_engine* e, const float* planes, const int* n_dev, int n_
 // fused heads on warp-level tensor-core MMAs (nn_heads.cu); tower = NHWC bf16 [n][64][128]
 int launch_heads_mma(az_engine* e, const __nv_bfloat16* tower, const int* n_dev, int n_static, float* policy_out, float* value_out,
                      const HeadScatter* scatter);
+// the same heads on tcgen05 (nn_heads_tc.cu, AZ_HEADS_TC=1): tiles of two boards, stage 1 and 2 as UMMA, softmax per pixel thread
+int launch_heads_tc(az_engine* e, const CUtensorMap* act_rows_map, const int* n_dev, int n_static, float* policy_out, float* value_out,
+                    const HeadScatter* scatter);
 // f32 NCHW planes -> bf16 NHWC (`ch` = 64 or 32 channels per square) into net->a_in
 void launch_planes_to_bf16(cudaStream_t s, const float* planes, __nv_bfloat16* out, int n, int ch);
 // positions -> bf16 NHWC planes (to_tensor fused with the layout the first convolution wants)

@@ -569,6 +569,20 @@ int tc_make_act_map(CUtensorMap* map, const void* base, int channels, int max_bo
     return r == CUDA_SUCCESS ? 0 : -(int)r - 1000;
 }
 
+int tc_make_rows_map(CUtensorMap* map, const void* base, int max_boards) {
+    // the same NHWC activation buffer seen as a matrix [max_boards * 64 pixel rows][128 channels]: boxes of 128 rows x 64 channels
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return -1;
+    cuuint64_t dims[2] = {128, (cuuint64_t)max_boards * 64};
+    cuuint64_t strides[1] = {256};
+    cuuint32_t box[2] = {64, 128};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -(int)r - 1000;
+}
+
 int tc_make_weight_map(CUtensorMap* map, const void* base, int cin) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) return -1;

@@ -6,6 +6,8 @@
 namespace azb {
 // activations: NHWC bf16 [max_boards][8][8][channels], channels in {64, 128}
 int tc_make_act_map(CUtensorMap* map, const void* base, int channels, int max_boards);
+// the same buffer as a matrix [max_boards * 64 pixel rows][128 channels] for the tcgen05 heads (nn_heads_tc.cu)
+int tc_make_rows_map(CUtensorMap* map, const void* base, int max_boards);
 // weights: bf16 [9 taps][128 out][cin], BatchNorm already folded
 int tc_make_weight_map(CUtensorMap* map, const void* base, int cin);
 // out = act( conv3x3(in) + bias (+ residual) ); the board count is read from n_boards_dev when non-null
