@@ -37,6 +37,7 @@ constexpr int kThreads = 64 + kEpiThreads;               // warp 0 TMA, warp 1 M
 constexpr int kTmemCols = 512;                           // per group: D1 at +0 (48 columns), D2 slots at +64 and +128
 static_assert(kOffW40 % 1024 == 0 && kOffW2 % 1024 == 0 && kOffP1 % 1024 == 0 && kOffExp % 1024 == 0, "operand tiles must be 1024-byte aligned");
 static_assert(kTotal <= 232448, "shared memory of one CTA");
+static_assert(2 * kThreads >= 48 * 16, "two weight chunks per thread cover W40");
 }  // namespace htc
 
 // ---------------------------------------------------------------- cta_group::1 forms of the primitives in tc_conv.cuh
@@ -136,10 +137,49 @@ k_heads_tc(const __grid_constant__ CUtensorMap act_map, const __nv_bfloat16* __r
     long long tacc[16] = {}, tlast = clock64();
     const long long tbegin = tlast;
 #endif
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    // The weight tiles are requested first and stored after everything that needs the board count: the count is a dependent
+    // global load itself (the search kernel's batch counter), and the two round trips would otherwise add up in every thread
+    uint4 wreg[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)}, w2reg = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+        const int i = t + u * kThreads;
+        if (i < 40 * 16) wreg[u] = __ldg(reinterpret_cast<const uint4*>(w40) + i);
+    }
+    if (t < 64 * 4) w2reg = __ldg(reinterpret_cast<const uint4*>(wp2) + t);
+    float breg = 0.0f;
+    if (t < 40) breg = b40[t];
+    else if (t >= 64 && t < 128) breg = bp2[t - 64];
     const int n = n_dev ? *n_dev : n_static;
     const int n_tiles = (n + 1) >> 1;
-    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const int my_tiles = (int)blockIdx.x < n_tiles ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+    // ---- epilogue thread coordinates (warps 2..17); computed here because the scatter metadata of the first two tiles is requested
+    // before the set-up below, so that its (TLB-missing, ~3 us) latency overlaps the weight staging and the first TMA / MMA round trip
+    const int et = t - 64;                 // 0..511
+    const int ew = warp - 2;               // 0..15
+    const int w = ew >> 3;                 // group: tiles k = w, w + 2, ...
+    const int q = warp & 3;                // TMEM lane quarter of this warp
+    const int cg = (ew & 7) >> 2;          // column half
+    const int row = q * 32 + lane;         // pixel row of the tile
+    const int bi = q >> 1, sq = row & 63;  // board of the tile, square
+    const int ti = (q & 1) + 2 * cg;       // warp of the board's team
+    const int tid128 = sq + 64 * cg;       // thread of the board's team
+    const int nw = (my_tiles - w + 1) >> 1;
+    // Scatter metadata two tiles ahead: (first edge, edge count) of the node waiting for this thread's board, and this thread's
+    // move word one tile ahead -- the chain edge_off -> edge_mv -> edge_P would otherwise cost two dependent global round
+    // trips per tile on the critical path of the group (ncu: the top stall of the first version)
+    unsigned long long eo_cur = 0, eo_nxt = 0, eo_n2 = 0;
+    int L_cur = 0, L_nxt = 0, L_n2 = 0;
+    uint32_t mv_cur = 0, mv_nxt = 0;
+    auto meta = [&](int j, unsigned long long& eo, int& L) {
+        eo = 0; L = 0;
+        if (sc.edge_P && j < nw) {
+            const int b = ((int)blockIdx.x + (2 * j + w) * (int)gridDim.x) * 2 + bi;
+            if (b < n) { eo = sc.edge_off[b]; L = sc.n_edges[b]; }
+        }
+    };
+    if (warp >= 2) { meta(0, eo_cur, L_cur); meta(1, eo_nxt, L_nxt); }
 
     if (t == 0) {
         tma_prefetch_desc(&act_map);
@@ -157,17 +197,20 @@ k_heads_tc(const __grid_constant__ CUtensorMap act_map, const __nv_bfloat16* __r
         }
     }
     // weights into the swizzled K-major operand layouts the UMMA descriptors describe (16-byte chunks, chunk ^= row bits)
-    for (int i = t; i < 48 * 16; i += kThreads) {
-        const int r = i >> 4, ch = i & 15;
-        const uint4 v = r < 40 ? __ldg(reinterpret_cast<const uint4*>(w40) + i) : make_uint4(0, 0, 0, 0);
-        *reinterpret_cast<uint4*>(smem + kOffW40 + (ch >> 3) * kW40Block + (r >> 3) * 1024 + (r & 7) * 128 + (((ch & 7) ^ (r & 7)) << 4)) = v;
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+        const int i = t + u * kThreads;   // rows 40..47 of W40 are zero (the MMA's N is a multiple of 16)
+        if (i < 48 * 16) {
+            const int r = i >> 4, ch = i & 15;
+            *reinterpret_cast<uint4*>(smem + kOffW40 + (ch >> 3) * kW40Block + (r >> 3) * 1024 + (r & 7) * 128 + (((ch & 7) ^ (r & 7)) << 4)) = wreg[u];
+        }
     }
-    for (int i = t; i < 64 * 4; i += kThreads) {
-        const int r = i >> 2, c = i & 3;
-        *reinterpret_cast<uint4*>(smem + kOffW2 + (r >> 3) * 512 + (r & 7) * 64 + ((c ^ ((r >> 1) & 3)) << 4)) = __ldg(reinterpret_cast<const uint4*>(wp2) + i);
+    if (t < 64 * 4) {
+        const int r = t >> 2, c = t & 3;
+        *reinterpret_cast<uint4*>(smem + kOffW2 + (r >> 3) * 512 + (r & 7) * 64 + ((c ^ ((r >> 1) & 3)) << 4)) = w2reg;
     }
-    if (t < 40) s_b40[t] = b40[t];
-    if (t >= 64 && t < 128) s_b2[t - 64] = bp2[t - 64];
+    if (t < 40) s_b40[t] = breg;
+    if (t >= 64 && t < 128) s_b2[t - 64] = breg;
     fence_proxy_async_smem();   // the tensor core reads these tiles through the async proxy
     if (warp == 1) tmem1_alloc(tmem_ptr_s, kTmemCols);
     tc_fence_before();
@@ -258,36 +301,12 @@ k_heads_tc(const __grid_constant__ CUtensorMap act_map, const __nv_bfloat16* __r
         // group w (8 warps) takes the tiles k = w, w + 2, ...; inside a group warp (q, cg) owns TMEM lane quarter q (32 pixel rows)
         // and column half cg (16 of the 32 policy channels of D1, 32 of the 64 output channels of D2), so a board is a team of
         // four warps and every scheduler has four epilogue warps to switch between
-        const int et = t - 64;                 // 0..511
-        const int ew = warp - 2;               // 0..15
-        const int w = ew >> 3;
-        const int q = warp & 3;
-        const int cg = (ew & 7) >> 2;
-        const int row = q * 32 + lane;         // pixel row of the tile
-        const int bi = q >> 1, sq = row & 63;  // board of the tile, square
-        const int ti = (q & 1) + 2 * cg;       // warp of the board's team
-        const int tid128 = sq + 64 * cg;       // thread of the board's team
-        const int nw = (my_tiles - w + 1) >> 1;
         const uint32_t t_d1 = tmem_base + ((uint32_t)(q * 32) << 16) + w * 192;
         float* se = reinterpret_cast<float*>(smem + kOffExp) + (w * 2 + bi) * 4096;
         float* red = s_red + (w * 2 + bi) * 8;   // [max of the 4 warps][sum of the 4 warps]
         const int team_bar = 2 + w * 2 + bi;
 
-        // Scatter metadata two tiles ahead: (first edge, edge count) of the node waiting for this thread's board, and this thread's
-        // move word one tile ahead -- the chain edge_off -> edge_mv -> edge_P would otherwise cost two dependent global round
-        // trips per tile on the critical path of the group (ncu: the top stall of the first version)
-        unsigned long long eo_cur = 0, eo_nxt = 0;
-        int L_cur = 0, L_nxt = 0;
-        uint32_t mv_cur = 0;
-        auto meta = [&](int j, unsigned long long& eo, int& L) {
-            eo = 0; L = 0;
-            if (sc.edge_P && j < nw) {
-                const int b = ((int)blockIdx.x + (2 * j + w) * (int)gridDim.x) * 2 + bi;
-                if (b < n) { eo = sc.edge_off[b]; L = sc.n_edges[b]; }
-            }
-        };
-        meta(0, eo_cur, L_cur);
-        meta(1, eo_nxt, L_nxt);
+        if (tid128 < L_cur) mv_cur = sc.edge_mv[eo_cur + tid128];   // the first move word (edge_off / n_edges were requested at kernel entry)
 
         // stage 1 of the group's tile j: D1 -> bias, ReLU -> P1 (bf16, shared memory) + the value head's input row
         auto epi1 = [&](int j) {
@@ -328,8 +347,11 @@ k_heads_tc(const __grid_constant__ CUtensorMap act_map, const __nv_bfloat16* __r
             const int k = 2 * j + w, slot = j & 1;
             const int b = ((int)blockIdx.x + k * (int)gridDim.x) * 2 + bi;
             const bool active = b < n;
+            // rotate the prefetched metadata HERE, a whole tile after the loads were issued (rotating at the end of the previous
+            // stage 2 made the register moves wait for loads issued a few thousand clocks earlier)
+            if (j > 0) { eo_cur = eo_nxt; L_cur = L_nxt; mv_cur = mv_nxt; eo_nxt = eo_n2; L_nxt = L_n2; }
             const unsigned long long eo = eo_cur; const int L = L_cur; const uint32_t mv0 = mv_cur;
-            unsigned long long eo_n2; int L_n2; uint32_t mv_nxt = 0;
+            mv_nxt = 0;
             if (tid128 < L_nxt) mv_nxt = sc.edge_mv[eo_nxt + tid128];   // consumed by the next tile of this group
             meta(j + 2, eo_n2, L_n2);
             HTC_T(5);
@@ -386,8 +408,6 @@ k_heads_tc(const __grid_constant__ CUtensorMap act_map, const __nv_bfloat16* __r
                 }
             }
             HTC_T(11);
-            eo_cur = eo_nxt; L_cur = L_nxt; mv_cur = mv_nxt;
-            eo_nxt = eo_n2; L_nxt = L_n2;
             if (policy_out && active) {
                 float* po = policy_out + (size_t)b * 4096 + cg * 32 * 64 + sq;
 #pragma unroll
@@ -399,8 +419,6 @@ k_heads_tc(const __grid_constant__ CUtensorMap act_map, const __nv_bfloat16* __r
         for (int g0 = 0; g0 < my_tiles; g0 += kGroupTiles) {
             const int jb = g0 >> 1, je = min(nw, jb + kGroupTiles / 2);
             if (jb < je) epi1(jb);
-            // the first move word: its address needs edge_off / n_edges, requested at kernel entry and here by now
-            if (g0 == 0 && tid128 < L_cur) mv_cur = sc.edge_mv[eo_cur + tid128];
             for (int j = jb; j < je; j++) {
                 if (j + 1 < je) epi1(j + 1);
                 epi2(j);
