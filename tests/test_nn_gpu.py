@@ -122,3 +122,55 @@ def test_launch_modes_give_identical_bits():
         assert out.returncode == 0, out.stderr[-2000:]
         digests.append([l for l in out.stdout.splitlines() if l.startswith("DIGEST")][0])
     assert len(set(digests)) == 1, digests
+
+
+def test_heads_beyond_one_value_batch_per_cta(weights, positions):
+    """k_heads_tc batches the value head per 16 tiles (32 boards) of a CTA and stages the fc1 weights into the drained activation
+    ring only when a CTA has ONE such batch (<= 4736 boards on 148 SMs).  4801 boards (odd: the last tile holds one board) take the
+    other path: several batches per CTA, weights from global memory.  Rows must equal the same boards evaluated alone."""
+    reps = (4801 + len(positions) - 1) // len(positions)
+    big = np.concatenate([positions] * reps)[:4801]
+    with az.Engine(max_games=4801, precision=0) as e:
+        e.load_weights(weights)
+        pol, val = e.forward(big)
+        assert np.allclose(pol.sum(1), 1.0, atol=1e-3)
+        for lo in (0, 200, 4600):
+            idx = np.arange(lo, min(lo + 200, 4801))
+            p1, v1 = e.forward(big[idx])
+            assert np.array_equal(pol[idx], p1) and np.array_equal(val[idx], v1), lo
+        p_last, v_last = e.forward(big[4800])
+        assert np.array_equal(pol[4800], p_last[0]) and val[4800] == v_last[0]
+
+
+_HEADS_SCRIPT = """
+import sys
+import numpy as np
+sys.path.insert(0, {tests!r})
+import _pkg  # noqa: F401
+import alphazero_chess_b200 as az
+from helpers import random_playouts
+p, _ = random_playouts(300, seed=8, max_plies=100)
+with az.Engine(max_games=300, precision=0) as e:
+    e.load_weights(az.random_weights(seed=3, randomize_bn=True))
+    pol, val = e.forward(p)
+np.save({out!r}, np.concatenate([pol.ravel(), val.ravel()]))
+"""
+
+
+def test_both_head_kernels_agree(tmp_path):
+    """AZ_HEADS_TC=1 (tcgen05 heads, default) and AZ_HEADS_TC=0 (warp-level mma.sync heads) accumulate in different orders, so
+    their outputs may differ in the last bits -- but by far less than the 1e-2 the bf16 path is allowed against fp32."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    outs = []
+    for mode in ("1", "0"):
+        out = str(tmp_path / f"heads{mode}.npy")
+        r = subprocess.run([sys.executable, "-c", _HEADS_SCRIPT.format(tests=here, out=out)], env=dict(os.environ, AZ_HEADS_TC=mode),
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(np.load(out))
+    d = np.abs(outs[0] - outs[1]).max()
+    print(f"\ntcgen05 heads vs mma.sync heads: max |d| = {d:.2e}")
+    assert d <= 2e-4
