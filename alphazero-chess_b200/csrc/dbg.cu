@@ -6,12 +6,12 @@
 extern "C" int az_dbg_conv3x3_tc(const void* in_bf16, int cin, const void* w_bf16, const float* bias, const void* residual,
                                  void* out_bf16, int n_boards, int relu, int iters, float* ms_out) {
     CUtensorMap in_map, w_map;
-    int r = azb::tc_make_act_map(&in_map, in_bf16, cin, n_boards);
+    const char* dbg_env = getenv("AZ_DBG_CONV");
+    const int dbg = dbg_env ? atoi(dbg_env) : 0;
+    int r = azb::tc_make_act_map(&in_map, in_bf16, cin, n_boards, (dbg & 64) && cin == 128);
     if (r) return r;
     r = azb::tc_make_weight_map(&w_map, w_bf16, cin);
     if (r) return r;
-    const char* dbg_env = getenv("AZ_DBG_CONV");
-    const int dbg = dbg_env ? atoi(dbg_env) : 0;
     const char* grid_env = getenv("AZ_DBG_GRID");
     const int grid = grid_env ? atoi(grid_env) : 148;
     cudaEvent_t e0, e1;

@@ -81,12 +81,14 @@ int net_create(az_engine* e) {
     for (int l = 0; l < 20; l++)
         if (tc_make_weight_map(&w->map_w_tower[l], w->h_w_tower + (size_t)l * 9 * 128 * 128, 128))
             return set_err(e, AZ_ERR_CUDA, "cuTensorMapEncodeTiled(w_tower)");
-    CUtensorMap host_maps[25];
+    CUtensorMap host_maps[28];
     for (int i = 0; i < 3; i++) host_maps[i] = w->map_a[i];
     for (int l = 0; l < 20; l++) host_maps[3 + l] = w->map_w_tower[l];
     host_maps[23] = w->map_a_in;
     host_maps[24] = w->map_w_in;
-    if (dmalloc(e, &w->d_maps, 25)) return AZ_ERR_OUT_OF_MEMORY;
+    for (int i = 0; i < 3; i++)   // 16-file boxes for the wide tower (AZ_TOWER_WIDE)
+        if (tc_make_act_map(&host_maps[25 + i], w->a_buf[i], 128, e->max_batch, 1)) return set_err(e, AZ_ERR_CUDA, "cuTensorMapEncodeTiled(act, wide)");
+    if (dmalloc(e, &w->d_maps, 28)) return AZ_ERR_OUT_OF_MEMORY;
     AZ_CUDA(e, cudaMemcpy(w->d_maps, host_maps, sizeof host_maps, cudaMemcpyHostToDevice));
     return 0;
 }
@@ -354,7 +356,8 @@ int net_forward_bf16(az_engine* e, const int* n_dev, int n_static, float* policy
     // an extra first layer of that launch (measured: 48 us inside vs 60 us alone per 4096 boards, epilogue-bound either
     // way, so the wave gains 0.2 % -- kept as an option), 0 = 21 launches
     // the input convolution can only run inside the tower launch (mode 2) with the 64-channel plane layout
-    const int fused = (e->knobs.tower_fused >= 2 && w->in_ch != 64) ? 1 : e->knobs.tower_fused;
+    const int wide = e->knobs.tower_wide;
+    const int fused = (e->knobs.tower_fused >= 2 && (w->in_ch != 64 || wide)) ? 1 : e->knobs.tower_fused;
     int r = 0;
     if (fused < 2) {
         e->n_launches += 1;
@@ -386,8 +389,8 @@ int net_forward_bf16(az_engine* e, const int* n_dev, int n_static, float* policy
         for (int lo = 0; lo < cap_tiles; lo += inkernel ? cap_tiles : per) {
             e->n_launches += 1;
             if (sample) e->prof_launches += 1;
-            r = inkernel ? tc_tower_launch(e->stream, w->d_maps, w->f_b_tower, act, n_dev, n_static, 20, fused >= 2, tgrid, 0, 0x7FFFFFFF, per, rel)
-                         : tc_tower_launch(e->stream, w->d_maps, w->f_b_tower, act, n_dev, n_static, 20, fused >= 2, tgrid, lo, lo + per, 0, rel);
+            r = inkernel ? tc_tower_launch(e->stream, w->d_maps, w->f_b_tower, act, n_dev, n_static, 20, fused >= 2, tgrid, 0, 0x7FFFFFFF, per, rel, wide)
+                         : tc_tower_launch(e->stream, w->d_maps, w->f_b_tower, act, n_dev, n_static, 20, fused >= 2, tgrid, lo, lo + per, 0, rel, wide);
             if (r) return set_err(e, AZ_ERR_CUDA, "tower launch failed");
         }
         x = 0;  // the fused tower works in place: block input and block output share a_buf[0], a_buf[1] holds conv1's output

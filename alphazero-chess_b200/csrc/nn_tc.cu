@@ -28,11 +28,14 @@ constexpr int kWTileBytes = 64 * 128;    // 64 output channels x 64 input channe
 
 // KROW = bytes per operand row in shared memory = input channels per K block x 2: 128 (64 channels, 128-byte swizzle) for the
 // tower and the 64-channel plane layout, 64 (32 channels, 64-byte swizzle) for the 32-channel plane layout of the input convolution
-template <int HALVES, int KROW = 128>
+// WIDE = 1 (experiment, AZ_DBG_CONV bit 6): ONE box per channel half serves all three horizontal taps.  The box spans files -1..14
+// (16-row pitch per (rank, board), files outside the board zero-filled by TMA), so the tap dx is a window that starts dx rows
+// (128 bytes) into every 8-row group: 8-row groups 2048 bytes apart, start address + dx * 128.
+template <int HALVES, int KROW = 128, int WIDE = 0>
 struct ConvSmem {
-    static constexpr int kStages = HALVES == 2 ? 4 : 6;
+    static constexpr int kStages = WIDE ? 2 : HALVES == 2 ? 4 : 6;
     static constexpr int kWTiles = HALVES * 9;
-    static constexpr int kStageB = 160 * KROW;
+    static constexpr int kStageB = (WIDE ? 320 : 160) * KROW;
     static constexpr int kWTileB = 64 * KROW;
     static constexpr int kWBytes = kWTiles * kWTileB;
     static constexpr int kABytes = kStages * kStageB;
@@ -60,12 +63,12 @@ constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreads2 = 64 + kEpiThreads;   // warp 0 TMA, warp 1 MMA/TMEM, then the epilogue warps
 static_assert(kEpiWarps == 8 || kEpiWarps == 16, "epilogue warps: 8 or 16");
 
-template <int HALVES, int KROW>
+template <int HALVES, int KROW, int WIDE = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap w_map,
                    const float* __restrict__ bias, const __nv_bfloat16* __restrict__ residual,
                    __nv_bfloat16* __restrict__ out, const int* __restrict__ n_boards_ptr, int n_boards_static, int relu, int dbg) {
-    using S = ConvSmem<HALVES, KROW>;
+    using S = ConvSmem<HALVES, KROW, WIDE>;
     constexpr int kStageBytes = S::kStageB, kWTileBytes = S::kWTileB;   // shadow the 128-byte-row constants of the tower
     constexpr int KSTEPS = KROW / 32;                                   // K = 16 elements = 32 bytes per MMA
     constexpr int NS = S::kStages;
@@ -108,6 +111,27 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
         // ---------------------------------------------------------------- TMA producer (both CTAs, warp-uniform)
         int stage = 0; uint32_t phase = 0; bool first = true;
         for (int t = first_tile; t < n_tiles; t += tile_step) {
+            if constexpr (WIDE) {
+                for (int half = 0; half < HALVES; half++) {
+                    if (first && elect_one()) {
+                        for (int dxi = 0; dxi < 3; dxi++)
+                            for (int dyi = 0; dyi < 3; dyi++) {
+                                const int wt = (half * 3 + dxi) * 3 + dyi, tap = dyi * 3 + dxi;
+                                if (rank == 0) mbar_arrive_expect_tx(&wfull_bar[wt], 2 * kWTileBytes);
+                                tma2_load_2d(w_sm + wt * kWTileBytes, &w_map, &wfull_bar[wt], half * 64, tap * 128 + (int)rank * 64);
+                            }
+                    }
+                    mbar_wait(&empty_bar[stage], phase ^ 1, 11);
+                    if (elect_one()) {
+                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);
+                        tma2_load_4d(a_sm + stage * kStageBytes, &in_map, &full_bar[stage], half * 64, -1, t * 4 + (int)rank * 2, -1);
+                    }
+                    __syncwarp();
+                    if (++stage == NS) { stage = 0; phase ^= 1; }
+                }
+                first = false;
+                continue;
+            }
             for (int half = 0; half < HALVES; half++)
                 for (int dxi = 0; dxi < 3; dxi++) {
                     if (first && elect_one()) {
@@ -142,6 +166,40 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
                 mbar_wait(&tempty_bar[acc], accphase ^ 1, 12);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * 128;
+                if constexpr (WIDE) {
+                    for (int half = 0; half < HALVES; half++) {
+                        mbar_wait(&full_bar[stage], phase, 13);
+                        if (lt == 0)
+                            for (int wt = 0; wt < 9; wt++) mbar_wait(&wfull_bar[half * 9 + wt], 0, 14);
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint32_t a_lo = (smem_u32(a_sm + stage * kStageBytes) & 0x3FFFF) >> 4;
+                            // 8-row groups (one rank of one board) are 16 rows = 2048 bytes apart
+                            const uint64_t abase = ((uint64_t)1 << 16) | ((uint64_t)(2048 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+#pragma unroll
+                            for (int dxi = 0; dxi < 3; dxi++) {
+                                const uint32_t b_lo = w_lo + (uint32_t)((half * 3 + dxi) * 3) * (kWTileBytes >> 4);
+                                // dbg bit 7: tell the hardware that the window starts dx rows into the 1024-byte swizzle pattern
+                                const uint64_t aoff = abase | ((dbg & 128) ? ((uint64_t)dxi << 49) : 0);
+#pragma unroll
+                                for (int dyi = 0; dyi < 3; dyi++) {
+#pragma unroll
+                                    for (int k = 0; k < 4; k++) {
+                                        const uint64_t ad = aoff | (uint64_t)(a_lo + dyi * (4096 >> 4) + dxi * (128 >> 4) + k * 2);
+                                        const uint64_t bd = dbase | (uint64_t)(b_lo + dyi * (kWTileBytes >> 4) + k * 2);
+                                        umma2_bf16(d_tmem, ad, bd, idesc, (half | dxi | dyi | k) != 0 ? 1u : 0u);
+                                    }
+                                }
+                            }
+                            umma2_commit_mc(&empty_bar[stage]);
+                        }
+                        __syncwarp();
+                        if (++stage == NS) { stage = 0; phase ^= 1; }
+                    }
+                    if (elect_one()) umma2_commit_mc(&tfull_bar[acc]);
+                    __syncwarp();
+                    continue;
+                }
                 for (int half = 0; half < HALVES; half++)
                     for (int dxi = 0; dxi < 3; dxi++) {
                         mbar_wait(&full_bar[stage], phase, 13);
@@ -264,9 +322,13 @@ struct TowerParams {
 };
 
 
+// WIDE = 1 (AZ_TOWER_WIDE): one TMA box per channel half serves the three horizontal taps (see ConvSmem): a third of the L2 -> shared
+// memory traffic and of the TMA instructions; the activation maps are then maps[25..27] (16-file boxes) and there is no stem.
+template <int WIDE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
 conv_tower_kernel(const TowerParams prm) {
-    using S = ConvSmem<2>;
+    using S = ConvSmem<2, 128, WIDE>;
+    constexpr int kStageBytes = S::kStageB;
     constexpr int NS = S::kStages;
     constexpr int kGroupBytes = 3 * kWTileBytes;  // the three dy taps of one (channel half, dx)
     extern __shared__ uint8_t smem_raw[];
@@ -327,7 +389,7 @@ conv_tower_kernel(const TowerParams prm) {
             const int layer = L - stem;
             const int blk_second = layer >= 0 ? (layer & 1) : 0;
             const int in_buf = blk_second ? 1 : 0;   // block input in act[0], conv1 output in act[1], conv2 back into act[0]
-            const CUtensorMap* in_map = layer >= 0 ? &prm.maps[in_buf] : &prm.maps[23];
+            const CUtensorMap* in_map = layer >= 0 ? &prm.maps[(WIDE ? 25 : 0) + in_buf] : &prm.maps[23];
             const CUtensorMap* w_map = layer >= 0 ? &prm.maps[3 + layer] : &prm.maps[24];
             const int halves = layer >= 0 ? 2 : 1;
             for (int i = 0; i < T; i++) {
@@ -356,10 +418,11 @@ conv_tower_kernel(const TowerParams prm) {
                             }
                             __syncwarp();
                         }
+                        if (WIDE && dxi != 2) continue;   // one box per channel half, requested after its three weight groups
                         mbar_wait(&empty_bar[stage], phase ^ 1, 22);
                         if (elect_one()) {
                             if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);
-                            tma2_load_4d(a_sm + stage * kStageBytes, in_map, &full_bar[stage], half * 64, dxi - 1, t * 4 + (int)rank * 2, -1);
+                            tma2_load_4d(a_sm + stage * kStageBytes, in_map, &full_bar[stage], half * 64, WIDE ? -1 : dxi - 1, t * 4 + (int)rank * 2, -1);
                         }
                         __syncwarp();
                         if (++stage == NS) { stage = 0; phase ^= 1; }
@@ -391,26 +454,30 @@ conv_tower_kernel(const TowerParams prm) {
                     for (int half = 0; half < halves; half++)
                         for (int dxi = 0; dxi < 3; dxi++) {
                             const int grp = half * 3 + dxi;
-                            mbar_wait(&full_bar[stage], phase, 24);
+                            if (!WIDE || dxi == 0) mbar_wait(&full_bar[stage], phase, 24);
                             if (i == 0) mbar_wait(&wfull_bar[grp], (uint32_t)((half == 0 ? u0 : u1) & 1), 25);
                             tc_fence_after();
                             if (elect_one()) {
                                 const uint32_t a_lo = (smem_u32(a_sm + stage * kStageBytes) & 0x3FFFF) >> 4;
                                 const uint32_t b_lo = w_lo + (uint32_t)(grp * 3) * (kWTileBytes >> 4);
+                                // WIDE: 8-row groups (one rank of one board) are 16 rows = 2048 bytes apart, a rank is 4096 bytes, and the
+                                // horizontal tap is a window starting dxi rows into every group (the swizzle follows the address bits)
+                                const uint64_t abase = WIDE ? (((uint64_t)1 << 16) | ((uint64_t)(2048 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61)) : dbase;
+                                const uint32_t a_dy = WIDE ? (4096 >> 4) : (2048 >> 4), a_dx = WIDE ? (uint32_t)dxi * (128 >> 4) : 0u;
 #pragma unroll
                                 for (int dyi = 0; dyi < 3; dyi++) {
 #pragma unroll
                                     for (int k = 0; k < 4; k++) {
-                                        const uint64_t ad = dbase | (uint64_t)(a_lo + dyi * (2048 >> 4) + k * 2);
+                                        const uint64_t ad = abase | (uint64_t)(a_lo + dyi * a_dy + a_dx + k * 2);
                                         const uint64_t bd = dbase | (uint64_t)(b_lo + dyi * (kWTileBytes >> 4) + k * 2);
                                         umma2_bf16(d_tmem, ad, bd, idesc, (half | dxi | dyi | k) != 0 ? 1u : 0u);
                                     }
                                 }
-                                umma2_commit_mc(&empty_bar[stage]);
+                                if (!WIDE || dxi == 2) umma2_commit_mc(&empty_bar[stage]);
                                 if (i == T - 1) umma2_commit_mc(&wempty_bar[grp]);  // weights of this group are free for the next layer
                             }
                             __syncwarp();
-                            if (++stage == NS) { stage = 0; phase ^= 1; }
+                            if (!WIDE || dxi == 2) { if (++stage == NS) { stage = 0; phase ^= 1; } }
                         }
                     if (elect_one()) umma2_commit_mc(&tfull_bar[acc]);
                     __syncwarp();
@@ -521,11 +588,14 @@ conv_tower_kernel(const TowerParams prm) {
 }
 
 int tc_tower_launch(cudaStream_t stream, const CUtensorMap* maps_dev, const float* bias, void* const* act, const int* n_boards_dev,
-                    int n_boards_static, int n_layers, int stem, int grid, int tile_lo, int tile_hi, int range_tiles, int release_arrive) {
+                    int n_boards_static, int n_layers, int stem, int grid, int tile_lo, int tile_hi, int range_tiles, int release_arrive,
+                    int wide) {
     static PerDeviceOnce once;
     if (once.first() &&
-        cudaFuncSetAttribute(conv_tower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<2>::kTotal) != cudaSuccess)
+        (cudaFuncSetAttribute(conv_tower_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<2>::kTotal) != cudaSuccess ||
+         cudaFuncSetAttribute(conv_tower_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<2, 128, 1>::kTotal) != cudaSuccess))
         return -2;
+    if (wide && stem) return -5;   // the in-kernel input convolution exists for the narrow boxes only
     if (grid <= 0) grid = 148;
     grid &= ~1;
     TowerParams p;
@@ -534,7 +604,8 @@ int tc_tower_launch(cudaStream_t stream, const CUtensorMap* maps_dev, const floa
     p.n_boards_ptr = n_boards_dev; p.n_boards_static = n_boards_static; p.n_layers = n_layers; p.stem = stem ? 1 : 0;
     p.tile_lo = tile_lo; p.tile_hi = tile_hi; p.range_tiles = range_tiles > 0 ? range_tiles : (1 << 30);
     p.release_arrive = release_arrive;
-    conv_tower_kernel<<<grid, kThreads2, ConvSmem<2>::kTotal, stream>>>(p);
+    if (wide) conv_tower_kernel<1><<<grid, kThreads2, ConvSmem<2, 128, 1>::kTotal, stream>>>(p);
+    else conv_tower_kernel<0><<<grid, kThreads2, ConvSmem<2>::kTotal, stream>>>(p);
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
 
@@ -554,14 +625,15 @@ static PFN_encodeTiled get_encode() {
     return fn;
 }
 
-int tc_make_act_map(CUtensorMap* map, const void* base, int channels, int max_boards) {
+int tc_make_act_map(CUtensorMap* map, const void* base, int channels, int max_boards, int wide) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) return -1;
     // dims fastest-first: channel, file, board, rank  (SMEM box order becomes [rank][board][file][channel])
     cuuint64_t dims[4] = {(cuuint64_t)channels, 8, (cuuint64_t)max_boards, 8};
     cuuint64_t strides[3] = {(cuuint64_t)channels * 2, (cuuint64_t)channels * 2 * 64, (cuuint64_t)channels * 2 * 8};
     // 64 channels (128-byte rows, 128-byte swizzle) per box, or the whole row of the 32-channel plane layout (64-byte swizzle)
-    cuuint32_t box[4] = {(cuuint32_t)(channels == 32 ? 32 : 64), 8, 2, 10};
+    // wide: files -1..14 (the files beyond the board are zero-filled), so that every (rank, board) group has a 16-row pitch
+    cuuint32_t box[4] = {(cuuint32_t)(channels == 32 ? 32 : 64), (cuuint32_t)(wide ? 16 : 8), 2, 10};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, channels == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -603,7 +675,8 @@ int tc_conv3x3_launch(cudaStream_t stream, const CUtensorMap* in_map, const CUte
         cudaError_t e1 = cudaFuncSetAttribute(conv3x3_tc2_kernel<1, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<1>::kTotal);
         cudaError_t e2 = cudaFuncSetAttribute(conv3x3_tc2_kernel<2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<2>::kTotal);
         cudaError_t e3 = cudaFuncSetAttribute(conv3x3_tc2_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<1, 64>::kTotal);
-        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) return -2;
+        cudaError_t e4 = cudaFuncSetAttribute(conv3x3_tc2_kernel<2, 128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<2, 128, 1>::kTotal);
+        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) return -2;
     }
     if (grid <= 0) grid = 148;
     grid &= ~1;  // CTA pairs
@@ -613,6 +686,9 @@ int tc_conv3x3_launch(cudaStream_t stream, const CUtensorMap* in_map, const CUte
     else if (cin == 64)
         conv3x3_tc2_kernel<1, 128><<<grid, kThreads2, ConvSmem<1>::kTotal, stream>>>(*in_map, *w_map, bias, (const __nv_bfloat16*)residual,
                                                                                     (__nv_bfloat16*)out, n_boards_dev, n_boards_static, relu, dbg);
+    else if (cin == 128 && (dbg & 64))   // the wide-box experiment: in_map must have been made with wide = 1
+        conv3x3_tc2_kernel<2, 128, 1><<<grid, kThreads2, ConvSmem<2, 128, 1>::kTotal, stream>>>(*in_map, *w_map, bias, (const __nv_bfloat16*)residual,
+                                                                                              (__nv_bfloat16*)out, n_boards_dev, n_boards_static, relu, dbg);
     else if (cin == 128)
         conv3x3_tc2_kernel<2, 128><<<grid, kThreads2, ConvSmem<2>::kTotal, stream>>>(*in_map, *w_map, bias, (const __nv_bfloat16*)residual,
                                                                                     (__nv_bfloat16*)out, n_boards_dev, n_boards_static, relu, dbg);
