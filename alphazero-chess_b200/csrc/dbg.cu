@@ -8,7 +8,7 @@ extern "C" int az_dbg_conv3x3_tc(const void* in_bf16, int cin, const void* w_bf1
     CUtensorMap in_map, w_map;
     const char* dbg_env = getenv("AZ_DBG_CONV");
     const int dbg = dbg_env ? atoi(dbg_env) : 0;
-    int r = azb::tc_make_act_map(&in_map, in_bf16, cin, n_boards, (dbg & 64) && cin == 128);
+    int r = azb::tc_make_act_map(&in_map, in_bf16, cin, n_boards, cin == 64 ? 0 : (dbg & 256) ? 2 : (dbg & 64) && cin == 128 ? 1 : 0);
     if (r) return r;
     r = azb::tc_make_weight_map(&w_map, w_bf16, cin);
     if (r) return r;

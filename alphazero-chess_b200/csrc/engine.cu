@@ -119,7 +119,7 @@ int az_engine_create(const az_config* cfg, az_engine** out) {
         e->knobs.tc_release_arrive = env_int("AZ_TC_RELEASE_ARRIVE", 0);
         e->knobs.adv_minb = env_int("AZ_ADV_MINB", 7);
         e->knobs.tower_grid = std::max(0, env_int("AZ_TOWER_GRID", 0));
-        e->knobs.tower_wide = env_int("AZ_TOWER_WIDE", 1) ? 1 : 0;
+        e->knobs.tower_wide = std::min(2, std::max(0, env_int("AZ_TOWER_WIDE", 2)));
         e->knobs.heads_tc = env_int("AZ_HEADS_TC", 1) ? 1 : 0;
         e->knobs.input_k32 = env_int("AZ_INPUT_K32", 1) ? 1 : 0;
     }

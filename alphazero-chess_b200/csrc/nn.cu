@@ -81,14 +81,16 @@ int net_create(az_engine* e) {
     for (int l = 0; l < 20; l++)
         if (tc_make_weight_map(&w->map_w_tower[l], w->h_w_tower + (size_t)l * 9 * 128 * 128, 128))
             return set_err(e, AZ_ERR_CUDA, "cuTensorMapEncodeTiled(w_tower)");
-    CUtensorMap host_maps[28];
+    CUtensorMap host_maps[31];
     for (int i = 0; i < 3; i++) host_maps[i] = w->map_a[i];
     for (int l = 0; l < 20; l++) host_maps[3 + l] = w->map_w_tower[l];
     host_maps[23] = w->map_a_in;
     host_maps[24] = w->map_w_in;
     for (int i = 0; i < 3; i++)   // 16-file boxes for the wide tower (AZ_TOWER_WIDE)
         if (tc_make_act_map(&host_maps[25 + i], w->a_buf[i], 128, e->max_batch, 1)) return set_err(e, AZ_ERR_CUDA, "cuTensorMapEncodeTiled(act, wide)");
-    if (dmalloc(e, &w->d_maps, 28)) return AZ_ERR_OUT_OF_MEMORY;
+    for (int i = 0; i < 3; i++)   // 10-file boxes (AZ_TOWER_WIDE=2)
+        if (tc_make_act_map(&host_maps[28 + i], w->a_buf[i], 128, e->max_batch, 2)) return set_err(e, AZ_ERR_CUDA, "cuTensorMapEncodeTiled(act, wide 2)");
+    if (dmalloc(e, &w->d_maps, 31)) return AZ_ERR_OUT_OF_MEMORY;
     AZ_CUDA(e, cudaMemcpy(w->d_maps, host_maps, sizeof host_maps, cudaMemcpyHostToDevice));
     return 0;
 }

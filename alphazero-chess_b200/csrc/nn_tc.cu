@@ -33,9 +33,10 @@ constexpr int kWTileBytes = 64 * 128;    // 64 output channels x 64 input channe
 // (128 bytes) into every 8-row group: 8-row groups 2048 bytes apart, start address + dx * 128.
 template <int HALVES, int KROW = 128, int WIDE = 0>
 struct ConvSmem {
-    static constexpr int kStages = WIDE ? 2 : HALVES == 2 ? 4 : 6;
+    static constexpr int kPitch = WIDE == 1 ? 16 : WIDE == 2 ? 10 : 8;   // rows (files) per (rank, board) group in a stage
+    static constexpr int kStages = HALVES == 1 ? 6 : WIDE == 1 ? 2 : WIDE == 2 ? 3 : 4;
     static constexpr int kWTiles = HALVES * 9;
-    static constexpr int kStageB = (WIDE ? 320 : 160) * KROW;
+    static constexpr int kStageB = 20 * kPitch * KROW;
     static constexpr int kWTileB = 64 * KROW;
     static constexpr int kWBytes = kWTiles * kWTileB;
     static constexpr int kABytes = kStages * kStageB;
@@ -174,8 +175,8 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
                         tc_fence_after();
                         if (elect_one()) {
                             const uint32_t a_lo = (smem_u32(a_sm + stage * kStageBytes) & 0x3FFFF) >> 4;
-                            // 8-row groups (one rank of one board) are 16 rows = 2048 bytes apart
-                            const uint64_t abase = ((uint64_t)1 << 16) | ((uint64_t)(2048 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+                            // 8-row groups (one rank of one board) are kPitch rows apart
+                            const uint64_t abase = ((uint64_t)1 << 16) | ((uint64_t)((S::kPitch * KROW) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)(KROW == 128 ? 2 : 4) << 61);
 #pragma unroll
                             for (int dxi = 0; dxi < 3; dxi++) {
                                 const uint32_t b_lo = w_lo + (uint32_t)((half * 3 + dxi) * 3) * (kWTileBytes >> 4);
@@ -184,8 +185,8 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
 #pragma unroll
                                 for (int dyi = 0; dyi < 3; dyi++) {
 #pragma unroll
-                                    for (int k = 0; k < 4; k++) {
-                                        const uint64_t ad = aoff | (uint64_t)(a_lo + dyi * (4096 >> 4) + dxi * (128 >> 4) + k * 2);
+                                    for (int k = 0; k < KSTEPS; k++) {
+                                        const uint64_t ad = aoff | (uint64_t)(a_lo + dyi * ((2 * S::kPitch * KROW) >> 4) + dxi * (KROW >> 4) + k * 2);
                                         const uint64_t bd = dbase | (uint64_t)(b_lo + dyi * (kWTileBytes >> 4) + k * 2);
                                         umma2_bf16(d_tmem, ad, bd, idesc, (half | dxi | dyi | k) != 0 ? 1u : 0u);
                                     }
@@ -389,7 +390,7 @@ conv_tower_kernel(const TowerParams prm) {
             const int layer = L - stem;
             const int blk_second = layer >= 0 ? (layer & 1) : 0;
             const int in_buf = blk_second ? 1 : 0;   // block input in act[0], conv1 output in act[1], conv2 back into act[0]
-            const CUtensorMap* in_map = layer >= 0 ? &prm.maps[(WIDE ? 25 : 0) + in_buf] : &prm.maps[23];
+            const CUtensorMap* in_map = layer >= 0 ? &prm.maps[(WIDE == 2 ? 28 : WIDE ? 25 : 0) + in_buf] : &prm.maps[23];
             const CUtensorMap* w_map = layer >= 0 ? &prm.maps[3 + layer] : &prm.maps[24];
             const int halves = layer >= 0 ? 2 : 1;
             for (int i = 0; i < T; i++) {
@@ -462,8 +463,8 @@ conv_tower_kernel(const TowerParams prm) {
                                 const uint32_t b_lo = w_lo + (uint32_t)(grp * 3) * (kWTileBytes >> 4);
                                 // WIDE: 8-row groups (one rank of one board) are 16 rows = 2048 bytes apart, a rank is 4096 bytes, and the
                                 // horizontal tap is a window starting dxi rows into every group (the swizzle follows the address bits)
-                                const uint64_t abase = WIDE ? (((uint64_t)1 << 16) | ((uint64_t)(2048 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61)) : dbase;
-                                const uint32_t a_dy = WIDE ? (4096 >> 4) : (2048 >> 4), a_dx = WIDE ? (uint32_t)dxi * (128 >> 4) : 0u;
+                                const uint64_t abase = WIDE ? (((uint64_t)1 << 16) | ((uint64_t)((S::kPitch * 128) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61)) : dbase;
+                                const uint32_t a_dy = (2 * S::kPitch * 128) >> 4, a_dx = WIDE ? (uint32_t)dxi * (128 >> 4) : 0u;
 #pragma unroll
                                 for (int dyi = 0; dyi < 3; dyi++) {
 #pragma unroll
@@ -593,7 +594,8 @@ int tc_tower_launch(cudaStream_t stream, const CUtensorMap* maps_dev, const floa
     static PerDeviceOnce once;
     if (once.first() &&
         (cudaFuncSetAttribute(conv_tower_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<2>::kTotal) != cudaSuccess ||
-         cudaFuncSetAttribute(conv_tower_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<2, 128, 1>::kTotal) != cudaSuccess))
+         cudaFuncSetAttribute(conv_tower_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<2, 128, 1>::kTotal) != cudaSuccess ||
+         cudaFuncSetAttribute(conv_tower_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<2, 128, 2>::kTotal) != cudaSuccess))
         return -2;
     if (wide && stem) return -5;   // the in-kernel input convolution exists for the narrow boxes only
     if (grid <= 0) grid = 148;
@@ -604,7 +606,8 @@ int tc_tower_launch(cudaStream_t stream, const CUtensorMap* maps_dev, const floa
     p.n_boards_ptr = n_boards_dev; p.n_boards_static = n_boards_static; p.n_layers = n_layers; p.stem = stem ? 1 : 0;
     p.tile_lo = tile_lo; p.tile_hi = tile_hi; p.range_tiles = range_tiles > 0 ? range_tiles : (1 << 30);
     p.release_arrive = release_arrive;
-    if (wide) conv_tower_kernel<1><<<grid, kThreads2, ConvSmem<2, 128, 1>::kTotal, stream>>>(p);
+    if (wide == 2) conv_tower_kernel<2><<<grid, kThreads2, ConvSmem<2, 128, 2>::kTotal, stream>>>(p);
+    else if (wide) conv_tower_kernel<1><<<grid, kThreads2, ConvSmem<2, 128, 1>::kTotal, stream>>>(p);
     else conv_tower_kernel<0><<<grid, kThreads2, ConvSmem<2>::kTotal, stream>>>(p);
     return cudaGetLastError() == cudaSuccess ? 0 : -4;
 }
@@ -633,7 +636,7 @@ int tc_make_act_map(CUtensorMap* map, const void* base, int channels, int max_bo
     cuuint64_t strides[3] = {(cuuint64_t)channels * 2, (cuuint64_t)channels * 2 * 64, (cuuint64_t)channels * 2 * 8};
     // 64 channels (128-byte rows, 128-byte swizzle) per box, or the whole row of the 32-channel plane layout (64-byte swizzle)
     // wide: files -1..14 (the files beyond the board are zero-filled), so that every (rank, board) group has a 16-row pitch
-    cuuint32_t box[4] = {(cuuint32_t)(channels == 32 ? 32 : 64), (cuuint32_t)(wide ? 16 : 8), 2, 10};
+    cuuint32_t box[4] = {(cuuint32_t)(channels == 32 ? 32 : 64), (cuuint32_t)(wide == 1 ? 16 : wide == 2 ? 10 : 8), 2, 10};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, channels == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -676,17 +679,25 @@ int tc_conv3x3_launch(cudaStream_t stream, const CUtensorMap* in_map, const CUte
         cudaError_t e2 = cudaFuncSetAttribute(conv3x3_tc2_kernel<2, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<2>::kTotal);
         cudaError_t e3 = cudaFuncSetAttribute(conv3x3_tc2_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<1, 64>::kTotal);
         cudaError_t e4 = cudaFuncSetAttribute(conv3x3_tc2_kernel<2, 128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<2, 128, 1>::kTotal);
-        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) return -2;
+        cudaError_t e5 = cudaFuncSetAttribute(conv3x3_tc2_kernel<2, 128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<2, 128, 2>::kTotal);
+        cudaError_t e6 = cudaFuncSetAttribute(conv3x3_tc2_kernel<1, 64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<1, 64, 2>::kTotal);
+        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess || e5 != cudaSuccess || e6 != cudaSuccess) return -2;
     }
     if (grid <= 0) grid = 148;
     grid &= ~1;  // CTA pairs
-    if (cin == 32)
+    if (cin == 32 && (dbg & 256))   // 10-file boxes: in_map must have been made with wide = 2
+        conv3x3_tc2_kernel<1, 64, 2><<<grid, kThreads2, ConvSmem<1, 64, 2>::kTotal, stream>>>(*in_map, *w_map, bias, (const __nv_bfloat16*)residual,
+                                                                                            (__nv_bfloat16*)out, n_boards_dev, n_boards_static, relu, dbg);
+    else if (cin == 32)
         conv3x3_tc2_kernel<1, 64><<<grid, kThreads2, ConvSmem<1, 64>::kTotal, stream>>>(*in_map, *w_map, bias, (const __nv_bfloat16*)residual,
                                                                                        (__nv_bfloat16*)out, n_boards_dev, n_boards_static, relu, dbg);
     else if (cin == 64)
         conv3x3_tc2_kernel<1, 128><<<grid, kThreads2, ConvSmem<1>::kTotal, stream>>>(*in_map, *w_map, bias, (const __nv_bfloat16*)residual,
                                                                                     (__nv_bfloat16*)out, n_boards_dev, n_boards_static, relu, dbg);
-    else if (cin == 128 && (dbg & 64))   // the wide-box experiment: in_map must have been made with wide = 1
+    else if (cin == 128 && (dbg & 256))  // 10-file boxes: in_map must have been made with wide = 2
+        conv3x3_tc2_kernel<2, 128, 2><<<grid, kThreads2, ConvSmem<2, 128, 2>::kTotal, stream>>>(*in_map, *w_map, bias, (const __nv_bfloat16*)residual,
+                                                                                              (__nv_bfloat16*)out, n_boards_dev, n_boards_static, relu, dbg);
+    else if (cin == 128 && (dbg & 64))   // 16-file boxes: in_map must have been made with wide = 1
         conv3x3_tc2_kernel<2, 128, 1><<<grid, kThreads2, ConvSmem<2, 128, 1>::kTotal, stream>>>(*in_map, *w_map, bias, (const __nv_bfloat16*)residual,
                                                                                               (__nv_bfloat16*)out, n_boards_dev, n_boards_static, relu, dbg);
     else if (cin == 128)

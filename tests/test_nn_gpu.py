@@ -113,9 +113,9 @@ def test_launch_modes_give_identical_bits():
     digests = []
     # the last two also force three board ranges inside the tower launch (ranges with and without tiles for a CTA pair)
     # and AZ_INPUT_K32=1 (32-channel plane layout: the two K blocks it drops per tap only ever added exact zeros)
-    # and AZ_TOWER_WIDE=1 (one 16-file TMA box per channel half instead of three 8-file boxes: the same MMAs in the same order)
+    # and AZ_TOWER_WIDE=1 / 2 (one 16-file / 10-file TMA box per channel half instead of three 8-file boxes: the same MMAs in the same order)
     for mode, split, k32, wide in (("0", None, "0", "0"), ("1", None, "0", "0"), ("2", None, "0", "0"), ("1", "3", "0", "0"), ("2", "3", "0", "0"),
-                                   ("1", None, "1", "0"), ("0", None, "1", "0"), ("2", "3", "1", "0"), ("1", None, "1", "1"), ("1", "3", "0", "1")):
+                                   ("1", None, "1", "0"), ("0", None, "1", "0"), ("2", "3", "1", "0"), ("1", None, "1", "1"), ("1", "3", "0", "1"), ("1", None, "1", "2"), ("1", "3", "1", "2"), ("0", None, "1", "2")):
         env = dict(os.environ, AZ_TOWER_FUSED=mode, AZ_INPUT_K32=k32, AZ_TOWER_WIDE=wide)
         if split:
             env["AZ_TOWER_SPLIT"] = split

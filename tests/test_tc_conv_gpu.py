@@ -36,7 +36,7 @@ def _run(n_boards, cin, residual, relu, iters=0):
 
 
 @pytest.mark.parametrize("n_boards", [1, 2, 3, 7, 299, 4096])
-@pytest.mark.parametrize("cin", [128, 64])
+@pytest.mark.parametrize("cin", [128, 64, 32])
 def test_conv3x3_matches_torch(n_boards, cin):
     out, ref, _ = _run(n_boards, cin, residual=True, relu=True)
     assert torch.isfinite(out).all()
@@ -52,9 +52,10 @@ def test_conv3x3_no_residual_no_relu():
 
 
 def test_conv3x3_input_layer_speed_report():
-    out, ref, ms = _run(4096, 64, residual=False, relu=True, iters=20)
-    print(f"\nconv3x3 tc (64 padded input channels): {ms * 1e3:.1f} us @4096 boards")
-    assert ms > 0
+    for cin in (64, 32):
+        out, ref, ms = _run(4096, cin, residual=False, relu=True, iters=20)
+        print(f"\nconv3x3 tc ({cin} padded input channels): {ms * 1e3:.1f} us @4096 boards")
+        assert ms > 0
 
 
 def test_conv3x3_speed_report():
