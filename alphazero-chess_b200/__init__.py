@@ -392,6 +392,10 @@ class ReplayBuffer:
         import torch
 
         dev = torch.device("cuda", int(self._e.config.device))
+        # The engine fills the tensors on ITS stream.  torch's caching allocator may hand out a block that kernels still queued on
+        # torch's stream (the previous step's backward / optimizer) are using under another name -- it only orders reuse within one
+        # stream -- so torch's stream is drained first; the engine call returns after synchronising its own stream.
+        torch.cuda.current_stream(dev).synchronize()
         planes = torch.empty((batch_size, NUM_PLANES, 8, 8), dtype=torch.float32, device=dev)
         policy = torch.empty((batch_size, ACTION_SPACE), dtype=torch.float32, device=dev)
         value = torch.empty(batch_size, dtype=torch.float32, device=dev)
