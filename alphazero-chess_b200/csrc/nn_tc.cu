@@ -9,10 +9,15 @@
 // (channel half, dx): the dx shift and the rank halo are resolved by signed box coordinates (out-of-bounds elements are
 // zero-filled = "same" padding), and because the box is laid out rank-major the three dy taps are just three
 // 1024B-aligned row windows of the same SMEM stage.  So 6 boxes (120 KB) feed the 72 MMAs of a tile instead of 18.
+// WIDE (the tower's default, AZ_TOWER_WIDE=2): ONE box {64 ch, 10 files (-1..8), 2 boards, 10 ranks} per channel half serves all
+// nine taps -- the files outside the board are zero-filled like the ranks, the 8-row groups of the A operand are 10 rows = 1280
+// bytes apart (the descriptor's stride byte offset) and tap (dx, dy) is the window starting dy * 2560 + dx * 128 bytes into the
+// stage.  The start address is then not 1024-byte aligned; that is legal because the tensor core derives the 128-byte-swizzle
+// XOR from the address bits (7..9), exactly as TMA wrote the tile.  2 boxes (51 KB written, 32 KB read from the L2) per tile.
 // BatchNorm is folded into weights/bias on the host; the epilogue applies bias (+ residual) (+ ReLU) and writes bf16.
 //
-//   conv3x3_tc2_kernel<HALVES>  one layer per launch (the 19->128 input convolution, and the tower with AZ_TOWER_FUSED=0)
-//   conv_tower_kernel           the 20 tower layers in one persistent launch
+//   conv3x3_tc2_kernel<HALVES, KROW, WIDE>  one layer per launch (the 19->128 input convolution, and the tower with AZ_TOWER_FUSED=0)
+//   conv_tower_kernel<WIDE>                 the 20 tower layers in one persistent launch
 // The single-CTA first version (N = 64 per CTA, issue-bound) is described in profiles/r1_conv_ablation.md.
 #include "tc_conv.cuh"
 #include "nn_tc.h"
@@ -23,7 +28,6 @@
 
 namespace azb {
 
-constexpr int kStageBytes = 160 * 128;   // {10 ranks x 2 boards x 8 files} rows x 64 channels bf16
 constexpr int kWTileBytes = 64 * 128;    // 64 output channels x 64 input channels bf16
 
 // KROW = bytes per operand row in shared memory = input channels per K block x 2: 128 (64 channels, 128-byte swizzle) for the
@@ -131,8 +135,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
                     if (++stage == NS) { stage = 0; phase ^= 1; }
                 }
                 first = false;
-                continue;
-            }
+            } else {
             for (int half = 0; half < HALVES; half++)
                 for (int dxi = 0; dxi < 3; dxi++) {
                     if (first && elect_one()) {
@@ -154,6 +157,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
                     if (++stage == NS) { stage = 0; phase ^= 1; }
                 }
             first = false;
+            }
         }
     } else if (warp == 1) {
         if (rank == 0) {
@@ -197,10 +201,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
                         __syncwarp();
                         if (++stage == NS) { stage = 0; phase ^= 1; }
                     }
-                    if (elect_one()) umma2_commit_mc(&tfull_bar[acc]);
-                    __syncwarp();
-                    continue;
-                }
+                } else {
                 for (int half = 0; half < HALVES; half++)
                     for (int dxi = 0; dxi < 3; dxi++) {
                         mbar_wait(&full_bar[stage], phase, 13);
@@ -224,6 +225,7 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
                         __syncwarp();
                         if (++stage == NS) { stage = 0; phase ^= 1; }
                     }
+                }
                 if (elect_one()) umma2_commit_mc(&tfull_bar[acc]);
                 __syncwarp();
             }
