@@ -137,7 +137,7 @@ k_heads_tc(const __grid_constant__ CUtensorMap act_map, const __nv_bfloat16* __r
     float* s_hid = reinterpret_cast<float*>(smem + kOffExp);   // [2 K halves][32][64], value head only (the exp tiles are dead by then)
 
 #ifdef AZ_HTC_TIMING
-    long long tacc[16] = {}, tlast = clock64();
+    long long tacc[20] = {}, tlast = clock64();
     const long long tbegin = tlast;
 #endif
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -393,8 +393,10 @@ k_heads_tc(const __grid_constant__ CUtensorMap act_map, const __nv_bfloat16* __r
                 s4[i & 3] += ev;
             }
             float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+            HTC_T(16);
             for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
             if (lane == 0) red[4 + ti] = sum;
+            HTC_T(17);
             if (sc.edge_P) {
 #pragma unroll
                 for (int i = 0; i < 32; i++) se[(cg * 32 + i) * 64 + sq] = __uint_as_float(v[i]);
@@ -483,8 +485,8 @@ k_heads_tc(const __grid_constant__ CUtensorMap act_map, const __nv_bfloat16* __r
 #ifdef AZ_HTC_TIMING
     if (blockIdx.x == 0 && lane == 0 && (warp <= 2 || warp == 10)) {
         const long long tot = clock64() - tbegin;
-        printf("htc warp %d total %lld | setup %lld | p1 %lld p2 %lld p3 %lld p4 %lld p5 %lld p6 %lld p7 %lld p8 %lld p9 %lld p10 %lld p11 %lld p12 %lld p13 %lld p14 %lld p15 %lld\n", warp, tot,
-               tacc[0], tacc[1], tacc[2], tacc[3], tacc[4], tacc[5], tacc[6], tacc[7], tacc[8], tacc[9], tacc[10], tacc[11], tacc[12], tacc[13], tacc[14], tacc[15]);
+        printf("htc warp %d total %lld | setup %lld | p1 %lld p2 %lld p3 %lld p4 %lld p5 %lld p6 %lld p7 %lld p8 %lld p9 %lld p10 %lld p11 %lld p12 %lld p13 %lld p14 %lld p15 %lld | exp %lld shfl %lld\n", warp, tot,
+               tacc[0], tacc[1], tacc[2], tacc[3], tacc[4], tacc[5], tacc[6], tacc[7], tacc[8], tacc[9], tacc[10], tacc[11], tacc[12], tacc[13], tacc[14], tacc[15], tacc[16], tacc[17]);
     }
 #endif
     tc_fence_before();
