@@ -363,7 +363,8 @@ int net_forward_bf16(az_engine* e, const int* n_dev, int n_static, float* policy
     int r = 0;
     if (fused < 2) {
         e->n_launches += 1;
-        r = tc_conv3x3_launch(e->stream, &w->map_a_in, &w->map_w_in, w->in_ch, w->f_b_in, nullptr, w->a_buf[0], n_dev, n_static, 1, grid, rel ? 32 : 0);
+        r = tc_conv3x3_launch(e->stream, &w->map_a_in, &w->map_w_in, w->in_ch, w->f_b_in, nullptr, w->a_buf[0], n_dev, n_static, 1, grid,
+                              (rel ? 32 : 0) | ((e->knobs.tower_l2hint & 8) ? 512 : 0));
         if (r) return set_err(e, AZ_ERR_CUDA, "tc conv (input) launch failed");
     }
     if (sample) {
@@ -391,8 +392,8 @@ int net_forward_bf16(az_engine* e, const int* n_dev, int n_static, float* policy
         for (int lo = 0; lo < cap_tiles; lo += inkernel ? cap_tiles : per) {
             e->n_launches += 1;
             if (sample) e->prof_launches += 1;
-            r = inkernel ? tc_tower_launch(e->stream, w->d_maps, w->f_b_tower, act, n_dev, n_static, 20, fused >= 2, tgrid, 0, 0x7FFFFFFF, per, rel, wide)
-                         : tc_tower_launch(e->stream, w->d_maps, w->f_b_tower, act, n_dev, n_static, 20, fused >= 2, tgrid, lo, lo + per, 0, rel, wide);
+            r = inkernel ? tc_tower_launch(e->stream, w->d_maps, w->f_b_tower, act, n_dev, n_static, 20, fused >= 2, tgrid, 0, 0x7FFFFFFF, per, rel, wide, e->knobs.tower_l2hint)
+                         : tc_tower_launch(e->stream, w->d_maps, w->f_b_tower, act, n_dev, n_static, 20, fused >= 2, tgrid, lo, lo + per, 0, rel, wide, e->knobs.tower_l2hint);
             if (r) return set_err(e, AZ_ERR_CUDA, "tower launch failed");
         }
         x = 0;  // the fused tower works in place: block input and block output share a_buf[0], a_buf[1] holds conv1's output

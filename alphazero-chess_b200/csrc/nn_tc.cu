@@ -288,7 +288,8 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
                             __nv_bfloat162 pk = __floats2bfloat162_rn(x0, x1);
                             packed[j] = *reinterpret_cast<uint32_t*>(&pk);
                         }
-                        if (!(dbg & 16)) st_global_v8(out + off + chunk * 32 + v * 16, packed);
+                        if (dbg & 512) st_global_v8_hint(out + off + chunk * 32 + v * 16, packed, l2_policy_evict_last());
+                        else if (!(dbg & 16)) st_global_v8(out + off + chunk * 32 + v * 16, packed);
                         else if (packed[0] == 0x12345678u && packed[7] == 0x9abcdef0u) st_global_v8(out + off, packed);
                     }
                 }
@@ -319,6 +320,7 @@ struct TowerParams {
     int n_boards_static;
     int n_layers;              // 20
     int release_arrive;        // 1: hand accumulators back with a release arrive (AZ_TC_RELEASE_ARRIVE=1, the first version)
+    int l2_hint;               // AZ_TOWER_L2HINT: bit 0 = activation stores, bit 1 = residual loads, bit 2 = activation TMA loads carry L2::evict_last
     int tile_lo, tile_hi;      // this launch covers tiles [tile_lo, min(all tiles, tile_hi)) (a tile = 4 boards) ...
     int range_tiles;           // ... as consecutive ranges of this many tiles: all layers of one range, then the next range
     int stem;                  // 1: run the input convolution (agent.rs:117; 64 padded channels -> act[0]) as a first layer
@@ -425,7 +427,8 @@ conv_tower_kernel(const TowerParams prm) {
                         mbar_wait(&empty_bar[stage], phase ^ 1, 22);
                         if (elect_one()) {
                             if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);
-                            tma2_load_4d(a_sm + stage * kStageBytes, in_map, &full_bar[stage], half * 64, WIDE ? -1 : dxi - 1, t * 4 + (int)rank * 2, -1);
+                            if (prm.l2_hint & 4) tma2_load_4d_hint(a_sm + stage * kStageBytes, in_map, &full_bar[stage], half * 64, WIDE ? -1 : dxi - 1, t * 4 + (int)rank * 2, -1, l2_policy_evict_last());
+                            else tma2_load_4d(a_sm + stage * kStageBytes, in_map, &full_bar[stage], half * 64, WIDE ? -1 : dxi - 1, t * 4 + (int)rank * 2, -1);
                         }
                         __syncwarp();
                         if (++stage == NS) { stage = 0; phase ^= 1; }
@@ -498,6 +501,7 @@ conv_tower_kernel(const TowerParams prm) {
         const int h = row >> 4, b = (row >> 3) & 1, w = row & 7;
         int lt = 0, g = 0;
         uint32_t done = 0;
+        const uint64_t l2pol = l2_policy_evict_last();
         for (int rg = 0; rg < n_ranges; rg++) {
         TOWER_RANGE_BEGIN();
         // completion is published lazily (after the next accumulator wait) and only every 4th tile when the pair has
@@ -527,7 +531,10 @@ conv_tower_kernel(const TowerParams prm) {
                 uint32_t res[kEpiCols / 2];
                 if (has_res) {
 #pragma unroll
-                    for (int k = 0; k < kEpiCols / 16; k++) ld_global_v8(residual + off + k * 16, &res[k * 8]);
+                    for (int k = 0; k < kEpiCols / 16; k++) {
+                        if (prm.l2_hint & 2) ld_global_v8_hint(residual + off + k * 16, &res[k * 8], l2pol);
+                        else ld_global_v8(residual + off + k * 16, &res[k * 8]);
+                    }
                 }
                 mbar_wait(&tfull_bar[acc], accphase, 26);
                 tc_fence_after();
@@ -566,7 +573,8 @@ conv_tower_kernel(const TowerParams prm) {
                                 __nv_bfloat162 pk = __floats2bfloat162_rn(x0, x1);
                                 packed[j] = *reinterpret_cast<uint32_t*>(&pk);
                             }
-                            st_global_v8(out + off + chunk * 32 + v * 16, packed);
+                            if (prm.l2_hint & 1) st_global_v8_hint(out + off + chunk * 32 + v * 16, packed, l2pol);
+                            else st_global_v8(out + off + chunk * 32 + v * 16, packed);
                         }
                     }
                 }
@@ -592,7 +600,7 @@ conv_tower_kernel(const TowerParams prm) {
 
 int tc_tower_launch(cudaStream_t stream, const CUtensorMap* maps_dev, const float* bias, void* const* act, const int* n_boards_dev,
                     int n_boards_static, int n_layers, int stem, int grid, int tile_lo, int tile_hi, int range_tiles, int release_arrive,
-                    int wide) {
+                    int wide, int l2_hint) {
     static PerDeviceOnce once;
     if (once.first() &&
         (cudaFuncSetAttribute(conv_tower_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<2>::kTotal) != cudaSuccess ||
@@ -608,6 +616,7 @@ int tc_tower_launch(cudaStream_t stream, const CUtensorMap* maps_dev, const floa
     p.n_boards_ptr = n_boards_dev; p.n_boards_static = n_boards_static; p.n_layers = n_layers; p.stem = stem ? 1 : 0;
     p.tile_lo = tile_lo; p.tile_hi = tile_hi; p.range_tiles = range_tiles > 0 ? range_tiles : (1 << 30);
     p.release_arrive = release_arrive;
+    p.l2_hint = l2_hint;
     if (wide == 2) conv_tower_kernel<2><<<grid, kThreads2, ConvSmem<2, 128, 2>::kTotal, stream>>>(p);
     else if (wide) conv_tower_kernel<1><<<grid, kThreads2, ConvSmem<2, 128, 1>::kTotal, stream>>>(p);
     else conv_tower_kernel<0><<<grid, kThreads2, ConvSmem<2>::kTotal, stream>>>(p);

@@ -16,5 +16,5 @@ int tc_conv3x3_launch(cudaStream_t stream, const CUtensorMap* in_map, const CUte
 // the 20-layer residual tower in one persistent launch; maps_dev = device array {act0, act1, act2, w[0..19]}
 int tc_tower_launch(cudaStream_t stream, const CUtensorMap* maps_dev, const float* bias, void* const* act, const int* n_boards_dev,
                     int n_boards_static, int n_layers, int stem, int grid, int tile_lo = 0, int tile_hi = 0x7FFFFFFF, int range_tiles = 0,
-                    int release_arrive = 0, int wide = 0);   // wide: one 16-file box per channel half (maps_dev[25..27])
+                    int release_arrive = 0, int wide = 0, int l2_hint = 0);   // wide: one 16-file box per channel half (maps_dev[25..27])
 }  // namespace azb

@@ -166,4 +166,30 @@ __device__ __forceinline__ void st_global_v8(void* p, const uint32_t* r) {
                  : "memory");
 }
 
+// ---------------------------------------------------------------- L2 eviction-priority hints (AZ_TOWER_L2HINT)
+// The tower's activations are rewritten in place layer after layer; lines that stay in the L2 until they are overwritten never
+// reach HBM.  evict_last asks the L2 to keep them in preference to everything else that streams through.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void ld_global_v8_hint(const void* p, uint32_t* r, uint64_t pol) {
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8], %9;"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(p), "l"(pol));
+}
+__device__ __forceinline__ void st_global_v8_hint(void* p, const uint32_t* r, uint64_t pol) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8}, %9;"
+                 ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d_hint(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1),
+        "r"(c2), "r"(c3), "l"(pol)
+        : "memory");
+}
+
 }  // namespace azb
