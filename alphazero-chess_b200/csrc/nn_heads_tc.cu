@@ -494,8 +494,6 @@ k_heads_tc(const __grid_constant__ CUtensorMap act_map, const __nv_bfloat16* __r
     if (warp == 1) { tc_fence_after(); tmem1_dealloc(tmem_base, kTmemCols); }
 }
 
-int tc_make_rows_map(CUtensorMap* map, const void* base, int max_boards);   // nn_tc.cu
-
 int launch_heads_tc(az_engine* e, const CUtensorMap* act_map, const int* n_dev, int n_static, float* policy_out, float* value_out,
                     const HeadScatter* scatter) {
     NetWeights* w = e->net;
