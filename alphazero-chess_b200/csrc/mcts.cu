@@ -672,6 +672,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB * 4 / WARPS) k_advance(const 
     const uint2 path_spec = ptr.path[(size_t)g * prm.node_cap + min((int)(threadIdx.x & 31), prm.node_cap - 1)];
     Ctx x{prm, ptr, &shared[threadIdx.x >> 5], g, (int)(threadIdx.x & 31), (size_t)g * prm.node_cap, (size_t)g * prm.edge_cap,
           ptr.ctl[g], 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (g == 0 && x.lane == 0 && ptr.batch_zero) *ptr.batch_zero = 0;   // the other wave parity's request counter (see run_wave)
     if (x.c.status != 0 && x.c.status != 4) return;
     if (!prm.consume && x.c.pending_node >= 0) return;   // extra pass: this game already waits for the network
 
@@ -991,6 +992,8 @@ int search_create(az_engine* e) {
     cudaMemset(q.counters, 0, sizeof(Counters));
     cudaMemset(q.stats, 0, (size_t)STAT_STRIPES * STAT_WIDTH * sizeof(unsigned long long));
     cudaMemset(q.batch_count, 0, 32);
+    st->batch_base = q.batch_count;
+    q.batch_zero = nullptr;
     return 0;
 }
 
@@ -1036,7 +1039,11 @@ static int run_wave(az_engine* e, SearchState* st) {
     const int blocks = (st->prm.n_games + WARPS - 1) / WARPS;
     st->prm.priors_scattered = (e->stub_kind == 0 && e->cfg.precision != 1) ? 1 : 0;
     if (st->prm.mode == 1) st->prm.cache_epoch = (uint32_t)((st->wave_counter++ / (unsigned long long)std::max(st->prm.S, 1)) & 63);
-    AZ_CUDA(e, cudaMemsetAsync(st->ptr.batch_count, 0, sizeof(int), e->stream));
+    // Two request counters alternate between waves: this wave's k_advance counts into one and clears the other, which the
+    // previous wave's network kernels (complete by stream order) were the last to read -- no memset launch per wave.
+    st->batch_parity ^= 1;
+    st->ptr.batch_count = st->batch_base + st->batch_parity;
+    st->ptr.batch_zero = st->batch_base + (st->batch_parity ^ 1);
     if (e->prof_every > 0 && e->stub_kind == 0 && e->cfg.precision != 1 && (e->prof_counter % (uint64_t)e->prof_every) == 0 &&
         !e->prof_adv_event) {
         cudaEventCreate(&e->prof_adv_event);
@@ -1131,14 +1138,17 @@ int az_search(az_engine* e, int n, const az_position* roots, const az_position* 
         else AZ_CUDA(e, cudaMemsetAsync(d_plies, 0, (size_t)n * 4, e->stream));
     }
     const int blocks = (n + WARPS - 1) / WARPS;
-    AZ_CUDA(e, cudaMemsetAsync(run.ptr.batch_count, 0, 16, e->stream));
+    run.batch_parity = 0;
+    run.ptr.batch_count = run.batch_base;
+    run.ptr.batch_zero = nullptr;
+    AZ_CUDA(e, cudaMemsetAsync(run.batch_base, 0, 16, e->stream));
     e->n_launches++;
     k_init_search<<<blocks, WARPS * 32, 0, e->stream>>>(run.prm, run.ptr, e->d_wire, d_hist, e->d_hist_off, d_ids, d_plies);
     AZ_CUDA(e, cudaGetLastError());
     int r = evaluate_batch(e, &run);
     if (r) return r;
     // every wave completes at least one simulation per active game
-    int* d_flags = run.ptr.batch_count + 4;
+    int* d_flags = run.batch_base + 4;
     int rc = AZ_OK;
     for (int wave = 0;; wave++) {
         r = run_wave(e, &run);
@@ -1214,6 +1224,10 @@ int az_selfplay_begin_n(az_engine* e, int n_games, uint64_t first_game_id, uint6
         r = net_forward_bf16(e, nullptr, 1, e->d_policy, e->d_value);
     }
     if (r) return r;
+    st->batch_parity = 0;
+    q.batch_count = st->batch_base;
+    q.batch_zero = nullptr;
+    AZ_CUDA(e, cudaMemsetAsync(st->batch_base, 0, 8, e->stream));   // both request counters (run_wave alternates them)
     k_start_prior<<<1, 32, 0, e->stream>>>(e->d_policy, q.start_prior);
     const int blocks = (n_games + WARPS - 1) / WARPS;
     e->n_launches += 2;
@@ -1236,7 +1250,7 @@ int az_selfplay_step(az_engine* e, int waves, az_selfplay_stats* out) {
     Counters c;
     unsigned long long stripes[STAT_STRIPES * STAT_WIDTH];
     int flags[4] = {0, 0, 0, 0};
-    int* d_flags = st->ptr.batch_count + 4;
+    int* d_flags = st->batch_base + 4;
     AZ_CUDA(e, cudaMemsetAsync(d_flags, 0, 16, e->stream));
     k_count_active<<<(st->prm.n_games + 127) / 128, 128, 0, e->stream>>>(st->prm, st->ptr, d_flags);
     AZ_CUDA(e, cudaMemcpyAsync(flags, d_flags, 16, cudaMemcpyDeviceToHost, e->stream));

@@ -96,7 +96,8 @@ struct SearchPtrs {
     uint2* path;         // [G][node_cap]: x = node | edge << 16, y = the edge's index in the game's edge pool (saves backup a lookup)
     DPos* hist;          // [G][HIST_CAP]
     // evaluation requests / results
-    int* batch_count;
+    int* batch_count;          // this wave's request counter (one of two: run_wave alternates, see batch_zero)
+    int* batch_zero;           // the other counter: k_advance clears it for the next wave (no memset launch per wave); may be null
     DPos* req_pos;             // [max_batch]
     __nv_bfloat16* req_bf16;   // [max_batch][64][plane_ch]
     float* req_f32;            // [max_batch][19][64]
@@ -122,6 +123,8 @@ struct SearchState {
     unsigned long long cache_evictions = 0;
     unsigned long long sum_search_depth = 0;
     int adv_passes = 1;                    // k_advance launches per wave (AZ_ADV_PASSES, see run_wave)
+    int* batch_base = nullptr;             // [8] ints: two alternating request counters, then four flag words
+    int batch_parity = 0;
     unsigned long long wave_counter = 0;   // self-play waves since az_selfplay_begin (cache epoch = wave_counter / S)
     unsigned long long* d_noise_ids = nullptr;  // [max_games] az_search staging (no allocation per call)
     uint32_t* d_noise_plies = nullptr;
