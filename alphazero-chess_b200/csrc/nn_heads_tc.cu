@@ -105,7 +105,7 @@ __device__ __forceinline__ void htc_mma_16816(float* d, uint32_t a0, uint32_t a1
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-// -DAZ_HTC_TIMING (tools/htc_timing.sh): block 0 prints the clocks its first epilogue warp, the MMA warp and the TMA warp spent per phase
+// -DAZ_HTC_TIMING (tools/htc_timing.sh): block 0 prints the clocks the first warp of each epilogue group, the MMA warp and the TMA warp spent per phase
 #ifdef AZ_HTC_TIMING
 #define HTC_T(i) do { const long long now_ = clock64(); tacc[i] += now_ - tlast; tlast = now_; } while (0)
 #else
@@ -124,9 +124,9 @@ k_heads_tc(const __grid_constant__ CUtensorMap act_map, const __nv_bfloat16* __r
     uint64_t* a_full = reinterpret_cast<uint64_t*>(misc);   // [kStages]   TMA bytes landed
     uint64_t* a_empty = a_full + kStages;                   // [kStages]   stage 1 MMAs of the tile have read the stage
     uint64_t* d1_full = a_empty + kStages;                  // [2]         per epilogue group: D1 complete
-    uint64_t* p1_ready = d1_full + 2;                       // [2]         D1 read out and P1 in shared memory (4 warp arrivals)
+    uint64_t* p1_ready = d1_full + 2;                       // [2]         D1 read out and P1 in shared memory (8 warp arrivals)
     uint64_t* d2_full = p1_ready + 2;                       // [2][2]      per group and D2 slot
-    uint64_t* d2_free = d2_full + 4;                        // [2][2]      D2 slot read out (4 warp arrivals)
+    uint64_t* d2_free = d2_full + 4;                        // [2][2]      D2 slot read out (8 warp arrivals)
     uint64_t* wl1_full = d2_free + 4;                       // value head: fc1 weights staged into the (then idle) activation ring
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(wl1_full + 1);
     float* s_b40 = reinterpret_cast<float*>(misc + 160);    // [40]
