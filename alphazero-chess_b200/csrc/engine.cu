@@ -121,6 +121,7 @@ int az_engine_create(const az_config* cfg, az_engine** out) {
         e->knobs.tower_grid = std::max(0, env_int("AZ_TOWER_GRID", 0));
         e->knobs.tower_wide = std::min(2, std::max(0, env_int("AZ_TOWER_WIDE", 2)));
         e->knobs.tower_l2hint = env_int("AZ_TOWER_L2HINT", 1) & 15;
+        e->knobs.input_epi2 = env_int("AZ_INPUT_EPI2", 0) ? 1 : 0;
         e->knobs.heads_tc = env_int("AZ_HEADS_TC", 1) ? 1 : 0;
         e->knobs.input_k32 = env_int("AZ_INPUT_K32", 1) ? 1 : 0;
     }

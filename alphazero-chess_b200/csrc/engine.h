@@ -77,6 +77,7 @@ struct az_engine {
         int tower_grid = 0;        // AZ_TOWER_GRID (0: every SM; the SM-partition experiment of profiles/)
         int tower_wide = 2;        // AZ_TOWER_WIDE: ONE TMA box per channel half serves the three horizontal taps of the tower; 2 (default) = 10-file boxes, three stages; 1 = 16-file boxes, two stages; 0 = one 8-file box per tap (round 1)
         int tower_l2hint = 1;      // AZ_TOWER_L2HINT (default 1): L2::evict_last on the tower's activation stores (1), residual loads (2), TMA loads (4)
+        int input_epi2 = 0;        // AZ_INPUT_EPI2: the input convolution runs two sets of epilogue warps on alternate tiles
         int heads_tc = 1;          // AZ_HEADS_TC (default 1): policy/value heads on tcgen05 (nn_heads_tc.cu); 0 = warp-level mma.sync kernel (nn_heads.cu)
         int input_k32 = 1;         // AZ_INPUT_K32 (default 1): 32-channel plane layout (K padded to 32 instead of 64 in the input convolution); 0 = 64 channels
     } knobs;

@@ -364,7 +364,7 @@ int net_forward_bf16(az_engine* e, const int* n_dev, int n_static, float* policy
     if (fused < 2) {
         e->n_launches += 1;
         r = tc_conv3x3_launch(e->stream, &w->map_a_in, &w->map_w_in, w->in_ch, w->f_b_in, nullptr, w->a_buf[0], n_dev, n_static, 1, grid,
-                              (rel ? 32 : 0) | ((e->knobs.tower_l2hint & 8) ? 512 : 0));
+                              (rel ? 32 : 0) | ((e->knobs.tower_l2hint & 8) ? 512 : 0) | (e->knobs.input_epi2 ? 1024 : 0));
         if (r) return set_err(e, AZ_ERR_CUDA, "tc conv (input) launch failed");
     }
     if (sample) {

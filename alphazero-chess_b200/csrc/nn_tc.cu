@@ -68,8 +68,11 @@ constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreads2 = 64 + kEpiThreads;   // warp 0 TMA, warp 1 MMA/TMEM, then the epilogue warps
 static_assert(kEpiWarps == 8 || kEpiWarps == 16, "epilogue warps: 8 or 16");
 
-template <int HALVES, int KROW, int WIDE = 0>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1)
+// GROUPS = 2 (the input convolution): two sets of epilogue warps take alternate tiles (set g always drains TMEM buffer g), so the
+// epilogues of consecutive tiles overlap in time.  The layer is bound by the latency of one tile's epilogue (wait, tcgen05.ld,
+// bias / ReLU / pack, stores), not by its width, which is why splitting one tile over 16 warps did not help (profiles/r2_ab.md 4).
+template <int HALVES, int KROW, int WIDE = 0, int GROUPS = 1>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + GROUPS * kEpiThreads, 1)
 conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap w_map,
                    const float* __restrict__ bias, const __nv_bfloat16* __restrict__ residual,
                    __nv_bfloat16* __restrict__ out, const int* __restrict__ n_boards_ptr, int n_boards_static, int relu, int dbg) {
@@ -233,11 +236,13 @@ conv3x3_tc2_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
     } else {
         // ------------------------------------------------ epilogue (TMEM lane quarter q, column group cg of kEpiCols columns)
         const int q = warp & 3;
-        const int cg = (warp - 2) >> 2;
+        const int egrp = (warp - 2) / kEpiWarps;            // epilogue set (GROUPS = 2: alternate tiles)
+        const int cg = ((warp - 2) % kEpiWarps) >> 2;
         const int row = q * 32 + lane;
         const int h = row >> 4, b = (row >> 3) & 1, w = row & 7;
         int lt = 0;
         for (int t = first_tile; t < n_tiles; t += tile_step, lt++) {
+            if (GROUPS == 2 && (lt & 1) != egrp) continue;
             const int acc = lt & 1; const uint32_t accphase = (lt >> 1) & 1;
             const int board = t * 4 + (int)rank * 2 + b;
             const bool valid = board < n_boards;
@@ -692,13 +697,17 @@ int tc_conv3x3_launch(cudaStream_t stream, const CUtensorMap* in_map, const CUte
         cudaError_t e4 = cudaFuncSetAttribute(conv3x3_tc2_kernel<2, 128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<2, 128, 1>::kTotal);
         cudaError_t e5 = cudaFuncSetAttribute(conv3x3_tc2_kernel<2, 128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<2, 128, 2>::kTotal);
         cudaError_t e6 = cudaFuncSetAttribute(conv3x3_tc2_kernel<1, 64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<1, 64, 2>::kTotal);
-        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess || e5 != cudaSuccess || e6 != cudaSuccess) return -2;
+        cudaError_t e7 = cudaFuncSetAttribute(conv3x3_tc2_kernel<1, 64, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvSmem<1, 64>::kTotal);
+        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess || e5 != cudaSuccess || e6 != cudaSuccess || e7 != cudaSuccess) return -2;
     }
     if (grid <= 0) grid = 148;
     grid &= ~1;  // CTA pairs
     if (cin == 32 && (dbg & 256))   // 10-file boxes: in_map must have been made with wide = 2
         conv3x3_tc2_kernel<1, 64, 2><<<grid, kThreads2, ConvSmem<1, 64, 2>::kTotal, stream>>>(*in_map, *w_map, bias, (const __nv_bfloat16*)residual,
                                                                                             (__nv_bfloat16*)out, n_boards_dev, n_boards_static, relu, dbg);
+    else if (cin == 32 && (dbg & 1024))   // two epilogue sets on alternate tiles
+        conv3x3_tc2_kernel<1, 64, 0, 2><<<grid, 64 + 2 * kEpiThreads, ConvSmem<1, 64>::kTotal, stream>>>(*in_map, *w_map, bias, (const __nv_bfloat16*)residual,
+                                                                                                  (__nv_bfloat16*)out, n_boards_dev, n_boards_static, relu, dbg);
     else if (cin == 32)
         conv3x3_tc2_kernel<1, 64><<<grid, kThreads2, ConvSmem<1, 64>::kTotal, stream>>>(*in_map, *w_map, bias, (const __nv_bfloat16*)residual,
                                                                                        (__nv_bfloat16*)out, n_boards_dev, n_boards_static, relu, dbg);
